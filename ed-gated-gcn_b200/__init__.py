@@ -1,1 +1,8 @@
 """B200-native gated-GCN hot path."""
+
+from .gcn import GraphConvolution, gcn_layer            # noqa: F401
+from .gated import GatedGCNStack, StackOutput, GATE_ARCHS  # noqa: F401
+from .graph import DepGraph, build_graph, graph_from_dense, tree_distance  # noqa: F401
+
+__all__ = ["GraphConvolution", "gcn_layer", "GatedGCNStack", "StackOutput", "GATE_ARCHS", "DepGraph",
+           "build_graph", "graph_from_dense", "tree_distance"]

@@ -1,0 +1,109 @@
+"""ctypes binding of ``csrc/libedgcn.so`` (the C ABI declared in ``include/edgcn.h``).
+
+There is no CPU or eager-PyTorch fallback: if the shared library is missing, or a
+tensor is not on a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libedgcn.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_SIGMOID, ACT_RELU = 0, 1, 2
+PAD_MAX_PLUS_1, PAD_ZERO = 0, 1
+DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
+
+_P, _I, _L, _Z, _F = c_void_p, c_int32, c_int64, c_size_t, c_float
+
+# name -> (restype, argtypes); mirrors include/edgcn.h one to one
+SIGNATURES = {
+    "edg_version": (c_int, []),
+    "edg_strerror": (c_char_p, [c_int]),
+    "edg_last_cuda_error": (c_char_p, []),
+    "edg_csr_from_heads": (c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "edg_csr_from_dense_count": (c_int, [_P, c_int, _I, _I, _L, _L, _L, _P, _P, _P]),
+    "edg_csr_from_dense_fill": (c_int, [_P, c_int, _I, _I, _L, _L, _L, _P, _P, _P]),
+    "edg_tree_dist": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "edg_dist_pad": (c_int, [_P, _P, _I, _I, c_int, _P, _P]),
+    "edg_aggregate": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, _P, c_int, _P]),
+    "edg_linear": (c_int, [_P, c_int, _L, _I, _I, _P, _L, _I, _P, c_int, _P, c_int, _L, _P]),
+    "edg_wgrad_workspace": (_Z, [_I, _I, _I, c_int]),
+    "edg_wgrad": (c_int, [_P, _L, _I, _P, _L, _I, c_int, _I, _P, _L, _P, c_int, c_int, _P, _Z, _P]),
+    "edg_cast_2d": (c_int, [_P, _L, _I, _I, _P, c_int, _L, c_int, _P]),
+    "edg_trigger_gather": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _P, _P, _L, c_int, _P]),
+    "edg_trigger_scatter_add": (c_int, [_P, _I, _I, _P, _P, _P, c_int, _L, _P]),
+    "edg_pool_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _I, _P, _P, _P]),
+    "edg_diversity_fwd": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
+    "edg_views_bwd": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _L, _P, c_int, _P]),
+    "edg_scores_kl_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "edg_head_bwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _L,
+                             _P, _L, _P, _P, _P, _I, _P]),
+    "edg_gate_rows": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, c_int, _L, _P]),
+    "edg_sigmoid_bwd": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, c_int, _L, _P]),
+    "edg_sum_scaled": (c_int, [_P, _L, _F, _P, _P]),
+    "edg_colsum_workspace": (_Z, [_I, _I]),
+    "edg_colsum": (c_int, [_P, c_int, _L, _I, _I, _P, c_int, _P, _Z, _P]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree shared library and attach the prototypes."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class EdgError(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        lib = load()
+        msg = lib.edg_strerror(rc).decode()
+        if rc == -6:
+            msg += ": " + lib.edg_last_cuda_error().decode()
+        raise EdgError(f"libedgcn status {rc}: {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EdgError("libedgcn takes CUDA tensors only (there is no CPU path)")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t_or_dtype) -> int:
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    try:
+        return DTYPES[d]
+    except KeyError:
+        raise EdgError(f"unsupported dtype {d}: the path computes in float32 or bfloat16") from None

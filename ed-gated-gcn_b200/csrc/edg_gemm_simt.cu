@@ -1,0 +1,257 @@
+// FFMA GEMMs of the fp32-parity mode (SURVEY hard part 1: single-pass TF32 misses the
+// 1e-5 bar, so the fp32 mode stays on the fp32 pipe).  Also instantiated for bf16 inputs as
+// the known-good cross-check of the tcgen05 kernels in the GPU tests.
+//   linear: C[M,Nout] = act(A[M,K] * W[Nout,K]^T + bias)
+//   wgrad : P[s][K1,K2] = sum_{r in split s} A[r,K1]^T B[r,K2]  (+ deterministic split reduce)
+#include "edg_common.cuh"
+
+namespace edg {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, int64_t valid, float (&f)[4]) {
+  // up to 4 consecutive elements, zero-filled past `valid`
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = (i < valid) ? to_f32(p[i]) : 0.f;
+}
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, int64_t valid, float (&f)[4]) {
+  if (valid >= 4 && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = (i < valid) ? p[i] : 0.f;
+  }
+}
+
+template <typename TA, typename TC>
+__global__ void __launch_bounds__(256)
+linear_simt_kernel(const TA* __restrict__ A, int64_t lda, int M, int K, const TA* __restrict__ W, int64_t ldw,
+                   int Nout, const float* __restrict__ bias, int act, TC* __restrict__ C, int64_t ldc) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Ws[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;      // loader: row 0..63, k offset 0,4,8,12
+  const int ty = tid >> 4, tx = tid & 15;           // compute: 4x4 micro tile
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    float a[4], w[4];
+    const int kk = k0 + lk;
+    const int am = m0 + lr, wn = n0 + lr;
+    if (am < M) load4<TA>(A + (int64_t)am * lda + kk, (int64_t)K - kk, a);
+    else a[0] = a[1] = a[2] = a[3] = 0.f;
+    if (wn < Nout) load4<TA>(W + (int64_t)wn * ldw + kk, (int64_t)K - kk, w);
+    else w[0] = w[1] = w[2] = w[3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { As[lk + i][lr] = a[i]; Ws[lk + i][lr] = w[i]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= Nout) {
+        if (n < ldc) C[(int64_t)m * ldc + n] = from_f32<TC>(0.f);   // keep row padding zero
+        continue;
+      }
+      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+      if (act == EDG_ACT_SIGMOID) v = sigmoidf_(v);
+      else if (act == EDG_ACT_RELU) v = fmaxf(v, 0.f);
+      C[(int64_t)m * ldc + n] = from_f32<TC>(v);
+    }
+  }
+}
+
+// partial[z][K1,K2] over rows [z*rows_per, ...)
+template <typename T>
+__global__ void __launch_bounds__(256)
+wgrad_simt_kernel(const T* __restrict__ A, int64_t lda, int K1, const T* __restrict__ B, int64_t ldb, int K2,
+                  int R, int rows_per, float* __restrict__ partial) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int r_beg = blockIdx.z * rows_per, r_end = min(R, r_beg + rows_per);
+  const int lr = tid >> 4, lc = (tid & 15) * 4;     // loader: r 0..15, col offset 0..60
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int r0 = r_beg; r0 < r_end; r0 += TK) {
+    const int r = r0 + lr;
+    float a[4], b[4];
+    if (r < r_end) {
+      load4<T>(A + (int64_t)r * lda + m0 + lc, (int64_t)K1 - (m0 + lc), a);
+      load4<T>(B + (int64_t)r * ldb + n0 + lc, (int64_t)K2 - (n0 + lc), b);
+    } else {
+      a[0] = a[1] = a[2] = a[3] = 0.f;
+      b[0] = b[1] = b[2] = b[3] = 0.f;
+    }
+    *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(&Bs[lr][lc]) = make_float4(b[0], b[1], b[2], b[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* P = partial + (int64_t)blockIdx.z * K1 * K2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= K1) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < K2) P[(int64_t)m * K2 + n] = acc[i][j];
+    }
+  }
+}
+
+// dW[m, n] (+)= sum_z partial[z][m*K2+n]   (fixed order -> deterministic)
+__global__ void split_reduce_kernel(const float* __restrict__ partial, int splits, int K1, int K2,
+                                    float* __restrict__ dW, int64_t lddw, int accumulate) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = (int64_t)K1 * K2;
+  if (idx >= tot) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * tot + idx];
+  const int m = (int)(idx / K2), n = (int)(idx - (int64_t)m * K2);
+  float* o = dW + (int64_t)m * lddw + n;
+  *o = accumulate ? (*o + s) : s;
+}
+
+// ---- column sums ------------------------------------------------------------
+constexpr int kColsumRowsPer = 1024;
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int64_t ldx, int R, int C, float* __restrict__ partial) {
+  // block = 32 columns x 8 row lanes; grid.y = row chunk
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const int r_beg = blockIdx.y * kColsumRowsPer, r_end = min(R, r_beg + kColsumRowsPer);
+  float s = 0.f;
+  if (c < C)
+    for (int r = r_beg + ry; r < r_end; r += 8) s += to_f32(x[(int64_t)r * ldx + c]);
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    partial[(int64_t)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += partial[(int64_t)k * C + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+void launch_split_reduce(const float* partial, int splits, int K1, int K2, float* dW, int64_t lddw, int accumulate,
+                         cudaStream_t s) {
+  const int64_t tot = (int64_t)K1 * K2;
+  split_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(partial, splits, K1, K2, dW, lddw, accumulate);
+}
+
+int wgrad_splits(int R, int K1, int K2) {
+  const int tiles = ((K1 + TM - 1) / TM) * ((K2 + TN - 1) / TN);
+  int want = (4 * kNumSMs + tiles - 1) / tiles;
+  int maxs = (R + 255) / 256;          // at least 256 rows per split
+  int s = want < maxs ? want : maxs;
+  return s < 1 ? 1 : s;
+}
+
+template <typename TA>
+int launch_linear_simt(const void* A, int64_t lda, int M, int K, const void* W, int64_t ldw, int Nout,
+                       const float* bias, int act, void* C, int c_dtype, int64_t ldc, cudaStream_t s) {
+  const int ncols = (int)(ldc < (int64_t)Nout + 16 ? ldc : Nout);       // also covers the padding columns
+  dim3 grid((ncols + TN - 1) / TN, (M + TM - 1) / TM);
+  if (grid.y > 65535) return EDG_ERR_UNSUPPORTED;
+  if (c_dtype == EDG_F32)
+    linear_simt_kernel<TA, float><<<grid, 256, 0, s>>>((const TA*)A, lda, M, K, (const TA*)W, ldw, Nout, bias, act, (float*)C, ldc);
+  else
+    linear_simt_kernel<TA, __nv_bfloat16><<<grid, 256, 0, s>>>((const TA*)A, lda, M, K, (const TA*)W, ldw, Nout, bias, act, (__nv_bfloat16*)C, ldc);
+  return check_launch();
+}
+template int launch_linear_simt<float>(const void*, int64_t, int, int, const void*, int64_t, int, const float*, int, void*, int, int64_t, cudaStream_t);
+template int launch_linear_simt<__nv_bfloat16>(const void*, int64_t, int, int, const void*, int64_t, int, const float*, int, void*, int, int64_t, cudaStream_t);
+
+template <typename T>
+int launch_wgrad_simt(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R,
+                      float* dW, int64_t lddw, int accumulate, float* ws, cudaStream_t s) {
+  const int splits = wgrad_splits(R, K1, K2);
+  int rows_per = (R + splits - 1) / splits;
+  rows_per = ((rows_per + TK - 1) / TK) * TK;
+  dim3 grid((K2 + TN - 1) / TN, (K1 + TM - 1) / TM, splits);
+  wgrad_simt_kernel<T><<<grid, 256, 0, s>>>((const T*)A, lda, K1, (const T*)B, ldb, K2, R, rows_per, ws);
+  launch_split_reduce(ws, splits, K1, K2, dW, lddw, accumulate, s);
+  return check_launch();
+}
+size_t wgrad_simt_workspace(int R, int K1, int K2) { return (size_t)wgrad_splits(R, K1, K2) * K1 * K2 * sizeof(float); }
+template int launch_wgrad_simt<float>(const void*, int64_t, int, const void*, int64_t, int, int, float*, int64_t, int, float*, cudaStream_t);
+template int launch_wgrad_simt<__nv_bfloat16>(const void*, int64_t, int, const void*, int64_t, int, int, float*, int64_t, int, float*, cudaStream_t);
+
+}  // namespace edg
+
+using namespace edg;
+
+extern "C" size_t edg_colsum_workspace(int32_t R, int32_t C) {
+  if (R <= 0 || C <= 0) return 0;
+  return (size_t)((R + kColsumRowsPer - 1) / kColsumRowsPer) * C * sizeof(float);
+}
+
+extern "C" int edg_colsum(const void* x, int dtype, int64_t ldx, int32_t R, int32_t C, float* out,
+                          int accumulate, void* ws, size_t ws_bytes, edg_stream stream) {
+  if (R < 0 || C <= 0 || !out) return EDG_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (R == 0) {
+    if (!accumulate) cudaMemsetAsync(out, 0, C * sizeof(float), s);
+    return check_launch();
+  }
+  if (!x || !ws) return EDG_ERR_ARG;
+  if (ws_bytes < edg_colsum_workspace(R, C)) return EDG_ERR_WORKSPACE;
+  const int chunks = (R + kColsumRowsPer - 1) / kColsumRowsPer;
+  dim3 grid((C + 31) / 32, chunks);
+  if (chunks > 65535) return EDG_ERR_UNSUPPORTED;
+  if (dtype == EDG_BF16)
+    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, R, C, (float*)ws);
+  else if (dtype == EDG_F32)
+    colsum_partial_kernel<float><<<grid, 256, 0, s>>>((const float*)x, ldx, R, C, (float*)ws);
+  else return EDG_ERR_DTYPE;
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, s>>>((const float*)ws, chunks, C, out, accumulate);
+  return check_launch();
+}

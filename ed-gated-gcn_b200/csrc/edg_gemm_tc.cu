@@ -1,0 +1,509 @@
+// tcgen05 (5th-gen tensor core) GEMMs for the bf16 mode -- sm_100a only.
+//
+//   linear_tc : C[M,Nout] = act(A[M,K] * W[Nout,K]^T + bias)     (K-major A and B, TMA-fed)
+//   wgrad_tc  : P[s][K1,K2] = A[rows_s,K1]^T * B[rows_s,K2]       (MN-major A and B, split over rows)
+//
+// Structure of both (one CTA per SM, 192 threads):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulators in TMEM)
+//   warps 2..5  : epilogue       (tcgen05.ld -> bias/activation -> global), one TMEM lane quarter each
+// linear_tc is persistent over (m,n) tiles with two TMEM accumulator stages, so the epilogue
+// of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "edg_common.cuh"
+
+namespace edg {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every MMA issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread `lane` gets row (lane quarter base + lane).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version = 1):
+//   [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 |
+//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> fp32.
+static inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                         // c_format  = F32
+  d |= 1u << 7;                         // a_format  = BF16
+  d |= 1u << 10;                        // b_format  = BF16
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// common tile constants
+// ---------------------------------------------------------------------------------------------
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // 64 bf16 = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+constexpr int kBBytesMax = 256 * kBlockK * 2;     // 32 KB
+constexpr int kStageBytes = kABytes + kBBytesMax; // 48 KB
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;                   // TMEM columns per accumulator stage
+constexpr int kThreads = 192;
+constexpr int kMaxBias = 1024;
+constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kMaxBias * sizeof(float) + 256;
+
+struct SmemLayout {
+  uint32_t base;       // 1024-aligned shared address of stage 0
+  __device__ uint32_t a(int s) const { return base + s * kStageBytes; }
+  __device__ uint32_t b(int s) const { return base + s * kStageBytes + kABytes; }
+  __device__ uint32_t bias() const { return base + kStages * kStageBytes; }
+  __device__ uint32_t bars() const { return bias() + kMaxBias * sizeof(float); }
+  __device__ uint32_t full(int s) const { return bars() + 8 * s; }
+  __device__ uint32_t empty(int s) const { return bars() + 8 * (kStages + s); }
+  __device__ uint32_t tfull(int s) const { return bars() + 8 * (2 * kStages + s); }
+  __device__ uint32_t tempty(int s) const { return bars() + 8 * (2 * kStages + 2 + s); }
+  __device__ uint32_t tmem_slot() const { return bars() + 8 * (2 * kStages + 4); }
+};
+
+template <typename TC> struct OutVec;
+template <> struct OutVec<float> {
+  static constexpr int G = 4;
+  __device__ static __forceinline__ void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct OutVec<__nv_bfloat16> {
+  static constexpr int G = 8;
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// linear_tc
+// ---------------------------------------------------------------------------------------------
+template <typename TC>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 int M, int K, int Nout, int block_n, int n_tiles, int num_tiles, uint32_t idesc,
+                 const float* __restrict__ bias, int act, TC* __restrict__ C, int64_t ldc) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemLayout L;
+  L.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (L.bias() - smem_u32(smem_raw)));
+
+  for (int i = threadIdx.x; i < Nout && i < kMaxBias; i += kThreads) bias_s[i] = bias ? bias[i] : 0.f;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < kStages; ++s) { mbar_init(L.full(s), 1); mbar_init(L.empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull(s), 1); mbar_init(L.tempty(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(L.tmem_slot(), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(L.tmem_slot()));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t stage_tx = kABytes + (uint32_t)block_n * kBlockK * 2;
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * block_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(L.empty(stage), phase ^ 1);
+          mbar_expect_tx(L.full(stage), stage_tx);
+          tma_load_2d(L.a(stage), &map_a, L.full(stage), kb * kBlockK, m0);
+          tma_load_2d(L.b(stage), &map_w, L.full(stage), kb * kBlockK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(L.tempty(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(L.full(stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t ad = make_desc_sw128(L.a(stage) + k * 32, 16, 1024);
+            const uint64_t bd = make_desc_sw128(L.b(stage) + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(L.empty(stage));           // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(L.tfull(as));                // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * block_n;
+      mbar_wait(L.tfull(as), aphase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      TC* crow = C + (int64_t)row * ldc;
+      for (int c0 = 0; c0 < block_n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride + c0, r);
+        if (row < M) {
+          constexpr int G = OutVec<TC>::G;
+#pragma unroll
+          for (int g = 0; g < 32; g += G) {
+            const int col = n0 + c0 + g;
+            if (c0 + g < block_n && col + G <= ldc) {
+              float v[G];
+#pragma unroll
+              for (int j = 0; j < G; ++j) {
+                float x = __uint_as_float(r[g + j]);
+                const int cj = col + j;
+                if (cj < Nout) {
+                  x += bias_s[cj < kMaxBias ? cj : 0];
+                  if (act == EDG_ACT_SIGMOID) x = sigmoidf_(x);
+                  else if (act == EDG_ACT_RELU) x = fmaxf(x, 0.f);
+                } else {
+                  x = 0.f;                       // keep the row padding finite and zero
+                }
+                v[j] = x;
+              }
+              OutVec<TC>::store(crow + col, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(L.tempty(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad_tc : both operands MN-major (rows of the activation matrices are the GEMM K dimension)
+//   smem stage = 64 activation rows; A = 2 boxes [64 rows x 64 cols], B = block_n/64 such boxes.
+//   canonical MN-major SWIZZLE_128B layout: 64-column atom contiguous (128 B), 8-row groups
+//   1024 B apart (SBO), next 64-column atom one box (8192 B) further (LBO).
+// ---------------------------------------------------------------------------------------------
+constexpr int kBoxBytes = 64 * 64 * 2;   // 8 KB
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                int R, int K1, int K2, int block_n, int rows_per, uint32_t idesc, float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemLayout L;
+  L.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * block_n;
+  const int r_beg = blockIdx.z * rows_per;
+  const int r_end = min(R, r_beg + rows_per);
+  const int num_kb = (r_end > r_beg) ? (r_end - r_beg + kBlockK - 1) / kBlockK : 0;
+  const int n_boxes = block_n / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages; ++s) { mbar_init(L.full(s), 1); mbar_init(L.empty(s), 1); }
+    mbar_init(L.tfull(0), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(L.tmem_slot(), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(L.tmem_slot()));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t stage_tx = (uint32_t)(2 + n_boxes) * kBoxBytes;
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(L.empty(stage), phase ^ 1);
+        mbar_expect_tx(L.full(stage), stage_tx);
+        const int r0 = r_beg + kb * kBlockK;
+        tma_load_2d(L.a(stage), &map_a, L.full(stage), m0, r0);
+        tma_load_2d(L.a(stage) + kBoxBytes, &map_a, L.full(stage), m0 + 64, r0);
+        for (int j = 0; j < n_boxes; ++j)
+          tma_load_2d(L.b(stage) + j * kBoxBytes, &map_b, L.full(stage), n0 + 64 * j, r0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(L.full(stage), phase);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t ad = make_desc_sw128(L.a(stage) + k * 2048, kBoxBytes, 1024);
+          const uint64_t bd = make_desc_sw128(L.b(stage) + k * 2048, kBoxBytes, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+        }
+        umma_commit(L.empty(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(L.tfull(0));
+    }
+  } else {
+    const int q = warp & 3;
+    float* P = partial + (int64_t)blockIdx.z * K1 * K2;
+    const int row = m0 + q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(L.tfull(0), 0);
+      tc_fence_after();
+    }
+    for (int c0 = 0; c0 < block_n; c0 += 32) {
+      uint32_t r[32];
+      if (num_kb > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+      if (row < K1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col < K2) P[(int64_t)row * K2 + col] = (num_kb > 0) ? __uint_as_float(r[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;      // resolved once; the pointer is process-wide and immutable
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (pitch ld elements), box = [box_rows, box_cols], 128B swizzle, OOB -> 0
+static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                         int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return EDG_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EDG_OK : EDG_ERR_CUDA;
+}
+
+static int pick_block_n(int Nout, int granule, int* n_tiles) {
+  int nt = (Nout + 255) / 256;
+  int bn = (Nout + nt - 1) / nt;
+  bn = ((bn + granule - 1) / granule) * granule;
+  if (bn > 256) { ++nt; bn = (((Nout + nt - 1) / nt) + granule - 1) / granule * granule; }
+  *n_tiles = (Nout + bn - 1) / bn;
+  return bn;
+}
+
+template <typename TC>
+static int launch_linear_tc_t(const CUtensorMap& ma, const CUtensorMap& mw, int M, int K, int Nout, int block_n,
+                              int n_tiles, const float* bias, int act, void* C, int64_t ldc, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(linear_tc_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int num_tiles = m_tiles * n_tiles;
+  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  const uint32_t idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
+  linear_tc_kernel<TC><<<grid, kThreads, kSmemBytes, s>>>(ma, mw, M, K, Nout, block_n, n_tiles, num_tiles, idesc,
+                                                          bias, act, (TC*)C, ldc);
+  return check_launch();
+}
+
+int launch_linear_tc(const void* A, int64_t lda, int M, int K, const void* W, int64_t ldw, int Nout,
+                     const float* bias, int act, void* C, int c_dtype, int64_t ldc, cudaStream_t s) {
+  if (Nout > kMaxBias) return EDG_ERR_UNSUPPORTED;
+  int n_tiles = 1;
+  const int block_n = pick_block_n(Nout, 16, &n_tiles);
+  CUtensorMap ma, mw;
+  int rc = make_map_bf16(&ma, A, M, K, lda, kBlockK, kBlockM);
+  if (rc) return rc;
+  rc = make_map_bf16(&mw, W, Nout, K, ldw, kBlockK, block_n);
+  if (rc) return rc;
+  if (c_dtype == EDG_F32) return launch_linear_tc_t<float>(ma, mw, M, K, Nout, block_n, n_tiles, bias, act, C, ldc, s);
+  if (c_dtype == EDG_BF16) return launch_linear_tc_t<__nv_bfloat16>(ma, mw, M, K, Nout, block_n, n_tiles, bias, act, C, ldc, s);
+  return EDG_ERR_DTYPE;
+}
+
+struct WgradPlan { int block_n, n_tiles, m_tiles, splits, rows_per; };
+static WgradPlan plan_wgrad_tc(int R, int K1, int K2) {
+  WgradPlan p;
+  p.block_n = pick_block_n(K2, 64, &p.n_tiles);
+  p.m_tiles = (K1 + kBlockM - 1) / kBlockM;
+  const int tiles = p.m_tiles * p.n_tiles;
+  int want = (kNumSMs + tiles - 1) / tiles;
+  int maxs = (R + 4 * kBlockK - 1) / (4 * kBlockK);
+  p.splits = want < maxs ? want : maxs;
+  if (p.splits < 1) p.splits = 1;
+  p.rows_per = (((R + p.splits - 1) / p.splits) + kBlockK - 1) / kBlockK * kBlockK;
+  p.splits = (R + p.rows_per - 1) / p.rows_per;
+  if (p.splits < 1) p.splits = 1;
+  return p;
+}
+size_t wgrad_tc_workspace(int R, int K1, int K2) {
+  WgradPlan p = plan_wgrad_tc(R, K1, K2);
+  return (size_t)p.splits * K1 * K2 * sizeof(float);
+}
+
+// defined in edg_gemm_simt.cu
+void launch_split_reduce(const float* partial, int splits, int K1, int K2, float* dW, int64_t lddw, int accumulate,
+                         cudaStream_t s);
+
+int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, float* dW,
+                    int64_t lddw, int accumulate, float* ws, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  WgradPlan p = plan_wgrad_tc(R, K1, K2);
+  CUtensorMap ma, mb;
+  int rc = make_map_bf16(&ma, A, R, K1, lda, 64, kBlockK);
+  if (rc) return rc;
+  rc = make_map_bf16(&mb, B, R, K2, ldb, 64, kBlockK);
+  if (rc) return rc;
+  const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 1, 1);
+  dim3 grid(p.m_tiles, p.n_tiles, p.splits);
+  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, R, K1, K2, p.block_n, p.rows_per, idesc, ws);
+  launch_split_reduce(ws, p.splits, K1, K2, dW, lddw, accumulate, s);
+  return check_launch();
+}
+
+}  // namespace edg

@@ -1,0 +1,290 @@
+"""The trigger-conditioned gated GCN block as one module (reference: the inline
+block every ``bert_amir*`` model repeats; canonical copy BertAmir55.forward,
+models/bert_amir5.py:615-648, parameters :559-572).
+
+``GatedGCNStack.forward`` computes, on packed rows and hand-written sm_100a kernels,
+
+    a      = x[trigger row]                                   (:604-605, :615-618)
+    g_l    = gate_l(a)                       l = 1..L         (:621-622, dropout p = 0)
+    h_l    = gc_l(h_{l-1}, A),  h_0 = x      (ungated chain)  (:626, :639)
+    xy     = sum_{l<l'} mean_b <max_t h_1*g_l, max_t h_1*g_l'> (:627-638)
+    x_out  = g_L * h_L;  pooled = max_t x_out                 (:639-640)
+    logits = logits_fn(a, pooled)            (host torch: self.dense(cat[...]), :643)
+    scores = <logits, fc(cat[x_out, a])>     (collapsed: x_out . v_b + c_b)  (:645-646)
+    kl     = mean_b sum_t softmax(scores) * softmax(float(dist))             (:648)
+
+and the matching backward pass, as ONE autograd node.  At L = 2 this is exactly the
+reference block.  CUDA only; no fallback.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .gcn import GraphConvolution, _compute_dtype
+from .graph import DepGraph
+
+# name -> (leading Sigmoid?, number of (Linear, Sigmoid) pairs); SURVEY 8a variant matrix
+GATE_ARCHS = {
+    "sig-2": (True, 2),     # BertAmir52/53/54/55   bert_amir5.py:562-571
+    "2": (False, 2),        # BertAmir5/51          bert_amir5.py:27-30
+    "3": (False, 3),        # BertAmir/BertAmir4    bert_amir.py:31-36
+    "sig-3": (True, 3),     # BertAmir2             bert_amir.py:180-187
+}
+
+StackOutput = namedtuple("StackOutput", ["logits", "xy", "kl", "scores", "pooled", "x_out"])
+
+
+def make_gate(D: int, arch: str) -> nn.Sequential:
+    lead, pairs = GATE_ARCHS[arch]
+    mods: List[nn.Module] = [nn.Sigmoid()] if lead else []
+    for _ in range(pairs):
+        mods += [nn.Linear(D, D), nn.Sigmoid()]
+    return nn.Sequential(*mods)
+
+
+class _GatedStackFn(torch.autograd.Function):
+    """inputs: x, then per layer (weight, bias), then per gate per pair (weight, bias),
+    then fc.weight, fc.bias.  ``cfg`` carries the non-tensor arguments."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, *params):
+        graph: DepGraph = cfg["graph"]
+        cd: torch.dtype = cfg["cdtype"]
+        Lyr, pairs, lead = cfg["L"], cfg["pairs"], cfg["lead"]
+        anchor, dist, logits_fn = cfg["anchor"], cfg["dist"], cfg["logits_fn"]
+        B, N, D = graph.n_graphs, graph.n_rows, x.shape[1]
+        gcn_p = [(params[2 * l], params[2 * l + 1]) for l in range(Lyr)]
+        o = 2 * Lyr
+        gate_p = [[(params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]) for i in range(pairs)]
+                  for g in range(Lyr)]
+        o += 2 * Lyr * pairs
+        fc_w, fc_b = params[o], params[o + 1]
+
+        xr = ops.as_rows(x, cd)
+        # ---- trigger vector and the gate MLPs (bert_amir5.py:615-622)
+        a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
+        gates = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
+        gate_saved = []
+        for g in range(Lyr):
+            s = s0
+            acts = [s0]
+            for i, (w, b) in enumerate(gate_p[g]):
+                wk = ops.cast_weight(w, cd, transpose=False)                    # nn.Linear [out,in] is K-major
+                last = i == pairs - 1
+                s = ops.linear(s, wk, b.detach().float().contiguous(), act=L.ACT_SIGMOID,
+                               out_dtype=torch.float32 if last else cd, out=gates[g] if last else None)
+                if not last:
+                    acts.append(s)
+            gate_saved.append(acts)
+        # ---- ungated GCN chain (bert_amir5.py:626, :639; gcn.py:33-45)
+        h = xr
+        ms, hs = [], []
+        for (w, b) in gcn_p:
+            m = ops.aggregate(h, graph, mode=0)
+            wt = ops.cast_weight(w, cd, transpose=True)
+            h = ops.linear(m, wt, b.detach().float().contiguous() if b is not None else None,
+                           act=L.ACT_RELU if cfg["relu"] else L.ACT_NONE)
+            ms.append(m)
+            hs.append(h)
+        # ---- gated views of layer 1 and the diversity term (:627-638)
+        v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
+        xy = ops.diversity_fwd(v_pooled) if Lyr > 1 else torch.zeros((), dtype=torch.float32, device=x.device)
+        # ---- output pooling (:639-640)
+        gL = gates[Lyr - 1]
+        pooled, p_arg = ops.pool_fwd(hs[-1], graph, gL.unsqueeze(0))
+        pooled, p_arg = pooled[0], p_arg[0]
+        # ---- classifier head on the host (torch autograd, tiny [B,*] tensors)  (:643, :645 collapsed)
+        with torch.enable_grad():
+            a_leaf = a_raw.detach().requires_grad_(True)
+            p_leaf = pooled.detach().requires_grad_(True)
+            logits = logits_fn(a_leaf, p_leaf)
+            lg = logits.float()
+            v = lg @ fc_w[:, :D].float()                                           # [B,D]
+            c = (lg * (a_leaf @ fc_w[:, D:].float().t() + fc_b.float())).sum(1)    # [B]
+        # ---- importance scores and the softmax product (:645-648)
+        scores, kl_b, kl = ops.scores_kl_fwd(hs[-1], graph, gL, v.detach().contiguous(), c.detach().contiguous(), dist)
+        x_out = ops.gate_rows(hs[-1], graph, gL, cd) if cfg["return_x_out"] else None
+
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None, not zero tensors
+        ctx.cfg = cfg
+        ctx.head = (a_leaf, p_leaf, logits, v, c)
+        ctx.gate_saved = gate_saved
+        ctx.n_params = len(params)
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(xr, gates, v_pooled, v_arg, p_arg, scores, kl_b, *ms, *hs, *params)
+        outs = (logits.detach(), xy, kl, scores, pooled)
+        return outs + ((x_out,) if x_out is not None else (None,))
+
+    @staticmethod
+    def backward(ctx, g_logits, g_xy, g_kl, g_scores, g_pooled, g_xout):
+        cfg = ctx.cfg
+        graph: DepGraph = cfg["graph"]
+        cd: torch.dtype = cfg["cdtype"]
+        Lyr, pairs, lead = cfg["L"], cfg["pairs"], cfg["lead"]
+        anchor, dist = cfg["anchor"], cfg["dist"]
+        saved = ctx.saved_tensors
+        xr, gates, v_pooled, v_arg, p_arg, scores, kl_b = saved[:7]
+        ms = saved[7:7 + Lyr]
+        hs = saved[7 + Lyr:7 + 2 * Lyr]
+        params = saved[7 + 2 * Lyr:]
+        B, N, D = graph.n_graphs, graph.n_rows, xr.shape[1]
+        dev = xr.device
+        a_leaf, p_leaf, logits, v, c = ctx.head
+        gL = gates[Lyr - 1]
+        hL = hs[-1]
+
+        def f32(t):
+            return None if t is None else t.detach().float().contiguous()
+
+        g_xy, g_kl, g_scores, g_pooled = f32(g_xy), f32(g_kl), f32(g_scores), f32(g_pooled)
+        if g_xout is not None:
+            g_xout = ops.as_rows(g_xout, cd)
+        need_scores = g_kl is not None or g_scores is not None
+        # ---- pass A over h_L: dv, dc (inputs of the host head's backward)
+        dv = dc = None
+        if need_scores:
+            _, _, dv, dc = ops.head_bwd(hL, graph, gL, v.detach().contiguous(), dist, scores, kl_b, g_kl, g_scores,
+                                        None, None, None, want_dh=False, want_dv=True)
+        # ---- host head backward: logits_fn, v, c  ->  d a, d pooled, and .grad of the head's own parameters
+        outs, grads = [], []
+        if g_logits is not None:
+            outs.append(logits); grads.append(g_logits.to(logits.dtype))
+        if dv is not None:
+            outs += [v, c]; grads += [dv, dc]
+        fc_w, fc_b = params[-2], params[-1]
+        d_fcw = d_fcb = None
+        ga_head = gp_head = None
+        if outs:
+            # one sweep through the host head graph: d a, d pooled, and the gradients of the
+            # parameters logits_fn closes over (e.g. self.dense), which are delivered to .grad here
+            cap = [p for p in cfg["head_params"] if p.requires_grad]
+            res = torch.autograd.grad(outs, [a_leaf, p_leaf] + cap, grads, allow_unused=True)
+            ga_head, gp_head = res[0], res[1]
+            for p, g in zip(cap, res[2:]):
+                if g is not None:
+                    p.grad = g if p.grad is None else p.grad + g
+            if dv is not None:
+                lg = logits.detach().float()
+                # v = lg @ Wx, c = sum(lg * (a Wa^T + b)): explicit fp32 formulas for the fc gradients
+                t = lg * dc[:, None]                                           # [B,C]
+                d_fcw = torch.cat([lg.t() @ dv, t.t() @ a_leaf.detach()], dim=1).to(fc_w.dtype)
+                d_fcb = t.sum(0).to(fc_b.dtype)
+        gp_total = g_pooled
+        if gp_head is not None:
+            gp_total = gp_head.float() if gp_total is None else gp_total + gp_head.float()
+        # ---- pass B over h_L: dh_L, dgate_L
+        dh, dgL, _, _ = ops.head_bwd(hL, graph, gL, v.detach().contiguous() if need_scores else None, dist,
+                                     scores if need_scores else None, kl_b, g_kl, g_scores,
+                                     gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
+                                     want_dh=True, want_dv=False)
+        dgates = torch.zeros((Lyr, B, D), dtype=torch.float32, device=dev)
+        dgates[Lyr - 1].copy_(dgL)
+        # ---- GCN chain backward (gcn.py:33-45)
+        grads_out: List[Optional[torch.Tensor]] = [None] * ctx.n_params
+        for l in range(Lyr - 1, -1, -1):
+            if l == 0 and g_xy is not None and Lyr > 1:
+                # gated views of h_1 feed xy (:627-638): add their gradient before leaving layer 1
+                ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, accumulate=True)
+            w, b = params[2 * l], params[2 * l + 1]
+            if cfg["relu"]:
+                dh = ops.as_rows(dh * (hs[l] > 0), cd)
+            dW, db = ops.wgrad(ms[l], dh, bias_of=2)
+            grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db.to(b.dtype)
+            wk = ops.cast_weight(w, cd, transpose=False)
+            dm = ops.linear(dh, wk, None)
+            dh = ops.aggregate(dm, graph, mode=1)
+        dx = dh
+        # ---- gate MLP backward (bert_amir5.py:562-571)
+        da = torch.zeros((B, D), dtype=torch.float32, device=dev) if ga_head is None else ga_head.float().clone()
+        o = 2 * Lyr
+        for g in range(Lyr):
+            acts = ctx.gate_saved[g]
+            dz = ops.sigmoid_bwd(gates[g], dgates[g], cd)                       # through the last Sigmoid
+            for i in range(pairs - 1, -1, -1):
+                w, b = params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]
+                dW, db = ops.wgrad(dz, acts[i], bias_of=1)                      # [out,in], [out]
+                grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
+                grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
+                wt = ops.cast_weight(w, cd, transpose=True)                     # [in,out]
+                if i > 0 or lead:
+                    ds = ops.linear(dz, wt, None)
+                    dz = ops.sigmoid_bwd(acts[i], ds, cd if i > 0 else torch.float32)
+                else:
+                    dz = ops.linear(dz, wt, None, out_dtype=torch.float32)
+            da += dz
+        ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
+        grads_out[-2], grads_out[-1] = d_fcw, d_fcb
+        if dx.dtype != ctx.x_dtype:
+            dx = dx.to(ctx.x_dtype)
+        return (None, dx) + tuple(grads_out)
+
+
+class GatedGCNStack(nn.Module):
+    """Owns gc1..gcL, gate1..gateL and fc with the reference's parameter names
+    (state-dict keys ``gc1.weight``, ``gate1.1.weight``, ``fc.0.weight`` ...,
+    bert_amir5.py:559-572) and runs the whole block fused."""
+
+    def __init__(self, hidden: int, n_layers: int = 2, n_classes: int = 2, gate_arch: str = "sig-2",
+                 relu: bool = False, dropout: float = 0.0, compute_dtype="f32"):
+        super().__init__()
+        if hidden % 4:
+            raise ValueError("hidden size must be a multiple of 4 (16-byte fp32 rows)")
+        self.hidden, self.n_layers, self.n_classes = hidden, n_layers, n_classes
+        self.gate_arch = gate_arch
+        self.relu = relu
+        self.dropout_p = dropout
+        self.compute_dtype = _compute_dtype(compute_dtype)
+        for l in range(1, n_layers + 1):
+            setattr(self, f"gc{l}", GraphConvolution(hidden, hidden, None, compute_dtype=self.compute_dtype))
+            setattr(self, f"gate{l}", make_gate(hidden, gate_arch))
+        self.fc = nn.Sequential(nn.Linear(2 * hidden, n_classes))        # bert_amir5.py:572
+
+    def _flat_params(self) -> List[torch.Tensor]:
+        ps: List[torch.Tensor] = []
+        for l in range(1, self.n_layers + 1):
+            gc = getattr(self, f"gc{l}")
+            ps += [gc.weight, gc.bias]
+        for l in range(1, self.n_layers + 1):
+            for m in getattr(self, f"gate{l}"):
+                if isinstance(m, nn.Linear):
+                    ps += [m.weight, m.bias]
+        ps += [self.fc[0].weight, self.fc[0].bias]
+        return ps
+
+    def forward(self, x: torch.Tensor, graph: DepGraph, anchor_index: torch.Tensor, dist_to_target: torch.Tensor,
+                logits_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+                head_params: Sequence[torch.Tensor] = (), return_x_out: bool = False) -> StackOutput:
+        """x [N,D] packed rows (or [B,T,D] with a dense-compat graph), graph, sentence-local
+        trigger index [B], distances (packed [N] or [B,T] for a dense-compat graph; int32/int64),
+        ``logits_fn(a [B,D], pooled [B,D]) -> [B,C]`` = the model's ``dense`` head (:643), and the
+        parameters ``logits_fn`` closes over (so their gradients are delivered)."""
+        if not x.is_cuda:
+            raise L.EdgError("GatedGCNStack runs on CUDA tensors only (there is no CPU path)")
+        if self.training and self.dropout_p > 0:
+            raise NotImplementedError(
+                "gate dropout p>0 in training mode is not implemented yet (bert_amir5.py:624-625 applies it to "
+                "the broadcast gate, per token); use dropout=0 or eval()")
+        shape3 = None
+        if x.dim() == 3:
+            shape3 = x.shape
+            x = x.reshape(-1, x.shape[-1])
+        dist = dist_to_target.reshape(-1)
+        if dist.dtype not in (torch.int32, torch.int64):
+            dist = dist.long()
+        dist = dist.contiguous()
+        lead, pairs = GATE_ARCHS[self.gate_arch]
+        cfg = dict(graph=graph, cdtype=self.compute_dtype, L=self.n_layers, pairs=pairs, lead=lead,
+                   anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
+                   head_params=list(head_params), relu=self.relu, return_x_out=return_x_out)
+        logits, xy, kl, scores, pooled, x_out = _GatedStackFn.apply(cfg, x, *self._flat_params())
+        if shape3 is not None:
+            scores = scores.reshape(shape3[0], shape3[1])
+            if x_out is not None:
+                x_out = x_out.reshape(shape3)
+        return StackOutput(logits, xy, kl, scores, pooled, x_out)

@@ -1,0 +1,194 @@
+"""Thin tensor-level wrappers over the C ABI: allocate outputs with torch (device
+memory + stream plumbing), pass raw pointers / leading dimensions to libedgcn.
+
+Row matrices are 2-D views ``[N, D]`` of a ``[N, ld]`` allocation with
+``ld = round_up(D, 16 bytes)`` so every row starts 16-byte aligned (128-bit
+loads, TMA global-stride rule).  Padding columns are always finite.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def row_pitch(D: int, dtype: torch.dtype) -> int:
+    return _round_up(D, 16 // torch.empty((), dtype=dtype).element_size())
+
+
+def alloc_rows(N: int, D: int, dtype: torch.dtype, device, zero: bool = False) -> torch.Tensor:
+    ld = row_pitch(D, dtype)
+    base = (torch.zeros if zero else torch.empty)((max(N, 1), ld), dtype=dtype, device=device)
+    return base[:N, :D]
+
+
+def as_rows(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Return ``t`` as an aligned 2-D row matrix of ``dtype`` (repacked only if needed)."""
+    if not t.is_cuda:
+        raise L.EdgError("libedgcn takes CUDA tensors only (there is no CPU path)")
+    assert t.dim() == 2
+    es = t.element_size()
+    ok = (t.dtype == dtype and t.stride(1) == 1 and (t.stride(0) * es) % 16 == 0 and t.data_ptr() % 16 == 0
+          and t.stride(0) >= t.shape[1])
+    if ok:
+        return t
+    out = alloc_rows(t.shape[0], t.shape[1], dtype, t.device, zero=True)
+    out.copy_(t)
+    return out
+
+
+def ld(t: torch.Tensor) -> int:
+    return t.stride(0)
+
+
+# ---------------------------------------------------------------------------
+def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    N, D = x.shape
+    out = alloc_rows(N, D, out_dtype or x.dtype, x.device)
+    L.call("edg_aggregate", L.ptr(x), L.dt(x), ld(x), L.ptr(out), L.dt(out), ld(out), N, D,
+           L.ptr(graph.row_ptr), L.ptr(graph.col), mode, L.stream())
+    return out
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = L.ACT_NONE,
+           out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(a @ w.T + bias)`` with ``w`` given as ``[Nout, K]`` (K contiguous)."""
+    M, K = a.shape
+    Nout = w.shape[0]
+    assert w.shape[1] == K and a.dtype == w.dtype
+    if out is None:
+        out = alloc_rows(M, Nout, out_dtype or a.dtype, a.device)
+    L.call("edg_linear", L.ptr(a), L.dt(a), ld(a), M, K, L.ptr(w), ld(w), Nout, L.ptr(bias), act,
+           L.ptr(out), L.dt(out), ld(out), L.stream())
+    return out
+
+
+def wgrad(a: torch.Tensor, b: torch.Tensor, bias_of: int = 0):
+    """``a.T @ b`` in fp32 (+ column sums of a (1) or b (2))."""
+    R, K1 = a.shape
+    K2 = b.shape[1]
+    assert b.shape[0] == R and a.dtype == b.dtype
+    dW = torch.empty((K1, K2), dtype=torch.float32, device=a.device)
+    db = torch.empty((K1 if bias_of == 1 else K2,), dtype=torch.float32, device=a.device) if bias_of else None
+    nbytes = L.load().edg_wgrad_workspace(R, K1, K2, L.dt(a))
+    ws = torch.empty((nbytes + 255) // 4, dtype=torch.float32, device=a.device)
+    L.call("edg_wgrad", L.ptr(a), ld(a), K1, L.ptr(b), ld(b), K2, L.dt(a), R, L.ptr(dW), K2, L.ptr(db), bias_of, 0,
+           L.ptr(ws), ws.numel() * 4, L.stream())
+    return dW, db
+
+
+def cast_weight(w: torch.Tensor, dtype: torch.dtype, transpose: bool) -> torch.Tensor:
+    """fp32 master weight ``[R,C]`` -> compute-dtype ``[R,C]`` or ``[C,R]`` row matrix."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    R, C = w.shape
+    ro, co = (C, R) if transpose else (R, C)
+    out = alloc_rows(ro, co, dtype, w.device)
+    L.call("edg_cast_2d", L.ptr(w), w.stride(0), R, C, L.ptr(out), L.dt(out), ld(out), int(transpose), L.stream())
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    R, C = x.shape
+    out = torch.empty((C,), dtype=torch.float32, device=x.device)
+    nbytes = L.load().edg_colsum_workspace(R, C)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=x.device)
+    L.call("edg_colsum", L.ptr(x), L.dt(x), ld(x), R, C, L.ptr(out), 0, L.ptr(ws), ws.numel() * 4, L.stream())
+    return out
+
+
+def trigger_gather(x: torch.Tensor, graph, anchor: torch.Tensor, lead_sigmoid: bool, want_raw: bool = True):
+    B, D = graph.n_graphs, x.shape[1]
+    raw = torch.empty((B, D), dtype=torch.float32, device=x.device) if want_raw else None
+    act = alloc_rows(B, D, x.dtype, x.device, zero=True)
+    L.call("edg_trigger_gather", L.ptr(x), L.dt(x), ld(x), L.ptr(graph.sent_ptr), L.ptr(anchor), B, D, L.ptr(raw),
+           L.ptr(act), ld(act), int(lead_sigmoid), L.stream())
+    return raw, act
+
+
+def trigger_scatter_add(da: torch.Tensor, graph, anchor: torch.Tensor, dx: torch.Tensor) -> None:
+    B, D = da.shape
+    L.call("edg_trigger_scatter_add", L.ptr(da), B, D, L.ptr(graph.sent_ptr), L.ptr(anchor), L.ptr(dx), L.dt(dx),
+           ld(dx), L.stream())
+
+
+def pool_fwd(h: torch.Tensor, graph, gates: torch.Tensor):
+    """gates fp32 [V,B,D] -> pooled fp32 [V,B,D], arg int32 [V,B,D]."""
+    V, B, D = gates.shape
+    pooled = torch.empty((V, B, D), dtype=torch.float32, device=h.device)
+    arg = torch.empty((V, B, D), dtype=torch.int32, device=h.device)
+    L.call("edg_pool_fwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gates), V, L.ptr(pooled),
+           L.ptr(arg), L.stream())
+    return pooled, arg
+
+
+def diversity_fwd(pooled: torch.Tensor) -> torch.Tensor:
+    V, B, D = pooled.shape
+    xy = torch.empty((), dtype=torch.float32, device=pooled.device)
+    ws = torch.empty(1024, dtype=torch.float32, device=pooled.device)
+    L.call("edg_diversity_fwd", L.ptr(pooled), V, B, D, L.ptr(xy), L.ptr(ws), L.stream())
+    return xy
+
+
+def views_bwd(pooled, arg, gates, h, g_xy, g_pooled, dh, dgates, accumulate: bool) -> None:
+    V, B, D = pooled.shape
+    L.call("edg_views_bwd", L.ptr(pooled), L.ptr(arg), L.ptr(gates), L.ptr(h), L.dt(h), ld(h), V, B, D, L.ptr(g_xy),
+           L.ptr(g_pooled), L.ptr(dh), ld(dh), L.ptr(dgates), int(accumulate), L.stream())
+
+
+def _dist_flag(dist: torch.Tensor) -> int:
+    if dist.dtype == torch.int64:
+        return 1
+    if dist.dtype == torch.int32:
+        return 0
+    raise L.EdgError("dist_to_target must be int32 or int64")
+
+
+def scores_kl_fwd(h, graph, gate, v, c, dist):
+    B, D = gate.shape
+    N = h.shape[0]
+    scores = torch.empty((N,), dtype=torch.float32, device=h.device)
+    kl_b = torch.empty((B,), dtype=torch.float32, device=h.device)
+    L.call("edg_scores_kl_fwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(v),
+           L.ptr(c), L.ptr(dist), _dist_flag(dist), L.ptr(scores), L.ptr(kl_b), L.stream())
+    kl = torch.empty((), dtype=torch.float32, device=h.device)
+    L.call("edg_sum_scaled", L.ptr(kl_b), B, 1.0 / B, L.ptr(kl), L.stream())
+    return scores, kl_b, kl
+
+
+def head_bwd(h, graph, gate, v, dist, scores, kl_b, g_kl, g_scores, g_pooled, arg, g_xout, want_dh: bool,
+             want_dv: bool):
+    B, D = gate.shape
+    N = h.shape[0]
+    dh = alloc_rows(N, D, h.dtype, h.device) if want_dh else None
+    dgate = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_dh else None
+    dv = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_dv else None
+    dc = torch.empty((B,), dtype=torch.float32, device=h.device) if want_dv else None
+    L.call("edg_head_bwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(v),
+           L.ptr(dist), _dist_flag(dist) if dist is not None else 0, L.ptr(scores), L.ptr(kl_b), L.ptr(g_kl),
+           L.ptr(g_scores), L.ptr(g_pooled), L.ptr(arg), L.ptr(g_xout), ld(g_xout) if g_xout is not None else 0,
+           L.ptr(dh), ld(dh) if dh is not None else 0, L.ptr(dgate), L.ptr(dv), L.ptr(dc), graph.max_len, L.stream())
+    return dh, dgate, dv, dc
+
+
+def gate_rows(h, graph, gate, out_dtype):
+    B, D = gate.shape
+    out = alloc_rows(h.shape[0], D, out_dtype, h.device)
+    L.call("edg_gate_rows", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(out),
+           L.dt(out), ld(out), L.stream())
+    return out
+
+
+def sigmoid_bwd(y: torch.Tensor, dy: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    R, C = y.shape
+    dz = alloc_rows(R, C, out_dtype, y.device, zero=True)
+    L.call("edg_sigmoid_bwd", L.ptr(y), L.dt(y), ld(y), L.ptr(dy), L.dt(dy), ld(dy), R, C, L.ptr(dz), L.dt(dz),
+           ld(dz), L.stream())
+    return dz

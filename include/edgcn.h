@@ -1,0 +1,221 @@
+/*
+ * edgcn.h -- C ABI of the B200-native gated-GCN hot path (libedgcn.so).
+ *
+ * This is the drop-in boundary for ONE path of laiviet/ed-gated-gcn: the
+ * trigger-conditioned gated graph convolution.  The reference
+ * is pure Python/PyTorch and has no FFI of its own; each entry point below names
+ * the reference lines whose work it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the ctypes binding and the one-line
+ * change to models/gcn.py that a reference maintainer would make.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch); the library
+ *     allocates nothing and keeps no global state;
+ *   - sizes and leading dimensions (ld*) are in ELEMENTS, not bytes;
+ *   - `stream` is the cudaStream_t to enqueue on (torch.cuda.current_stream());
+ *     calls only enqueue work, they never synchronise;
+ *   - return value: EDG_OK (0) or a negative edg_status; nothing throws or
+ *     exits across the ABI; asynchronous CUDA faults surface at the caller's
+ *     next synchronisation as usual;
+ *   - re-entrant and thread-safe (autograd calls backward from another host thread);
+ *   - sm_100a only: there is no CPU path and no other-arch path.
+ *
+ * Layout vocabulary
+ *   sentence b owns the packed token rows [sent_ptr[b], sent_ptr[b+1]);
+ *   N = total rows, B = sentences (= graphs = (sentence, trigger) pairs);
+ *   CSR (row_ptr[N+1], col[nnz]) holds, for row i, the GLOBAL row ids of
+ *   self + parent + children in ascending order (the non-zeros of graph.py:66-75);
+ *   activations are row-major [N, ld] in fp32 or bf16, rows 16-byte aligned.
+ */
+#ifndef EDGCN_H_
+#define EDGCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDG_ABI_VERSION 1
+
+typedef enum {
+  EDG_OK = 0,
+  EDG_ERR_ARG = -1,         /* null pointer, negative size, bad enum            */
+  EDG_ERR_ALIGN = -2,       /* pointer or leading dimension not 16-byte aligned */
+  EDG_ERR_DTYPE = -3,       /* dtype combination not implemented                */
+  EDG_ERR_ARCH = -4,        /* device is not sm_100                             */
+  EDG_ERR_WORKSPACE = -5,   /* workspace too small (see the *_workspace query)  */
+  EDG_ERR_CUDA = -6,        /* a CUDA runtime/driver call failed at enqueue     */
+  EDG_ERR_UNSUPPORTED = -7  /* shape outside what the kernels implement         */
+} edg_status;
+
+typedef enum { EDG_F32 = 0, EDG_BF16 = 1 } edg_dtype;
+typedef enum { EDG_ACT_NONE = 0, EDG_ACT_SIGMOID = 1, EDG_ACT_RELU = 2 } edg_act;
+typedef enum { EDG_PAD_MAX_PLUS_1 = 0, EDG_PAD_ZERO = 1 } edg_pad;
+typedef void* edg_stream;   /* cudaStream_t */
+
+int edg_version(void);
+const char* edg_strerror(int status);
+/* Last CUDA error string recorded by this thread's most recent failing call. */
+const char* edg_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------- */
+/* Integer kernels (bit-exact against the reference)                          */
+/* ------------------------------------------------------------------------- */
+
+/* graph.py:66-75 (gen_graph, matrix part) in packed form.  heads[N] holds the
+ * sentence-local head index of every token (-1 = root; out-of-range or self
+ * heads are treated as root).  Writes row_ptr[N+1], col (capacity >= 3N),
+ * row_sent[N] (sentence id of each row).  ws: B+1 int32 of scratch.
+ * max_len = longest sentence (<= 4096). */
+int edg_csr_from_heads(const int32_t* heads, const int32_t* sent_ptr, int32_t B, int32_t N,
+                       int32_t max_len, int32_t* row_ptr, int32_t* col, int32_t* row_sent,
+                       int32_t* ws, edg_stream stream);
+
+/* Compat path for the unchanged forward(text, adj) signature (models/gcn.py:30):
+ * dense [B,T,T] adjacency (fp32 or int64, any strides) -> packed CSR over B*T rows
+ * (padding rows are self-loop singletons, graph.py:66).  Two calls because the
+ * caller must size `col`: _count fills row_ptr[B*T+1] (nnz = row_ptr[B*T]) and
+ * flags[0] = entries that are neither 0 nor 1, flags[1] = asymmetric entries;
+ * _fill writes col. */
+int edg_csr_from_dense_count(const void* adj, int adj_is_i64, int32_t B, int32_t T,
+                             int64_t stride_b, int64_t stride_r, int64_t stride_c,
+                             int32_t* row_ptr, int32_t* flags, edg_stream stream);
+int edg_csr_from_dense_fill(const void* adj, int adj_is_i64, int32_t B, int32_t T,
+                            int64_t stride_b, int64_t stride_r, int64_t stride_c,
+                            const int32_t* row_ptr, int32_t* col, edg_stream stream);
+
+/* data_utils.py:302-323 (get_dist / get_dist_to_target): hop count from every
+ * token to the trigger + 1 (trigger -> 1); a token that cannot reach the trigger
+ * gets 100001.  anchor[B] is sentence-local.  dist[N] is packed. */
+int edg_tree_dist(const int32_t* row_ptr, const int32_t* col, const int32_t* sent_ptr,
+                  const int32_t* anchor, int32_t B, int32_t max_len, int32_t* dist,
+                  edg_stream stream);
+
+/* data_utils.py:486-488 (pad with max+1) / :593-594 (pad with 0): packed
+ * distances -> int64 [B,T] as collate_fn lays them out (data_utils.py:378). */
+int edg_dist_pad(const int32_t* dist, const int32_t* sent_ptr, int32_t B, int32_t T,
+                 int pad_mode, int64_t* out, edg_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* Graph convolution (models/gcn.py:30-45)                                    */
+/* ------------------------------------------------------------------------- */
+
+/* Degree-normalised neighbour aggregation, the `adj @ . / (rowsum + 1)` half of
+ * gcn.py:35,41 on the packed CSR.
+ *   mode 0 (forward):  y[i] = 1/(deg_i+1) * sum_{j in row i} x[j]
+ *   mode 1 (backward): y[j] = sum_{i in row j} x[i] / (deg_i+1)   (A symmetric)
+ * x and y may differ in dtype; accumulation is fp32. */
+int edg_aggregate(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
+                  int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
+                  edg_stream stream);
+
+/* C[M,Nout] = act(A[M,K] * W^T + bias), W given as [Nout,K] with K contiguous
+ * (nn.Linear layout).  Replaces torch.matmul(text, weight) of gcn.py:34 (with a
+ * transposed weight copy) and the nn.Linear calls of the gate MLPs
+ * (bert_amir5.py:562-571).  bf16 inputs run on tcgen05 tensor cores fed by TMA;
+ * fp32 inputs run an FFMA kernel (fp32-parity mode).  bias is fp32 or NULL. */
+int edg_linear(const void* A, int ab_dtype, int64_t lda, int32_t M, int32_t K,
+               const void* W, int64_t ldw, int32_t Nout, const float* bias, int act,
+               void* C, int c_dtype, int64_t ldc, edg_stream stream);
+
+/* dW[K1,K2] (+)= A[R,K1]^T * B[R,K2]  (fp32 result).  Replaces autograd's weight
+ * gradients of gcn.py:34 and of the gate Linears.  bias_of: 0 none, 1 column
+ * sums of A, 2 column sums of B -> dbias.  ws: edg_wgrad_workspace() bytes.
+ * accumulate != 0 adds into dW/dbias instead of overwriting. */
+size_t edg_wgrad_workspace(int32_t R, int32_t K1, int32_t K2, int dtype);
+int edg_wgrad(const void* A, int64_t lda, int32_t K1, const void* B, int64_t ldb, int32_t K2,
+              int dtype, int32_t R, float* dW, int64_t lddw, float* dbias, int bias_of,
+              int accumulate, void* ws, size_t ws_bytes, edg_stream stream);
+
+/* fp32 [R,C] master weight -> compute-dtype copy, optionally transposed, padding
+ * columns up to ldd zero-filled. */
+int edg_cast_2d(const float* src, int64_t lds, int32_t R, int32_t C, void* dst, int dst_dtype,
+                int64_t ldd, int transpose, edg_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* Gated block (models/bert_amir5.py:615-648)                                 */
+/* ------------------------------------------------------------------------- */
+
+/* bert_amir5.py:604-605,615-618: the trigger row of every sentence.
+ * raw[B,D] fp32 = x[sent_ptr[b]+anchor[b]]; act (compute dtype, ld = ldact) =
+ * sigmoid(raw) when lead_sigmoid else raw (first op of the gate MLP, :562). */
+int edg_trigger_gather(const void* x, int dtype, int64_t ldx, const int32_t* sent_ptr,
+                       const int32_t* anchor, int32_t B, int32_t D, float* raw, void* act,
+                       int64_t ldact, int lead_sigmoid, edg_stream stream);
+/* backward of the gather: dx[sent_ptr[b]+anchor[b]] += da[b]  (rows are distinct). */
+int edg_trigger_scatter_add(const float* da, int32_t B, int32_t D, const int32_t* sent_ptr,
+                            const int32_t* anchor, void* dx, int dtype, int64_t lddx,
+                            edg_stream stream);
+
+/* bert_amir5.py:627-636,640: pooled[v,b,:] = max_t h[t,:]*gates[v,b,:] over the
+ * sentence's rows, arg = global row of the maximum (first row wins ties). */
+int edg_pool_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
+                 int32_t D, const float* gates, int32_t V, float* pooled, int32_t* arg,
+                 edg_stream stream);
+
+/* bert_amir5.py:638: xy = sum_{v<v'} mean_b sum_d pooled[v]*pooled[v'].
+ * ws: 1024 floats. */
+int edg_diversity_fwd(const float* pooled, int32_t V, int32_t B, int32_t D, float* xy, float* ws,
+                      edg_stream stream);
+
+/* backward of the pooled views and the diversity term: with
+ * dp[v] = g_xy/B * sum_{v'!=v} pooled[v'] (+ g_pooled[v] when given),
+ *   dh[arg[v,b,d], d] += dp[v,b,d]*gates[v,b,d]   (added into dh)
+ *   dgates[v,b,d]     (+)= dp[v,b,d]*h[arg[v,b,d], d]
+ * g_xy is a device scalar (NULL = 0). */
+int edg_views_bwd(const float* pooled, const int32_t* arg, const float* gates, const void* h,
+                  int dtype, int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy,
+                  const float* g_pooled, void* dh, int64_t lddh, float* dgates, int accumulate_dgates,
+                  edg_stream stream);
+
+/* bert_amir5.py:645-648 in collapsed form:
+ *   scores[i] = sum_d h[i,d]*gate[b,d]*v[b,d] + c[b]
+ *   kl_b[b]   = sum_t softmax_t(scores)*softmax_t(float(dist))
+ * dist is packed int32 (dist_i64 = 0) or int64. */
+int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
+                      int32_t D, const float* gate, const float* v, const float* c,
+                      const void* dist, int dist_i64, float* scores, float* kl_b,
+                      edg_stream stream);
+
+/* backward of x_out = gate*h_L through scores/kl, the final max-pool and an
+ * optional direct gradient on x_out:
+ *   ds[i]   = g_kl/B * P_i*(Q_i - kl_b) + g_scores[i]
+ *   dh[i,d] = gate*( ds[i]*v + [i==arg[b,d]]*g_pooled[b,d] + g_xout[i,d] )
+ *   dgate[b,d] = sum_t h*( ds*v + [..]*g_pooled + g_xout ),  dv[b,d] = sum_t ds*h*gate,
+ *   dc[b] = sum_t ds.
+ * g_kl: device scalar or NULL; g_scores, g_pooled, g_xout may be NULL.
+ * dh/dgate may be NULL (first pass: only dv/dc, which the host needs before it can
+ * back-propagate through the classifier head to obtain g_pooled).
+ * max_len = longest sentence (sizes the shared-memory ds buffer; <= 8192). */
+int edg_head_bwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
+                 int32_t D, const float* gate, const float* v, const void* dist, int dist_i64,
+                 const float* scores, const float* kl_b, const float* g_kl, const float* g_scores,
+                 const float* g_pooled, const int32_t* arg, const void* g_xout, int64_t ldgx,
+                 void* dh, int64_t lddh, float* dgate, float* dv, float* dc, int32_t max_len,
+                 edg_stream stream);
+
+/* x_out[i,:] = gate[b(i),:]*h[i,:]  (bert_amir5.py:639), only materialised when a
+ * caller asks for the per-token output. */
+int edg_gate_rows(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
+                  int32_t D, const float* gate, void* out, int out_dtype, int64_t ldo,
+                  edg_stream stream);
+
+/* elementwise helpers of the gate MLP backward: dz = dy*y*(1-y) (nn.Sigmoid). */
+int edg_sigmoid_bwd(const void* y, int y_dtype, int64_t ldy, const void* dy, int dy_dtype,
+                    int64_t lddy, int32_t R, int32_t C, void* dz, int dz_dtype, int64_t lddz,
+                    edg_stream stream);
+
+/* out[0] = scale * sum(in[0..n))   (deterministic; used for the batch means). */
+int edg_sum_scaled(const float* in, int64_t n, float scale, float* out, edg_stream stream);
+
+/* column sums of a [R,C] matrix -> fp32 out[C]; ws: edg_colsum_workspace bytes. */
+size_t edg_colsum_workspace(int32_t R, int32_t C);
+int edg_colsum(const void* x, int dtype, int64_t ldx, int32_t R, int32_t C, float* out,
+               int accumulate, void* ws, size_t ws_bytes, edg_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDGCN_H_ */

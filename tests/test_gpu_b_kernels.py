@@ -1,0 +1,158 @@
+"""Floating-point kernels one by one, through the C ABI, against CPU torch fp32/fp64.
+fp32 mode: <= 1e-5 relative (max|a-b| / max|b|); bf16 mode: <= 2e-2 relative."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import DEV, rel, tol_for, dense_inputs, pack_rows
+from oracle import ref_oracle as O
+
+pytestmark = pytest.mark.gpu
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def _batch_graph(B, lo, hi, seed, skewed=False):
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import synth
+    batch = synth.make_batch(B, lo, hi, seed=seed, skewed=skewed)
+    g = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=DEV)
+    return batch, g
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("D", [300, 256, 8, 20])
+def test_aggregate_forward_and_transpose(dtype, D):
+    from ed_gated_gcn_b200 import ops
+    batch, g = _batch_graph(37, 1, 50, seed=D)
+    x = torch.randn(batch.n_rows, D)
+    xr = ops.as_rows(x.to(DEV), dtype)
+    x_used = xr.float().cpu()
+    # oracle: per sentence, exact-size adjacency (packed mode has no pad rows)
+    want, want_t = [], []
+    for b, h in enumerate(batch.heads_list()):
+        lo, hi = batch.sent_ptr[b], batch.sent_ptr[b + 1]
+        a = torch.from_numpy(O.dense_adjacency_from_heads(h, len(h))).float()
+        xs = x_used[lo:hi]
+        den = a.sum(1, keepdim=True) + 1
+        want.append((a @ xs) / den)                  # gcn.py:35,41
+        want_t.append(a.t() @ (xs / den))            # its adjoint
+    y = ops.aggregate(xr, g, mode=0)
+    yt = ops.aggregate(xr, g, mode=1)
+    assert rel(y.float(), torch.cat(want)) < (1e-6 if dtype == torch.float32 else 8e-3)
+    assert rel(yt.float(), torch.cat(want_t)) < (1e-6 if dtype == torch.float32 else 8e-3)
+    # mixed dtype output path
+    y32 = ops.aggregate(xr, g, mode=0, out_dtype=torch.float32)
+    assert rel(y32, torch.cat(want)) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(1, 16, 16), (127, 300, 300), (128, 64, 256), (1000, 300, 300), (513, 768, 768),
+                                   (4096, 256, 256), (77, 40, 24), (300, 304, 8)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear(dtype, shape, act):
+    from ed_gated_gcn_b200 import ops
+    M, K, Nout = shape
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(Nout, K, generator=g) / K ** 0.5
+    bias = torch.randn(Nout, generator=g)
+    ar, wr = ops.as_rows(a.to(DEV), dtype), ops.as_rows(w.to(DEV), dtype)
+    want = ar.float().cpu().double() @ wr.float().cpu().double().t() + bias.double()
+    if act == 1:
+        want = torch.sigmoid(want)
+    for out_dtype in (dtype, torch.float32):
+        got = ops.linear(ar, wr, bias.to(DEV), act=act, out_dtype=out_dtype)
+        tol = 2e-6 if out_dtype == torch.float32 else 5e-3
+        assert rel(got.float(), want) < tol, (shape, out_dtype)
+        # the row padding must stay finite/zero: later kernels read whole 16-byte chunks
+        base = got.as_strided((M, got.stride(0)), (got.stride(0), 1))
+        assert torch.isfinite(base.float()).all()
+        assert (base[:, Nout:] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(50, 16, 16), (1000, 300, 300), (4096, 256, 256), (3000, 768, 768), (129, 300, 40),
+                                   (64, 8, 304)])
+def test_wgrad(dtype, shape):
+    from ed_gated_gcn_b200 import ops
+    R, K1, K2 = shape
+    g = torch.Generator().manual_seed(R + K1)
+    a = torch.randn(R, K1, generator=g)
+    b = torch.randn(R, K2, generator=g)
+    ar, br = ops.as_rows(a.to(DEV), dtype), ops.as_rows(b.to(DEV), dtype)
+    ad, bd = ar.float().cpu().double(), br.float().cpu().double()
+    for bias_of in (0, 1, 2):
+        dW, db = ops.wgrad(ar, br, bias_of=bias_of)
+        assert rel(dW, ad.t() @ bd) < 2e-6
+        if bias_of == 1:
+            assert rel(db, ad.sum(0)) < 2e-6
+        if bias_of == 2:
+            assert rel(db, bd.sum(0)) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_tensor_core_kernels_agree_with_ffma_kernels(dtype, monkeypatch):
+    """bf16: tcgen05 results vs torch on the same bf16 inputs at a full-size shape (C2 rows)."""
+    if dtype != torch.bfloat16:
+        pytest.skip("tensor-core path is bf16 only")
+    from ed_gated_gcn_b200 import ops
+    M, K, Nout = 112_640, 300, 300
+    g = torch.Generator().manual_seed(1)
+    a = ops.as_rows(torch.randn(M, K, generator=g).to(DEV), dtype)
+    w = ops.as_rows((torch.randn(Nout, K, generator=g) / K ** 0.5).to(DEV), dtype)
+    got = ops.linear(a, w, None, out_dtype=torch.float32)
+    want = a.float() @ w.float().t()                   # cuBLAS fp32 as the on-device checker
+    assert rel(got, want) < 1e-5
+    dW, _ = ops.wgrad(a, a)
+    assert rel(dW, a.float().t() @ a.float()) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pool_views_ties_and_diversity(dtype):
+    from ed_gated_gcn_b200 import ops
+    batch, g = _batch_graph(21, 1, 30, seed=4)
+    D, V = 40, 3
+    h = torch.randn(batch.n_rows, D)
+    h[batch.sent_ptr[3]:batch.sent_ptr[4]] = 0.25              # a sentence of identical rows: first row must win
+    gates = torch.rand(V, batch.n_graphs, D) + 0.05
+    hr = ops.as_rows(h.to(DEV), dtype)
+    pooled, arg = ops.pool_fwd(hr, g, gates.to(DEV))
+    hu = hr.float().cpu()
+    for b in range(batch.n_graphs):
+        lo, hi = int(batch.sent_ptr[b]), int(batch.sent_ptr[b + 1])
+        for v in range(V):
+            val, idx = torch.max(hu[lo:hi] * gates[v, b][None, :], dim=0)
+            assert torch.equal(pooled[v, b].cpu(), val)
+            if b == 3:
+                assert (arg[v, b].cpu() == lo).all()
+            else:
+                assert torch.equal(arg[v, b].cpu().long(), idx + lo)
+    xy = ops.diversity_fwd(pooled)
+    p = pooled.double().cpu()
+    want = sum((p[i] * p[j]).sum(1).mean() for i in range(V) for j in range(i + 1, V))
+    assert rel(xy, want) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("i64", [False, True])
+def test_scores_kl(dtype, i64):
+    from ed_gated_gcn_b200 import ops
+    import ed_gated_gcn_b200 as E
+    batch, g = _batch_graph(19, 1, 45, seed=8)
+    D = 300
+    B = batch.n_graphs
+    h = ops.as_rows(torch.randn(batch.n_rows, D).to(DEV), dtype)
+    gate = torch.rand(B, D); v = torch.randn(B, D) * 0.1; c = torch.randn(B)
+    dist = E.tree_distance(g, torch.from_numpy(batch.anchor).to(DEV))
+    if i64:
+        dist = dist.long()
+    scores, kl_b, kl = ops.scores_kl_fwd(h, g, gate.to(DEV), v.to(DEV), c.to(DEV), dist)
+    hu = h.float().cpu().double()
+    for b in range(B):
+        lo, hi = int(batch.sent_ptr[b]), int(batch.sent_ptr[b + 1])
+        s = (hu[lo:hi] * gate[b].double() * v[b].double()).sum(1) + c[b].double()
+        assert rel(scores[lo:hi], s) < 2e-6
+        q = torch.softmax(dist[lo:hi].cpu().double(), 0)
+        want = (torch.softmax(s, 0) * q).sum()
+        assert abs(kl_b[b].item() - want.item()) < 2e-6
+    assert abs(kl.item() - kl_b.double().mean().item()) < 1e-6
