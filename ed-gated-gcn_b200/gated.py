@@ -37,7 +37,7 @@ GATE_ARCHS = {
     "sig-3": (True, 3),     # BertAmir2             bert_amir.py:180-187
 }
 
-StackOutput = namedtuple("StackOutput", ["logits", "xy", "kl", "scores", "pooled", "x_out"])
+StackOutput = namedtuple("StackOutput", ["logits", "xy", "kl", "scores", "pooled", "x_out", "pooled_arg", "view_arg"])
 
 
 def make_gate(D: int, arch: str) -> nn.Sequential:
@@ -118,11 +118,12 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.n_params = len(params)
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(xr, gates, v_pooled, v_arg, p_arg, scores, kl_b, *ms, *hs, *params)
-        outs = (logits.detach(), xy, kl, scores, pooled)
-        return outs + ((x_out,) if x_out is not None else (None,))
+        # arg-max rows (global row ids), like the indices torch.max returns at :635-636/:640
+        ctx.mark_non_differentiable(p_arg, v_arg)
+        return logits.detach(), xy, kl, scores, pooled, x_out, p_arg, v_arg
 
     @staticmethod
-    def backward(ctx, g_logits, g_xy, g_kl, g_scores, g_pooled, g_xout):
+    def backward(ctx, g_logits, g_xy, g_kl, g_scores, g_pooled, g_xout, _g_parg=None, _g_varg=None):
         cfg = ctx.cfg
         graph: DepGraph = cfg["graph"]
         cd: torch.dtype = cfg["cdtype"]
@@ -282,9 +283,9 @@ class GatedGCNStack(nn.Module):
         cfg = dict(graph=graph, cdtype=self.compute_dtype, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
                    head_params=list(head_params), relu=self.relu, return_x_out=return_x_out)
-        logits, xy, kl, scores, pooled, x_out = _GatedStackFn.apply(cfg, x, *self._flat_params())
+        logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params())
         if shape3 is not None:
             scores = scores.reshape(shape3[0], shape3[1])
             if x_out is not None:
                 x_out = x_out.reshape(shape3)
-        return StackOutput(logits, xy, kl, scores, pooled, x_out)
+        return StackOutput(logits, xy, kl, scores, pooled, x_out, p_arg, v_arg)

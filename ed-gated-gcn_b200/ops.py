@@ -22,8 +22,8 @@ def row_pitch(D: int, dtype: torch.dtype) -> int:
     return _round_up(D, 16 // torch.empty((), dtype=dtype).element_size())
 
 
-def alloc_rows(N: int, D: int, dtype: torch.dtype, device, zero: bool = False) -> torch.Tensor:
-    ld = row_pitch(D, dtype)
+def alloc_rows(N: int, D: int, dtype: torch.dtype, device, zero: bool = False, min_ld: int = 0) -> torch.Tensor:
+    ld = max(row_pitch(D, dtype), min_ld)
     base = (torch.zeros if zero else torch.empty)((max(N, 1), ld), dtype=dtype, device=device)
     return base[:N, :D]
 
@@ -50,7 +50,8 @@ def ld(t: torch.Tensor) -> int:
 # ---------------------------------------------------------------------------
 def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     N, D = x.shape
-    out = alloc_rows(N, D, out_dtype or x.dtype, x.device)
+    # the kernel walks 16-byte chunks of the INPUT dtype, so the output pitch must cover the same columns
+    out = alloc_rows(N, D, out_dtype or x.dtype, x.device, min_ld=row_pitch(D, x.dtype))
     L.call("edg_aggregate", L.ptr(x), L.dt(x), ld(x), L.ptr(out), L.dt(out), ld(out), N, D,
            L.ptr(graph.row_ptr), L.ptr(graph.col), mode, L.stream())
     return out

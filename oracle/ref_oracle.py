@@ -221,7 +221,8 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
                     dist: torch.Tensor, gcn_params: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]],
                     gate_params: Sequence[Sequence[Tuple[torch.Tensor, torch.Tensor]]],
                     fc_w: torch.Tensor, fc_b: torch.Tensor, logits_fn,
-                    lead_sigmoid: bool = True) -> Dict[str, torch.Tensor]:
+                    lead_sigmoid: bool = True, forced_view_arg: Optional[torch.Tensor] = None,
+                    forced_final_arg: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """The canonical block, bert_amir5.py:615-648, for ``L = len(gcn_params)``
     layers (the reference has L = 2: gc1, gc2).
 
@@ -233,6 +234,13 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
     L > 2 follows SURVEY 8a/A5: an ungated chain h_l = gc_l(h_{l-1}); the output
     is gate_L * h_L; the diversity term sums over all pairs of gated views of
     h_1.  At L = 2 this is literally :626-640.
+
+    ``forced_view_arg [L,B,D]`` / ``forced_final_arg [B,D]`` (token indices) replace the
+    arg-max of the pooling steps by a given routing.  torch.max is discontinuous: a
+    bf16 computation legitimately picks another row when two rows tie within bf16
+    resolution, and the gradient then flows elsewhere.  The bf16 tests therefore compare
+    gradients against this oracle with the CUDA path's own routing, and separately check
+    that every re-routed position is such a near-tie.
     """
     B, T, D = x.shape
     L = len(gcn_params)
@@ -245,13 +253,19 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
         h = gcn_layer_ref(h, adj, w, b)
         hs.append(h)
     h1 = hs[0]
-    views = [torch.max(h1 * g[:, None, :], dim=1)[0] for g in gates]  # :627-636
+    def pool(t, forced):                                              # torch.max(t, 1)[0], :635-636/:640
+        if forced is None:
+            return torch.max(t, dim=1)[0]
+        return torch.gather(t, 1, forced.long()[:, None, :])[:, 0, :]
+
+    views = [pool(h1 * g[:, None, :], None if forced_view_arg is None else forced_view_arg[i])
+             for i, g in enumerate(gates)]                            # :627-636
     xy = x.new_zeros(())
     for i in range(L):
         for j in range(i + 1, L):
             xy = xy + (views[i] * views[j]).sum(1).mean()             # :638
     x_out = gates[-1][:, None, :] * hs[-1]                            # :639
-    pooled = torch.max(x_out, dim=1)[0]                               # :640
+    pooled = pool(x_out, forced_final_arg)                            # :640
     logits = logits_fn(aspect, pooled)                                # :643
     cat = torch.cat([x_out, aspect[:, None, :].expand(B, T, D)], dim=2)
     output_w = cat @ fc_w.t() + fc_b                                  # :645

@@ -19,7 +19,7 @@ def _batch_graph(B, lo, hi, seed, skewed=False):
     return batch, g
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
 @pytest.mark.parametrize("D", [300, 256, 8, 20])
 def test_aggregate_forward_and_transpose(dtype, D):
     from ed_gated_gcn_b200 import ops
@@ -45,7 +45,7 @@ def test_aggregate_forward_and_transpose(dtype, D):
     assert rel(y32, torch.cat(want)) < 1e-6
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
 @pytest.mark.parametrize("shape", [(1, 16, 16), (127, 300, 300), (128, 64, 256), (1000, 300, 300), (513, 768, 768),
                                    (4096, 256, 256), (77, 40, 24), (300, 304, 8)])
 @pytest.mark.parametrize("act", [0, 1])
@@ -70,7 +70,7 @@ def test_linear(dtype, shape, act):
         assert (base[:, Nout:] == 0).all()
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
 @pytest.mark.parametrize("shape", [(50, 16, 16), (1000, 300, 300), (4096, 256, 256), (3000, 768, 768), (129, 300, 40),
                                    (64, 8, 304)])
 def test_wgrad(dtype, shape):
@@ -90,7 +90,7 @@ def test_wgrad(dtype, shape):
             assert rel(db, bd.sum(0)) < 2e-6
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
 def test_tensor_core_kernels_agree_with_ffma_kernels(dtype, monkeypatch):
     """bf16: tcgen05 results vs torch on the same bf16 inputs at a full-size shape (C2 rows)."""
     if dtype != torch.bfloat16:
@@ -107,7 +107,7 @@ def test_tensor_core_kernels_agree_with_ffma_kernels(dtype, monkeypatch):
     assert rel(dW, a.float().t() @ a.float()) < 2e-5
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
 def test_pool_views_ties_and_diversity(dtype):
     from ed_gated_gcn_b200 import ops
     batch, g = _batch_graph(21, 1, 30, seed=4)
@@ -133,7 +133,7 @@ def test_pool_views_ties_and_diversity(dtype):
     assert rel(xy, want) < 1e-6
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
 @pytest.mark.parametrize("i64", [False, True])
 def test_scores_kl(dtype, i64):
     from ed_gated_gcn_b200 import ops
