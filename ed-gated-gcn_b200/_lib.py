@@ -31,7 +31,7 @@ SIGNATURES = {
     "edg_csr_from_dense_fill": (c_int, [_P, c_int, _I, _I, _L, _L, _L, _P, _P, _P]),
     "edg_tree_dist": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "edg_dist_pad": (c_int, [_P, _P, _I, _I, c_int, _P, _P]),
-    "edg_aggregate": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, _P, c_int, _P]),
+    "edg_aggregate": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, _P, c_int, _P, _P, _I, _I, _P]),
     "edg_linear": (c_int, [_P, c_int, _L, _I, _I, _P, _L, _I, _P, c_int, _P, c_int, _L, _P]),
     "edg_wgrad_workspace": (_Z, [_I, _I, _I, c_int]),
     "edg_wgrad": (c_int, [_P, _L, _I, _P, _L, _I, c_int, _I, _P, _L, _P, c_int, c_int, _P, _Z, _P]),
@@ -84,8 +84,28 @@ def check(rc: int) -> None:
         raise EdgError(f"libedgcn status {rc}: {msg}")
 
 
+# kernels enqueued per C-ABI call (for the launch counter bench.py reports)
+def _kernels_of(name: str, args) -> int:
+    if name == "edg_wgrad":
+        return 2 + (2 if args[11] else 0)
+    if name == "edg_csr_from_heads":
+        return 3
+    if name in ("edg_csr_from_dense_count", "edg_diversity_fwd", "edg_colsum"):
+        return 2
+    if name == "edg_pool_fwd":
+        return (args[7] + 3) // 4
+    return 1
+
+
+LAUNCHES = {"calls": 0, "kernels": 0}
+HOOK = None          # bench.py installs a (name, args, fn) -> rc wrapper to time kernels with CUDA events
+
+
 def call(name: str, *args) -> None:
-    check(getattr(load(), name)(*args))
+    fn = getattr(load(), name)
+    LAUNCHES["calls"] += 1
+    LAUNCHES["kernels"] += _kernels_of(name, args)
+    check(HOOK(name, args, fn) if HOOK is not None else fn(*args))
 
 
 def ptr(t):

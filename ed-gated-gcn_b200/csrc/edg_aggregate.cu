@@ -6,6 +6,8 @@
 // request is a fully used 32-byte sector stream.  A row's neighbours live in the same
 // sentence (a few KB away), so the 2-3 extra row reads per output row hit L1/L2; compulsory
 // DRAM traffic is one read + one write of the [N,D] matrix plus 16 B/row of CSR.
+#include <stdlib.h>
+
 #include "edg_common.cuh"
 
 namespace edg {
@@ -29,7 +31,7 @@ template <> __device__ __forceinline__ void store_chunk<__nv_bfloat16, 4>(__nv_b
 
 template <typename TI, typename TO, int MODE>
 __global__ void __launch_bounds__(256)
-aggregate_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int N, int chunks,
+aggregate_flat_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int N, int chunks,
                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col) {
   constexpr int E = Vec16<TI>::kElems;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,19 +78,172 @@ aggregate_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int6
   store_chunk<TO, E>(y + (int64_t)row * ldy + c, acc);
 }
 
+// ---- shared-memory staged variant ------------------------------------------------------------
+// A block owns the sentences that START inside a window of `tile_rows` packed rows.  Those
+// sentences' rows are contiguous in memory, so ONE bulk asynchronous copy (cp.async.bulk, TMA
+// engine, mbarrier completion) stages them in shared memory; every neighbour of a staged row is
+// in the same sentence, hence also staged: the gathers are 128-bit shared-memory loads and each
+// hidden row leaves HBM/L2 exactly once.  Several blocks per SM overlap copy and gather.
+__device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <typename TI, typename TO, int MODE>
+__global__ void __launch_bounds__(256)
+aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int N, int B,
+                        int tile_rows, int cap_rows, const int32_t* __restrict__ sent_ptr,
+                        const int32_t* __restrict__ row_sent, const int32_t* __restrict__ row_ptr,
+                        const int32_t* __restrict__ col) {
+  constexpr int E = Vec16<TI>::kElems;
+  extern __shared__ __align__(128) uint8_t agg_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int range[2];
+  const int nthreads = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const size_t pitch = (size_t)ldx * sizeof(TI);
+  int32_t* rp_s = reinterpret_cast<int32_t*>(agg_smem + (size_t)cap_rows * pitch);   // [cap_rows + 1] (+3 pad)
+  int32_t* col_s = rp_s + cap_rows + 4;                                             // [4 * cap_rows]
+  float* inv_s = reinterpret_cast<float*>(col_s + 4 * cap_rows);                    // [cap_rows] 1/(deg+1)
+  const int cap_nnz = 4 * cap_rows;
+  if (tid == 0) {
+    // sentences that START in [w0, w1): first sentence starting at or after w0 / w1
+    const int w0 = blockIdx.x * tile_rows, w1 = w0 + tile_rows;
+    int s0 = B, s1 = B;
+    if (w0 < N) { s0 = row_sent[w0]; if (sent_ptr[s0] < w0) ++s0; }
+    if (w1 < N) { s1 = row_sent[w1]; if (sent_ptr[s1] < w1) ++s1; }
+    const int r0 = sent_ptr[s0], r1 = sent_ptr[s1];
+    range[0] = r0; range[1] = r1;
+    const uint32_t b32 = agg_smem_u32(&bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int n = r1 - r0;
+    if (n > 0 && n <= cap_rows) {
+      const uint32_t bytes = (uint32_t)n * (uint32_t)pitch;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(agg_smem_u32(agg_smem)), "l"(x + (int64_t)r0 * ldx), "r"(bytes), "r"(b32) : "memory");
+    }
+  }
+  __syncthreads();
+  const int r0 = range[0], r1 = range[1], n = r1 - r0;
+  if (n <= 0) return;
+  const bool staged = n <= cap_rows;          // a sentence longer than the buffer: gather from global instead
+  // the tile's slice of the CSR goes to shared memory too (coalesced), while the bulk copy is in flight:
+  // the per-row loop below then never waits on a dependent global load
+  bool csr_s = staged;
+  if (staged) {
+    for (int i = tid; i <= n; i += nthreads) rp_s[i] = __ldg(row_ptr + r0 + i);
+    __syncthreads();
+    const int e0 = rp_s[0], nnz = rp_s[n] - e0;
+    csr_s = nnz <= cap_nnz;
+    if (csr_s)
+      for (int i = tid; i < nnz; i += nthreads) col_s[i] = __ldg(col + e0 + i) - r0;   // tile-local row ids
+    for (int i = tid; i < n; i += nthreads) inv_s[i] = __frcp_rn((float)(rp_s[i + 1] - rp_s[i] + 1));
+    __syncthreads();
+    const uint32_t b32 = agg_smem_u32(&bar);
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(b32) : "memory");
+    }
+  }
+  const int c = threadIdx.x * E;
+  const uint8_t* xs = agg_smem + (size_t)c * sizeof(TI);
+  for (int lr = threadIdx.y; lr < n; lr += blockDim.y) {
+    const int row = r0 + lr;
+    int beg, end;
+    if (csr_s) { beg = rp_s[lr]; end = rp_s[lr + 1]; } else { beg = __ldg(row_ptr + row); end = __ldg(row_ptr + row + 1); }
+    const int e0 = csr_s ? rp_s[0] : 0;
+    float acc[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = 0.f;
+    for (int e = beg; e < end; e += 4) {
+      int nb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) nb[q] = (e + q < end) ? (csr_s ? col_s[e + q - e0] : __ldg(col + e + q) - r0) : -1;
+      uint4 raw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (nb[q] >= 0) {
+          if (staged) raw[q] = *reinterpret_cast<const uint4*>(xs + (size_t)nb[q] * pitch);
+          else raw[q] = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)(nb[q] + r0) * ldx + c));
+        }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (nb[q] < 0) continue;
+        float v[E];
+        if (sizeof(TI) == 2) {
+          const uint32_t wv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v[(2 * i) % E] = __uint_as_float(wv[i] << 16); v[(2 * i + 1) % E] = __uint_as_float(wv[i] & 0xffff0000u); }
+        } else {
+          v[0] = __uint_as_float(raw[q].x); v[1] = __uint_as_float(raw[q].y); v[2 % E] = __uint_as_float(raw[q].z); v[3 % E] = __uint_as_float(raw[q].w);
+        }
+        if (MODE == 1) {
+          const float wgt = staged ? inv_s[nb[q]]
+                                   : __frcp_rn((float)(__ldg(row_ptr + nb[q] + r0 + 1) - __ldg(row_ptr + nb[q] + r0) + 1));
+#pragma unroll
+          for (int k = 0; k < E; ++k) acc[k] = fmaf(v[k], wgt, acc[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < E; ++k) acc[k] += v[k];
+        }
+      }
+    }
+    if (MODE == 0) {
+      const float inv = staged ? inv_s[lr] : __frcp_rn((float)(end - beg + 1));      // 1 / (rowsum(adj) + 1), gcn.py:35
+#pragma unroll
+      for (int k = 0; k < E; ++k) acc[k] *= inv;
+    }
+    store_chunk<TO, E>(y + (int64_t)row * ldy + c, acc);
+  }
+}
+
+// experiment switch (bring-up only): EDG_AGG_VARIANT = 0 flat gather from global, 3 = shared-memory staged (default)
+static int agg_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EDG_AGG_VARIANT"); v = e ? atoi(e) : 3; }
+  return v;
+}
+
 template <typename TI, typename TO>
 static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, int N, int D,
-                            const int32_t* row_ptr, const int32_t* col, int mode, cudaStream_t s) {
+                            const int32_t* row_ptr, const int32_t* col, int mode, const int32_t* sent_ptr,
+                            const int32_t* row_sent, int B, int max_len, cudaStream_t s) {
   constexpr int E = Vec16<TI>::kElems;
   const int chunks = (D + E - 1) / E;
   if (ldx < (int64_t)chunks * E || ldy < (int64_t)chunks * E) return EDG_ERR_ALIGN;
-  const int64_t total = (int64_t)N * chunks;
-  const int64_t blocks = (total + 255) / 256;
-  if (blocks > 0x7fffffffll) return EDG_ERR_UNSUPPORTED;
-  if (mode == 0)
-    aggregate_kernel<TI, TO, 0><<<(unsigned)blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col);
-  else
-    aggregate_kernel<TI, TO, 1><<<(unsigned)blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col);
+  if (chunks > 256) return EDG_ERR_UNSUPPORTED;
+  const size_t pitch = (size_t)ldx * sizeof(TI);
+  // staged variant: ~72 KB windows (3 blocks per SM); falls back to the flat kernel when a
+  // sentence cannot fit next to a useful window
+  int cap_rows = (int)((72 * 1024) / (pitch + 24));
+  int tile_rows = cap_rows - max_len + 1;
+  if (tile_rows < 16) {
+    cap_rows = (int)((200 * 1024) / (pitch + 24));
+    tile_rows = cap_rows - max_len + 1;
+  }
+  const bool staged = agg_variant() == 3 && sent_ptr && row_sent && B > 0 && max_len > 0 && tile_rows >= 8;
+  if (!staged) {
+    const int64_t total = (int64_t)N * chunks;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (mode == 0) aggregate_flat_kernel<TI, TO, 0><<<blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col);
+    else aggregate_flat_kernel<TI, TO, 1><<<blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col);
+    return check_launch();
+  }
+  int rpb = 256 / chunks;
+  if (rpb > 32) rpb = 32;
+  dim3 block(chunks, rpb);
+  const size_t smem = (size_t)cap_rows * pitch + (size_t)(6 * cap_rows + 8) * sizeof(int32_t);
+  const unsigned blocks = (unsigned)((N + tile_rows - 1) / tile_rows);
+  auto k0 = aggregate_staged_kernel<TI, TO, 0>;
+  auto k1 = aggregate_staged_kernel<TI, TO, 1>;
+  static size_t attr0 = 0, attr1 = 0;         // largest dynamic smem opted into so far (per instantiation)
+  if (mode == 0) {
+    if (smem > attr0) { if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch(); attr0 = smem; }
+    k0<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col);
+  } else {
+    if (smem > attr1) { if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch(); attr1 = smem; }
+    k1<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col);
+  }
   return check_launch();
 }
 
@@ -98,15 +253,16 @@ using namespace edg;
 
 extern "C" int edg_aggregate(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
                              int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
+                             const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
                              edg_stream stream) {
   if (N < 0 || D <= 0 || (mode != 0 && mode != 1)) return EDG_ERR_ARG;
   if (N == 0) return EDG_OK;
   if (!x || !y || !row_ptr || !col) return EDG_ERR_ARG;
   if (!aligned16(x) || !aligned16(y) || !row_pitch_ok(x_dtype, ldx) || !row_pitch_ok(y_dtype, ldy)) return EDG_ERR_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == EDG_BF16 && y_dtype == EDG_BF16) return launch_aggregate<__nv_bfloat16, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, s);
-  if (x_dtype == EDG_F32 && y_dtype == EDG_F32) return launch_aggregate<float, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, s);
-  if (x_dtype == EDG_F32 && y_dtype == EDG_BF16) return launch_aggregate<float, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, s);
-  if (x_dtype == EDG_BF16 && y_dtype == EDG_F32) return launch_aggregate<__nv_bfloat16, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, s);
+  if (x_dtype == EDG_BF16 && y_dtype == EDG_BF16) return launch_aggregate<__nv_bfloat16, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, s);
+  if (x_dtype == EDG_F32 && y_dtype == EDG_F32) return launch_aggregate<float, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, s);
+  if (x_dtype == EDG_F32 && y_dtype == EDG_BF16) return launch_aggregate<float, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, s);
+  if (x_dtype == EDG_BF16 && y_dtype == EDG_F32) return launch_aggregate<__nv_bfloat16, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, s);
   return EDG_ERR_DTYPE;
 }

@@ -96,7 +96,8 @@ def graph_from_dense(adj: torch.Tensor, check: bool = True) -> DepGraph:
         L.call("edg_csr_from_dense_fill", L.ptr(adj), is64, B, T, adj.stride(0), adj.stride(1), adj.stride(2),
                L.ptr(row_ptr), L.ptr(col), L.stream())
     sent_ptr = torch.arange(0, rows + 1, T, dtype=torch.int32, device=dev)
-    return DepGraph(sent_ptr, row_ptr, col, None, B, rows, T, padded_T=T)
+    row_sent = torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(T)
+    return DepGraph(sent_ptr, row_ptr, col, row_sent, B, rows, T, padded_T=T)
 
 
 def tree_distance(graph: DepGraph, anchor_index: torch.Tensor, pad: Optional[str] = None,

@@ -53,7 +53,8 @@ def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype
     # the kernel walks 16-byte chunks of the INPUT dtype, so the output pitch must cover the same columns
     out = alloc_rows(N, D, out_dtype or x.dtype, x.device, min_ld=row_pitch(D, x.dtype))
     L.call("edg_aggregate", L.ptr(x), L.dt(x), ld(x), L.ptr(out), L.dt(out), ld(out), N, D,
-           L.ptr(graph.row_ptr), L.ptr(graph.col), mode, L.stream())
+           L.ptr(graph.row_ptr), L.ptr(graph.col), mode, L.ptr(graph.sent_ptr), L.ptr(graph.row_sent),
+           graph.n_graphs, graph.max_len, L.stream())
     return out
 
 

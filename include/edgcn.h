@@ -106,9 +106,13 @@ int edg_dist_pad(const int32_t* dist, const int32_t* sent_ptr, int32_t B, int32_
  * gcn.py:35,41 on the packed CSR.
  *   mode 0 (forward):  y[i] = 1/(deg_i+1) * sum_{j in row i} x[j]
  *   mode 1 (backward): y[j] = sum_{i in row j} x[i] / (deg_i+1)   (A symmetric)
- * x and y may differ in dtype; accumulation is fp32. */
+ * x and y may differ in dtype; accumulation is fp32.
+ * sent_ptr[B+1], row_sent[N] and max_len (longest sentence) enable the shared-memory staged
+ * kernel (rows of whole sentences are bulk-copied into shared memory once and gathered from
+ * there); pass NULL/0 to gather straight from global memory. */
 int edg_aggregate(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
                   int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
+                  const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
                   edg_stream stream);
 
 /* C[M,Nout] = act(A[M,K] * W^T + bias), W given as [Nout,K] with K contiguous
