@@ -86,6 +86,36 @@ aggregate_flat_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y,
 // hidden row leaves HBM/L2 exactly once.  Several blocks per SM overlap copy and gather.
 __device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// rows [r0, r1) straight from global memory (window overflow: a sentence longer than the buffer, or a
+// non-tree graph with more than 4 non-zeros per row on average)
+template <typename TI, typename TO, int MODE>
+__device__ __noinline__ void aggregate_rows_global(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy,
+                                                   int r0, int r1, const int32_t* __restrict__ row_ptr,
+                                                   const int32_t* __restrict__ col) {
+  constexpr int E = Vec16<TI>::kElems;
+  const int c = threadIdx.x * E;
+  for (int row = r0 + threadIdx.y; row < r1; row += blockDim.y) {
+    const int beg = __ldg(row_ptr + row), end = __ldg(row_ptr + row + 1);
+    float acc[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = 0.f;
+    for (int e = beg; e < end; ++e) {
+      const int j = __ldg(col + e);
+      float v[E];
+      Vec16<TI>::load(x + (int64_t)j * ldx + c, v);
+      const float w = (MODE == 1) ? __frcp_rn((float)(__ldg(row_ptr + j + 1) - __ldg(row_ptr + j) + 1)) : 1.f;
+#pragma unroll
+      for (int k = 0; k < E; ++k) acc[k] = fmaf(v[k], w, acc[k]);
+    }
+    if (MODE == 0) {
+      const float inv = __frcp_rn((float)(end - beg + 1));
+#pragma unroll
+      for (int k = 0; k < E; ++k) acc[k] *= inv;
+    }
+    store_chunk<TO, E>(y + (int64_t)row * ldy + c, acc);
+  }
+}
+
 template <typename TI, typename TO, int MODE>
 __global__ void __launch_bounds__(256)
 aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int N, int B,
@@ -98,11 +128,12 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
   __shared__ int range[2];
   const int nthreads = blockDim.x * blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const size_t pitch = (size_t)ldx * sizeof(TI);
+  const int pitch = (int)(ldx * (int64_t)sizeof(TI));                                // bytes per staged row
   int32_t* rp_s = reinterpret_cast<int32_t*>(agg_smem + (size_t)cap_rows * pitch);   // [cap_rows + 1] (+3 pad)
-  int32_t* col_s = rp_s + cap_rows + 4;                                             // [4 * cap_rows]
+  int32_t* col_s = rp_s + cap_rows + 4;                                             // [4 * cap_rows] tile-local ids
   float* inv_s = reinterpret_cast<float*>(col_s + 4 * cap_rows);                    // [cap_rows] 1/(deg+1)
   const int cap_nnz = 4 * cap_rows;
+  const uint32_t b32 = agg_smem_u32(&bar);
   if (tid == 0) {
     // sentences that START in [w0, w1): first sentence starting at or after w0 / w1
     const int w0 = blockIdx.x * tile_rows, w1 = w0 + tile_rows;
@@ -111,7 +142,6 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
     if (w1 < N) { s1 = row_sent[w1]; if (sent_ptr[s1] < w1) ++s1; }
     const int r0 = sent_ptr[s0], r1 = sent_ptr[s1];
     range[0] = r0; range[1] = r1;
-    const uint32_t b32 = agg_smem_u32(&bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const int n = r1 - r0;
@@ -125,75 +155,68 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
   __syncthreads();
   const int r0 = range[0], r1 = range[1], n = r1 - r0;
   if (n <= 0) return;
-  const bool staged = n <= cap_rows;          // a sentence longer than the buffer: gather from global instead
-  // the tile's slice of the CSR goes to shared memory too (coalesced), while the bulk copy is in flight:
-  // the per-row loop below then never waits on a dependent global load
-  bool csr_s = staged;
-  if (staged) {
-    for (int i = tid; i <= n; i += nthreads) rp_s[i] = __ldg(row_ptr + r0 + i);
-    __syncthreads();
-    const int e0 = rp_s[0], nnz = rp_s[n] - e0;
-    csr_s = nnz <= cap_nnz;
-    if (csr_s)
-      for (int i = tid; i < nnz; i += nthreads) col_s[i] = __ldg(col + e0 + i) - r0;   // tile-local row ids
-    for (int i = tid; i < n; i += nthreads) inv_s[i] = __frcp_rn((float)(rp_s[i + 1] - rp_s[i] + 1));
-    __syncthreads();
-    const uint32_t b32 = agg_smem_u32(&bar);
+  if (n > cap_rows) {                               // nothing was staged
+    aggregate_rows_global<TI, TO, MODE>(x, ldx, y, ldy, r0, r1, row_ptr, col);
+    return;
+  }
+  // the tile's slice of the CSR (as tile-local ids) and 1/(deg+1) go to shared memory while the bulk copy flies
+  for (int i = tid; i <= n; i += nthreads) rp_s[i] = __ldg(row_ptr + r0 + i);
+  __syncthreads();
+  const int e0 = rp_s[0], nnz = rp_s[n] - e0;
+  const bool fits = nnz <= cap_nnz;
+  if (fits)
+    for (int i = tid; i < nnz; i += nthreads) col_s[i] = __ldg(col + e0 + i) - r0;
+  for (int i = tid; i < n; i += nthreads) inv_s[i] = __frcp_rn((float)(rp_s[i + 1] - rp_s[i] + 1));
+  __syncthreads();
+  {
     uint32_t ok = 0;
     while (!ok) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(ok) : "r"(b32) : "memory");
     }
   }
-  const int c = threadIdx.x * E;
-  const uint8_t* xs = agg_smem + (size_t)c * sizeof(TI);
-  for (int lr = threadIdx.y; lr < n; lr += blockDim.y) {
-    const int row = r0 + lr;
-    int beg, end;
-    if (csr_s) { beg = rp_s[lr]; end = rp_s[lr + 1]; } else { beg = __ldg(row_ptr + row); end = __ldg(row_ptr + row + 1); }
-    const int e0 = csr_s ? rp_s[0] : 0;
+  if (!fits) {                                      // dense-ish graph: keep the staged copy unused, gather from global
+    aggregate_rows_global<TI, TO, MODE>(x, ldx, y, ldy, r0, r1, row_ptr, col);
+    return;
+  }
+  // ---- hot loop: shared memory only -------------------------------------------------------------------
+  const uint32_t xs = agg_smem_u32(agg_smem) + threadIdx.x * 16;     // this thread's 16-byte column of the window
+  TO* yrow = y + (int64_t)(r0 + (int)threadIdx.y) * ldy + threadIdx.x * E;
+  const int64_t ystep = (int64_t)blockDim.y * ldy;
+  for (int lr = threadIdx.y; lr < n; lr += blockDim.y, yrow += ystep) {
+    const int beg = rp_s[lr] - e0, end = rp_s[lr + 1] - e0;
     float acc[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = 0.f;
-    for (int e = beg; e < end; e += 4) {
-      int nb[4];
+#pragma unroll 2
+    for (int e = beg; e < end; ++e) {
+      const int j = col_s[e];
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(xs + (uint32_t)(j * pitch)));
+      float v[8];
+      if (sizeof(TI) == 2) {
+        v[0] = __uint_as_float(w0 << 16); v[1] = __uint_as_float(w0 & 0xffff0000u);
+        v[2] = __uint_as_float(w1 << 16); v[3] = __uint_as_float(w1 & 0xffff0000u);
+        v[4] = __uint_as_float(w2 << 16); v[5] = __uint_as_float(w2 & 0xffff0000u);
+        v[6] = __uint_as_float(w3 << 16); v[7] = __uint_as_float(w3 & 0xffff0000u);
+      } else {
+        v[0] = __uint_as_float(w0); v[1] = __uint_as_float(w1); v[2] = __uint_as_float(w2); v[3] = __uint_as_float(w3);
+      }
+      if (MODE == 1) {
+        const float wgt = inv_s[j];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) nb[q] = (e + q < end) ? (csr_s ? col_s[e + q - e0] : __ldg(col + e + q) - r0) : -1;
-      uint4 raw[4];
+        for (int k = 0; k < E; ++k) acc[k] = fmaf(v[k], wgt, acc[k]);
+      } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (nb[q] >= 0) {
-          if (staged) raw[q] = *reinterpret_cast<const uint4*>(xs + (size_t)nb[q] * pitch);
-          else raw[q] = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)(nb[q] + r0) * ldx + c));
-        }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (nb[q] < 0) continue;
-        float v[E];
-        if (sizeof(TI) == 2) {
-          const uint32_t wv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { v[(2 * i) % E] = __uint_as_float(wv[i] << 16); v[(2 * i + 1) % E] = __uint_as_float(wv[i] & 0xffff0000u); }
-        } else {
-          v[0] = __uint_as_float(raw[q].x); v[1] = __uint_as_float(raw[q].y); v[2 % E] = __uint_as_float(raw[q].z); v[3 % E] = __uint_as_float(raw[q].w);
-        }
-        if (MODE == 1) {
-          const float wgt = staged ? inv_s[nb[q]]
-                                   : __frcp_rn((float)(__ldg(row_ptr + nb[q] + r0 + 1) - __ldg(row_ptr + nb[q] + r0) + 1));
-#pragma unroll
-          for (int k = 0; k < E; ++k) acc[k] = fmaf(v[k], wgt, acc[k]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < E; ++k) acc[k] += v[k];
-        }
+        for (int k = 0; k < E; ++k) acc[k] += v[k];
       }
     }
     if (MODE == 0) {
-      const float inv = staged ? inv_s[lr] : __frcp_rn((float)(end - beg + 1));      // 1 / (rowsum(adj) + 1), gcn.py:35
+      const float inv = inv_s[lr];                 // 1 / (rowsum(adj) + 1), gcn.py:35
 #pragma unroll
       for (int k = 0; k < E; ++k) acc[k] *= inv;
     }
-    store_chunk<TO, E>(y + (int64_t)row * ldy + c, acc);
+    store_chunk<TO, E>(yrow, acc);
   }
 }
 

@@ -58,22 +58,23 @@ pool_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict_
       best[v][k] = -INFINITY;
       where[v][k] = beg < end ? beg : -1;
     }
-  for (int t = beg; t < end; t += 2) {
-    float f0[E], f1[E];
-    Vec16<T>::load(h + (int64_t)t * ldh + c, f0);
-    const bool two = (t + 1 < end);
-    if (two) Vec16<T>::load(h + (int64_t)(t + 1) * ldh + c, f1);
+  constexpr int U = 4;                        // rows in flight per thread (memory-level parallelism)
+  for (int t = beg; t < end; t += U) {
+    float f[U][E];
 #pragma unroll
-    for (int v = 0; v < V; ++v)
+    for (int u = 0; u < U; ++u)
+      if (t + u < end) Vec16<T>::load(h + (int64_t)(t + u) * ldh + c, f[u]);
 #pragma unroll
-      for (int k = 0; k < E; ++k) {
-        const float a = f0[k] * g[v][k];
-        if (a > best[v][k]) { best[v][k] = a; where[v][k] = t; }     // strict: first row wins ties
-        if (two) {
-          const float a1 = f1[k] * g[v][k];
-          if (a1 > best[v][k]) { best[v][k] = a1; where[v][k] = t + 1; }
+    for (int u = 0; u < U; ++u) {
+      if (t + u >= end) break;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          const float a = f[u][k] * g[v][k];
+          if (a > best[v][k]) { best[v][k] = a; where[v][k] = t + u; }     // strict: first row wins ties
         }
-      }
+    }
   }
 #pragma unroll
   for (int v = 0; v < V; ++v)
@@ -195,19 +196,34 @@ scores_kl_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
                     ? __ldg(gate + (int64_t)b * D + c + k) * __ldg(vvec + (int64_t)b * D + c + k) : 0.f;
   }
   const float cb = cvec ? __ldg(cvec + b) : 0.f;
-  for (int t = beg; t < end; ++t) {
-    float s = 0.f;
+  constexpr int U = 4;                        // rows in flight per warp
+  for (int t = beg; t < end; t += U) {
+    float sacc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) sacc[u] = 0.f;
 #pragma unroll
     for (int q = 0; q < kMaxQ; ++q) {
       if (lane + 32 * q < chunks) {
-        float f[E];
-        Vec16<T>::load(h + (int64_t)t * ldh + (lane + 32 * q) * E, f);
+        float f[U][E];
 #pragma unroll
-        for (int k = 0; k < E; ++k) s = fmaf(f[k], w[q][k], s);
+        for (int u = 0; u < U; ++u)
+          if (t + u < end) Vec16<T>::load(h + (int64_t)(t + u) * ldh + (lane + 32 * q) * E, f[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (t + u < end) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) sacc[u] = fmaf(f[u][k], w[q][k], sacc[u]);
+          }
       }
     }
-    s = warp_sum(s);
-    if (lane == 0) scores[t] = s + cb;
+#pragma unroll
+    for (int u = 0; u < U; ++u) sacc[u] = warp_sum(sacc[u]);
+    if (lane < U && t + lane < end) {
+      float mine = sacc[0];
+#pragma unroll
+      for (int u = 1; u < U; ++u) mine = (lane == u) ? sacc[u] : mine;
+      scores[t + lane] = mine + cb;
+    }
   }
   __syncwarp();
   float ms, zs, mq, zq;
@@ -274,21 +290,32 @@ head_bwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict_
     where[k] = (ok && g_pooled) ? __ldg(arg + o) : -1;
     ag[k] = 0.f; av[k] = 0.f;
   }
-  for (int t = beg; t < end; ++t) {
-    float f[E], gx[E], o[E];
-    Vec16<T>::load(h + (int64_t)t * ldh + c, f);
-    if (g_xout) Vec16<T>::load(g_xout + (int64_t)t * ldgx + c, gx);
-    const float dst = ds[t - beg];
+  constexpr int U = 4;                        // rows in flight per thread
+  for (int t0 = beg; t0 < end; t0 += U) {
+    float f[U][E], gx[U][E];
 #pragma unroll
-    for (int k = 0; k < E; ++k) {
-      float coef = dst * vv[k];
-      if (where[k] == t) coef += gp[k];
-      if (g_xout) coef += gx[k];
-      o[k] = g[k] * coef;
-      ag[k] = fmaf(f[k], coef, ag[k]);
-      av[k] = fmaf(dst * f[k], g[k], av[k]);
+    for (int u = 0; u < U; ++u)
+      if (t0 + u < end) {
+        Vec16<T>::load(h + (int64_t)(t0 + u) * ldh + c, f[u]);
+        if (g_xout) Vec16<T>::load(g_xout + (int64_t)(t0 + u) * ldgx + c, gx[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u;
+      if (t >= end) break;
+      float o[E];
+      const float dst = ds[t - beg];
+#pragma unroll
+      for (int k = 0; k < E; ++k) {
+        float coef = dst * vv[k];
+        if (where[k] == t) coef += gp[k];
+        if (g_xout) coef += gx[u][k];
+        o[k] = g[k] * coef;
+        ag[k] = fmaf(f[u][k], coef, ag[k]);
+        av[k] = fmaf(dst * f[u][k], g[k], av[k]);
+      }
+      if (dh) Vec16<T>::store(dh + (int64_t)t * lddh + c, o);
     }
-    if (dh) Vec16<T>::store(dh + (int64_t)t * lddh + c, o);
   }
 #pragma unroll
   for (int k = 0; k < E; ++k)
