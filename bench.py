@@ -186,6 +186,10 @@ def run_b200(args):
 
     c, batch, x_host, tgt_host = make_workload(args.config, rank)
     cd = torch.bfloat16 if c["dtype"] == "bf16" else torch.float32
+    if cd == torch.bfloat16:
+        # the caller's own classifier head (self.dense, bert_amir5.py:643) is host torch: let cuBLAS use TF32
+        # tensor cores for it in the bf16 configuration (the fp32 parity mode keeps full fp32)
+        torch.backends.cuda.matmul.allow_tf32 = True
     stack, dense = build_model(c, dev)
     params = list(stack.parameters()) + list(dense.parameters())
     if world > 1:
@@ -197,8 +201,10 @@ def run_b200(args):
     head_params = list(dense.parameters())
 
     # ---- device-resident inputs (the `value` number)
-    x_dev = ops.alloc_rows(batch.n_rows, c["D"], cd, dev, zero=True)
-    x_dev.copy_(x_host)
+    # the whole padded [N, pitch] allocation is the leaf: its gradient comes back dense, so autograd keeps
+    # it without the strided copy a [:, :D] view would need
+    x_dev = torch.zeros(batch.n_rows, ops.row_pitch(c["D"], cd), dtype=cd, device=dev)
+    x_dev[:, :c["D"]].copy_(x_host)
     x_dev.requires_grad_(True)
     graph = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=dev)
     anchor = torch.from_numpy(batch.anchor).to(dev)
@@ -228,7 +234,7 @@ def run_b200(args):
 
     def step_e2e_enqueue():
         opt.zero_grad(set_to_none=True)
-        xb = x_pin.to(dev, non_blocking=True)[:, :c["D"]].requires_grad_(True)
+        xb = x_pin.to(dev, non_blocking=True).requires_grad_(True)
         g = E.build_graph(heads_pin.to(dev, non_blocking=True), sp_pin.to(dev, non_blocking=True), max_len=max_len,
                           device=dev)
         an = anchor_pin.to(dev, non_blocking=True)

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128)
 scores_kl_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr, int B, int D,
                      int chunks, const float* __restrict__ gate, const float* __restrict__ vvec,
                      const float* __restrict__ cvec, const void* __restrict__ dist, float* __restrict__ scores,
-                     float* __restrict__ kl_b) {
+                     float* __restrict__ kl_b, float* __restrict__ dv_unit, float* __restrict__ dc_unit) {
   constexpr int E = Vec16<T>::kElems;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -233,6 +233,39 @@ scores_kl_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
     acc += (expf(scores[t] - ms) / zs) * (expf(dist_at<I64>(dist, t) - mq) / zq);
   acc = warp_sum(acc);
   if (lane == 0) kl_b[b] = acc;
+  if (dv_unit == nullptr) return;
+  // d kl / d v_b and d kl / d c_b per unit upstream gradient (the backward pass only scales them):
+  //   u_t = P_t (Q_t - kl_b) / B,  dv_unit[d] = sum_t u_t h[t,d] gate[d],  dc_unit = sum_t u_t
+  // second sweep over the sentence's rows (just read: L1/L2 hits)
+  const float klb = acc, invB = 1.0f / (float)B;
+  float dvu[kMaxQ][E];
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q)
+#pragma unroll
+    for (int k = 0; k < E; ++k) dvu[q][k] = 0.f;
+  float dcu = 0.f;
+  for (int t = beg; t < end; ++t) {
+    const float u = (expf(scores[t] - ms) / zs) * ((expf(dist_at<I64>(dist, t) - mq) / zq) - klb) * invB;
+    dcu += u;
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q) {
+      if (lane + 32 * q < chunks) {
+        float f[E];
+        Vec16<T>::load(h + (int64_t)t * ldh + (lane + 32 * q) * E, f);
+#pragma unroll
+        for (int k = 0; k < E; ++k) dvu[q][k] = fmaf(u, f[k], dvu[q][k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q) {
+    const int c = (lane + 32 * q) * E;
+#pragma unroll
+    for (int k = 0; k < E; ++k)
+      if (lane + 32 * q < chunks && c + k < D)
+        dv_unit[(int64_t)b * D + c + k] = dvu[q][k] * __ldg(gate + (int64_t)b * D + c + k);
+  }
+  if (lane == 0 && dc_unit) dc_unit[b] = dcu;
 }
 
 // one block per sentence; phase 1: ds[t] into shared memory; phase 2: thread = 16-byte
@@ -473,7 +506,7 @@ extern "C" int edg_views_bwd(const float* pooled, const int32_t* arg, const floa
 extern "C" int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                                  int32_t D, const float* gate, const float* v, const float* c,
                                  const void* dist, int dist_i64, float* scores, float* kl_b,
-                                 edg_stream stream) {
+                                 float* dv_unit, float* dc_unit, edg_stream stream) {
   if (B < 0 || D <= 0) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
   if (!h || !sent_ptr || !gate || !v || !dist || !scores || !kl_b) return EDG_ERR_ARG;
@@ -484,8 +517,8 @@ extern "C" int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const in
     constexpr int E = Vec16<T>::kElems;
     const int chunks = (D + E - 1) / E;
     if (chunks > 32 * kMaxQ) return EDG_ERR_UNSUPPORTED;
-    if (dist_i64) scores_kl_fwd_kernel<T, 1><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b);
-    else scores_kl_fwd_kernel<T, 0><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b);
+    if (dist_i64) scores_kl_fwd_kernel<T, 1><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit);
+    else scores_kl_fwd_kernel<T, 0><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit);
   })
   return check_launch();
 }

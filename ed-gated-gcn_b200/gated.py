@@ -58,7 +58,8 @@ class _GatedStackFn(torch.autograd.Function):
         cd: torch.dtype = cfg["cdtype"]
         Lyr, pairs, lead = cfg["L"], cfg["pairs"], cfg["lead"]
         anchor, dist, logits_fn = cfg["anchor"], cfg["dist"], cfg["logits_fn"]
-        B, N, D = graph.n_graphs, graph.n_rows, x.shape[1]
+        D = cfg["D"]
+        B, N = graph.n_graphs, graph.n_rows
         gcn_p = [(params[2 * l], params[2 * l + 1]) for l in range(Lyr)]
         o = 2 * Lyr
         gate_p = [[(params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]) for i in range(pairs)]
@@ -66,7 +67,10 @@ class _GatedStackFn(torch.autograd.Function):
         o += 2 * Lyr * pairs
         fc_w, fc_b = params[o], params[o + 1]
 
-        xr = ops.as_rows(x, cd)
+        # x is [N, D], or the whole padded allocation [N, pitch >= D] (then dx comes back in the same dense
+        # layout and autograd can keep it without a copy)
+        ctx.x_padded = x.shape[1] != D
+        xr = ops.as_rows(x[:, :D] if ctx.x_padded else x, cd)
         # ---- trigger vector and the gate MLPs (bert_amir5.py:615-622)
         a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
         gates = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
@@ -108,7 +112,10 @@ class _GatedStackFn(torch.autograd.Function):
             v = lg @ fc_w[:, :D].float()                                           # [B,D]
             c = (lg * (a_leaf @ fc_w[:, D:].float().t() + fc_b.float())).sum(1)    # [B]
         # ---- importance scores and the softmax product (:645-648)
-        scores, kl_b, kl = ops.scores_kl_fwd(hs[-1], graph, gL, v.detach().contiguous(), c.detach().contiguous(), dist)
+        # (also d kl/d v, d kl/d c per unit gradient: saves the backward pass one sweep over h_L)
+        scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hs[-1], graph, gL, v.detach().contiguous(),
+                                                       c.detach().contiguous(), dist, want_units=True)
+        ctx.kl_units = (dvu, dcu)
         x_out = ops.gate_rows(hs[-1], graph, gL, cd) if cfg["return_x_out"] else None
 
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not zero tensors
@@ -117,6 +124,7 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.gate_saved = gate_saved
         ctx.n_params = len(params)
         ctx.x_dtype = x.dtype
+        ctx.x_cols = x.shape[1]
         ctx.save_for_backward(xr, gates, v_pooled, v_arg, p_arg, scores, kl_b, *ms, *hs, *params)
         # arg-max rows (global row ids), like the indices torch.max returns at :635-636/:640
         ctx.mark_non_differentiable(p_arg, v_arg)
@@ -149,7 +157,9 @@ class _GatedStackFn(torch.autograd.Function):
         need_scores = g_kl is not None or g_scores is not None
         # ---- pass A over h_L: dv, dc (inputs of the host head's backward)
         dv = dc = None
-        if need_scores:
+        if need_scores and g_scores is None:
+            dv, dc = ctx.kl_units[0] * g_kl, ctx.kl_units[1] * g_kl          # precomputed in the forward sweep
+        elif need_scores:
             _, _, dv, dc = ops.head_bwd(hL, graph, gL, v.detach().contiguous(), dist, scores, kl_b, g_kl, g_scores,
                                         None, None, None, want_dh=False, want_dv=True)
         # ---- host head backward: logits_fn, v, c  ->  d a, d pooled, and .grad of the head's own parameters
@@ -221,6 +231,12 @@ class _GatedStackFn(torch.autograd.Function):
             da += dz
         ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
         grads_out[-2], grads_out[-1] = d_fcw, d_fcb
+        if ctx.x_padded:        # hand back the whole [N, pitch] allocation (padding columns are finite)
+            dx = dx.as_strided((N, dx.stride(0)), (dx.stride(0), 1))
+            if dx.shape[1] != ctx.x_cols:
+                full = torch.zeros((N, ctx.x_cols), dtype=dx.dtype, device=dev)
+                full[:, :D] = dx[:, :D]
+                dx = full
         if dx.dtype != ctx.x_dtype:
             dx = dx.to(ctx.x_dtype)
         return (None, dx) + tuple(grads_out)
@@ -280,7 +296,9 @@ class GatedGCNStack(nn.Module):
             dist = dist.long()
         dist = dist.contiguous()
         lead, pairs = GATE_ARCHS[self.gate_arch]
-        cfg = dict(graph=graph, cdtype=self.compute_dtype, L=self.n_layers, pairs=pairs, lead=lead,
+        if x.shape[-1] != self.hidden and x.shape[-1] != ops.row_pitch(self.hidden, x.dtype):
+            raise L.EdgError(f"expected {self.hidden} feature columns (or the padded pitch), got {x.shape[-1]}")
+        cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
                    head_params=list(head_params), relu=self.relu, return_x_out=return_x_out)
         logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params())

@@ -153,15 +153,19 @@ def _dist_flag(dist: torch.Tensor) -> int:
     raise L.EdgError("dist_to_target must be int32 or int64")
 
 
-def scores_kl_fwd(h, graph, gate, v, c, dist):
+def scores_kl_fwd(h, graph, gate, v, c, dist, want_units: bool = False):
     B, D = gate.shape
     N = h.shape[0]
     scores = torch.empty((N,), dtype=torch.float32, device=h.device)
     kl_b = torch.empty((B,), dtype=torch.float32, device=h.device)
+    dvu = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_units else None
+    dcu = torch.empty((B,), dtype=torch.float32, device=h.device) if want_units else None
     L.call("edg_scores_kl_fwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(v),
-           L.ptr(c), L.ptr(dist), _dist_flag(dist), L.ptr(scores), L.ptr(kl_b), L.stream())
+           L.ptr(c), L.ptr(dist), _dist_flag(dist), L.ptr(scores), L.ptr(kl_b), L.ptr(dvu), L.ptr(dcu), L.stream())
     kl = torch.empty((), dtype=torch.float32, device=h.device)
     L.call("edg_sum_scaled", L.ptr(kl_b), B, 1.0 / B, L.ptr(kl), L.stream())
+    if want_units:
+        return scores, kl_b, kl, dvu, dcu
     return scores, kl_b, kl
 
 

@@ -177,11 +177,13 @@ int edg_views_bwd(const float* pooled, const int32_t* arg, const float* gates, c
 /* bert_amir5.py:645-648 in collapsed form:
  *   scores[i] = sum_d h[i,d]*gate[b,d]*v[b,d] + c[b]
  *   kl_b[b]   = sum_t softmax_t(scores)*softmax_t(float(dist))
- * dist is packed int32 (dist_i64 = 0) or int64. */
+ * dist is packed int32 (dist_i64 = 0) or int64.
+ * Optional (NULL to skip): dv_unit[B,D], dc_unit[B] = d kl / d v, d kl / d c per unit upstream
+ * gradient, so that the backward pass needs no extra sweep over h when only kl carries gradient. */
 int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                       int32_t D, const float* gate, const float* v, const float* c,
                       const void* dist, int dist_i64, float* scores, float* kl_b,
-                      edg_stream stream);
+                      float* dv_unit, float* dc_unit, edg_stream stream);
 
 /* backward of x_out = gate*h_L through scores/kl, the final max-pool and an
  * optional direct gradient on x_out:
