@@ -26,7 +26,7 @@ size_t wgrad_simt_workspace(int R, int K1, int K2);
 int launch_linear_tc(const void* A, int64_t lda, int M, int K, const void* W, int64_t ldw, int Nout,
                      const float* bias, int act, void* C, int c_dtype, int64_t ldc, cudaStream_t s);
 int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, float* dW,
-                    int64_t lddw, int accumulate, float* ws, cudaStream_t s);
+                    int64_t lddw, float* dbias, int bias_of, int accumulate, float* ws, cudaStream_t s);
 size_t wgrad_tc_workspace(int R, int K1, int K2);
 
 // Bring-up switch for the GPU tests only: EDG_FORCE_SIMT=1 routes bf16 GEMMs through the FFMA
@@ -113,7 +113,7 @@ extern "C" int edg_wgrad(const void* A, int64_t lda, int32_t K1, const void* B, 
   const bool tc = (dtype == EDG_BF16) && !force_simt();
   size_t gemm_ws = tc ? wgrad_tc_workspace(R, K1, K2) : wgrad_simt_workspace(R, K1, K2);
   if (dtype == EDG_F32) rc = launch_wgrad_simt<float>(A, lda, K1, B, ldb, K2, R, dW, lddw, accumulate, (float*)ws, s);
-  else if (tc) rc = launch_wgrad_tc(A, lda, K1, B, ldb, K2, R, dW, lddw, accumulate, (float*)ws, s);
+  else if (tc) return launch_wgrad_tc(A, lda, K1, B, ldb, K2, R, dW, lddw, dbias, bias_of, accumulate, (float*)ws, s);
   else rc = launch_wgrad_simt<__nv_bfloat16>(A, lda, K1, B, ldb, K2, R, dW, lddw, accumulate, (float*)ws, s);
   if (rc) return rc;
   if (bias_of) {

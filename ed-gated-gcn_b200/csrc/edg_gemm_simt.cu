@@ -181,6 +181,31 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int chunk
   out[c] = accumulate ? out[c] + s : s;
 }
 
+// as split_reduce, for partials of extended shape [K1e, K2e] whose extra row (bias_of 2) or column (bias_of 1)
+// holds the bias gradient
+__global__ void split_reduce_bias_kernel(const float* __restrict__ partial, int splits, int K1, int K2, int K1e, int K2e,
+                                         float* __restrict__ dW, int64_t lddw, float* __restrict__ dbias, int bias_of,
+                                         int accumulate) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = (int64_t)K1e * K2e;
+  if (idx >= tot) return;
+  const int m = (int)(idx / K2e), n = (int)(idx - (int64_t)m * K2e);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * tot + idx];
+  float* o = nullptr;
+  if (m < K1 && n < K2) o = dW + (int64_t)m * lddw + n;
+  else if (bias_of == 2 && m == K1 && n < K2) o = dbias + n;
+  else if (bias_of == 1 && n == K2 && m < K1) o = dbias + m;
+  if (o) *o = accumulate ? (*o + s) : s;
+}
+
+void launch_split_reduce_bias(const float* partial, int splits, int K1, int K2, int K1e, int K2e, float* dW, int64_t lddw,
+                              float* dbias, int bias_of, int accumulate, cudaStream_t s) {
+  const int64_t tot = (int64_t)K1e * K2e;
+  split_reduce_bias_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(partial, splits, K1, K2, K1e, K2e, dW, lddw, dbias,
+                                                                         bias_of, accumulate);
+}
+
 void launch_split_reduce(const float* partial, int splits, int K1, int K2, float* dW, int64_t lddw, int accumulate,
                          cudaStream_t s) {
   const int64_t tot = (int64_t)K1 * K2;

@@ -10,6 +10,7 @@
 // linear_tc is persistent over (m,n) tiles with two TMEM accumulator stages, so the epilogue
 // of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "edg_common.cuh"
 
@@ -83,7 +84,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread `lane` gets row (lane quarter base + lane).
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -93,8 +94,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version = 1):
 //   [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 |
@@ -133,7 +134,8 @@ constexpr int kBBytesMax = 256 * kBlockK * 2;     // 32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax; // 48 KB
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                   // TMEM columns per accumulator stage
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // wgrad: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kLinThreads = 320;       // linear: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int kMaxBias = 1024;
 constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kMaxBias * sizeof(float) + 256;
 
@@ -171,8 +173,44 @@ template <> struct OutVec<__nv_bfloat16> {
 // ---------------------------------------------------------------------------------------------
 // linear_tc
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == EDG_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-x));
+  if (act == EDG_ACT_RELU) return fmaxf(x, 0.f);
+  return x;
+}
+
+// one 32-column chunk of one accumulator row -> bias, activation, convert, 128-bit stores
 template <typename TC>
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int col0, int Nout, int64_t ldc, int act,
+                                               const float* __restrict__ bias_s, TC* __restrict__ crow) {
+  constexpr int G = OutVec<TC>::G;
+  if (col0 + 32 <= Nout) {                      // interior chunk: no per-element guards
+#pragma unroll
+    for (int g = 0; g < 32; g += G) {
+      float v[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) v[j] = apply_act(__uint_as_float(r[g + j]) + bias_s[col0 + g + j], act);
+      OutVec<TC>::store(crow + col0 + g, v);
+    }
+  } else {                                      // last chunk of the row: zero the padding, skip what is past ldc
+#pragma unroll
+    for (int g = 0; g < 32; g += G) {
+      const int col = col0 + g;
+      if (col + G <= ldc) {
+        float v[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const int cj = col + j;
+          v[j] = (cj < Nout) ? apply_act(__uint_as_float(r[g + j]) + bias_s[cj < kMaxBias ? cj : 0], act) : 0.f;
+        }
+        OutVec<TC>::store(crow + col, v);
+      }
+    }
+  }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(kLinThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  int M, int K, int Nout, int block_n, int n_tiles, int num_tiles, uint32_t idesc,
                  const float* __restrict__ bias, int act, TC* __restrict__ C, int64_t ldc) {
@@ -183,12 +221,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (L.bias() - smem_u32(smem_raw)));
 
-  for (int i = threadIdx.x; i < Nout && i < kMaxBias; i += kThreads) bias_s[i] = bias ? bias[i] : 0.f;
+  for (int i = threadIdx.x; i < kMaxBias; i += kLinThreads) bias_s[i] = (bias && i < Nout) ? bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < kStages; ++s) { mbar_init(L.full(s), 1); mbar_init(L.empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull(s), 1); mbar_init(L.tempty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull(s), 1); mbar_init(L.tempty(s), 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(L.tmem_slot(), kTmemCols);
@@ -239,7 +277,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else {
-    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    // 8 epilogue warps: warp w reads TMEM lane quarter (w & 3); the two warps of a quarter take alternate
+    // 32-column chunks.  TMEM loads are software-pipelined one chunk ahead of the arithmetic.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int n_chunks = (block_n + 31) / 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -248,34 +290,164 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(L.tfull(as), aphase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
-      TC* crow = C + (int64_t)row * ldc;
-      for (int c0 = 0; c0 < block_n; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride + c0, r);
-        if (row < M) {
-          constexpr int G = OutVec<TC>::G;
-#pragma unroll
-          for (int g = 0; g < 32; g += G) {
-            const int col = n0 + c0 + g;
-            if (c0 + g < block_n && col + G <= ldc) {
-              float v[G];
-#pragma unroll
-              for (int j = 0; j < G; ++j) {
-                float x = __uint_as_float(r[g + j]);
-                const int cj = col + j;
-                if (cj < Nout) {
-                  x += bias_s[cj < kMaxBias ? cj : 0];
-                  if (act == EDG_ACT_SIGMOID) x = sigmoidf_(x);
-                  else if (act == EDG_ACT_RELU) x = fmaxf(x, 0.f);
-                } else {
-                  x = 0.f;                       // keep the row padding finite and zero
-                }
-                v[j] = x;
-              }
-              OutVec<TC>::store(crow + col, v);
-            }
-          }
+      const bool row_ok = row < M;
+      TC* crow = C + (int64_t)(row_ok ? row : 0) * ldc;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride;
+      uint32_t ra[32], rb[32];
+      int ci = half;
+      if (ci < n_chunks) tmem_ld_32x32_nowait(tbase + ci * 32, ra);
+      while (ci < n_chunks) {
+        tmem_wait_ld();
+        const int nxt = ci + 2;
+        if (nxt < n_chunks) tmem_ld_32x32_nowait(tbase + nxt * 32, rb);
+        if (row_ok && n0 + ci * 32 < ldc) epilogue_chunk<TC>(ra, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
+        ci = nxt;
+        if (ci >= n_chunks) break;
+        tmem_wait_ld();
+        const int nx2 = ci + 2;
+        if (nx2 < n_chunks) tmem_ld_32x32_nowait(tbase + nx2 * 32, ra);
+        if (row_ok && n0 + ci * 32 < ldc) epilogue_chunk<TC>(rb, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
+        ci = nx2;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(L.tempty(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// linear_ws : the same GEMM with the WEIGHT TILE STATIONARY in shared memory.
+// At D = 300 the streaming kernel above re-reads its [block_n x K] weight tile from L2 for every M tile
+// (100 KB per 40 KB of output) and is L2-bandwidth bound.  Here CTA c keeps the weight rows of ONE N tile
+// (c % n_tiles) resident for its whole life and walks the M tiles c / n_tiles, + gridDim/n_tiles, ...; only
+// the activation tiles stream through the TMA ring.  The CTAs of the same M tile run side by side, so the
+// second read of an activation tile is an L2 hit.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWsMaxStages = 8;
+struct WsLayout {
+  uint32_t base; int w_bytes_kb; int num_kb; int stages;
+  __device__ uint32_t w(int kb) const { return base + kb * w_bytes_kb; }
+  __device__ uint32_t a(int s) const { return base + num_kb * w_bytes_kb + s * kABytes; }
+  __device__ uint32_t bias() const { return a(stages); }
+  __device__ uint32_t bars() const { return bias() + kMaxBias * sizeof(float); }
+  __device__ uint32_t full(int s) const { return bars() + 8 * s; }
+  __device__ uint32_t empty(int s) const { return bars() + 8 * (kWsMaxStages + s); }
+  __device__ uint32_t tfull(int s) const { return bars() + 8 * (2 * kWsMaxStages + s); }
+  __device__ uint32_t tempty(int s) const { return bars() + 8 * (2 * kWsMaxStages + 2 + s); }
+  __device__ uint32_t wfull() const { return bars() + 8 * (2 * kWsMaxStages + 4); }
+  __device__ uint32_t tmem_slot() const { return bars() + 8 * (2 * kWsMaxStages + 5); }
+};
+
+template <typename TC>
+__global__ void __launch_bounds__(kLinThreads, 1)
+linear_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 int M, int K, int Nout, int block_n, int n_tiles, int m_tiles, int stages, uint32_t idesc,
+                 const float* __restrict__ bias, int act, TC* __restrict__ C, int64_t ldc) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  WsLayout L;
+  L.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  L.num_kb = (K + kBlockK - 1) / kBlockK;
+  L.w_bytes_kb = block_n * kBlockK * 2;
+  L.stages = stages;
+  const int num_kb = L.num_kb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (L.bias() - smem_u32(smem_raw)));
+  const int n_tile = blockIdx.x % n_tiles, n0 = n_tile * block_n;
+  const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
+
+  for (int i = threadIdx.x; i < kMaxBias; i += kLinThreads) bias_s[i] = (bias && i < Nout) ? bias[i] : 0.f;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < stages; ++s) { mbar_init(L.full(s), 1); mbar_init(L.empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull(s), 1); mbar_init(L.tempty(s), 8); }
+    mbar_init(L.wfull(), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(L.tmem_slot(), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(L.tmem_slot()));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // the stationary weight tile: num_kb boxes [block_n rows x 64 k], one barrier
+      mbar_expect_tx(L.wfull(), (uint32_t)(num_kb * L.w_bytes_kb));
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(L.w(kb), &map_w, L.wfull(), kb * kBlockK, n0);
+      int stage = 0; uint32_t phase = 0;
+      for (int mt = m_first; mt < m_tiles; mt += m_step) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(L.empty(stage), phase ^ 1);
+          mbar_expect_tx(L.full(stage), kABytes);
+          tma_load_2d(L.a(stage), &map_a, L.full(stage), kb * kBlockK, mt * kBlockM);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(L.wfull(), 0);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int mt = m_first; mt < m_tiles; mt += m_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(L.tempty(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(L.full(stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t ad = make_desc_sw128(L.a(stage) + k * 32, 16, 1024);
+            const uint64_t bd = make_desc_sw128(L.w(kb) + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(L.empty(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(L.tfull(as));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int n_chunks = (block_n + 31) / 32;
+    int it = 0;
+    for (int mt = m_first; mt < m_tiles; mt += m_step, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(L.tfull(as), aphase);
+      tc_fence_after();
+      const int row = mt * kBlockM + q * 32 + lane;
+      const bool row_ok = row < M;
+      TC* crow = C + (int64_t)(row_ok ? row : 0) * ldc;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride;
+      uint32_t ra[32], rb[32];
+      int ci = half;
+      if (ci < n_chunks) tmem_ld_32x32_nowait(tbase + ci * 32, ra);
+      while (ci < n_chunks) {
+        tmem_wait_ld();
+        const int nxt = ci + 2;
+        if (nxt < n_chunks) tmem_ld_32x32_nowait(tbase + nxt * 32, rb);
+        if (row_ok && n0 + ci * 32 < ldc) epilogue_chunk<TC>(ra, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
+        ci = nxt;
+        if (ci >= n_chunks) break;
+        tmem_wait_ld();
+        const int nx2 = ci + 2;
+        if (nx2 < n_chunks) tmem_ld_32x32_nowait(tbase + nx2 * 32, ra);
+        if (row_ok && n0 + ci * 32 < ldc) epilogue_chunk<TC>(rb, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
+        ci = nx2;
       }
       tc_fence_before();
       __syncwarp();
@@ -298,9 +470,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 constexpr int kBoxBytes = 64 * 64 * 2;   // 8 KB
 
+// Bias gradients ride along for free: `ones_a` >= 0 plants a column of ones at A column `ones_a` (= K1), so
+// output row K1 is the column sum of B; `ones_b` >= 0 does the same on the B side (output column K2 = column
+// sums of A).  The ones are written into the landed smem tile (swizzled address) right before the MMAs.
+__device__ __forceinline__ void plant_ones(uint32_t box_base, int col_in_box, int rows_valid, int lane) {
+  // box = [64 rows x 64 bf16] with 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+  const int chunk = col_in_box >> 3, within = (col_in_box & 7) * 2;
+  for (int r = lane; r < 64; r += 32) {
+    const uint32_t addr = box_base + r * 128 + (((chunk ^ (r & 7)) << 4) | within);
+    const uint16_t v = (r < rows_valid) ? 0x3F80 : 0;      // bf16 1.0 for real rows only
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                int R, int K1, int K2, int block_n, int rows_per, uint32_t idesc, float* __restrict__ partial) {
+                int R, int K1e, int K2e, int block_n, int rows_per, uint32_t idesc, int ones_a, int ones_b,
+                float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout L;
   L.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -310,6 +496,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int r_end = min(R, r_beg + rows_per);
   const int num_kb = (r_end > r_beg) ? (r_end - r_beg + kBlockK - 1) / kBlockK : 0;
   const int n_boxes = block_n / 64;
+  const bool plant_a = ones_a >= m0 && ones_a < m0 + kBlockM;
+  const bool plant_b = ones_b >= n0 && ones_b < n0 + block_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -341,11 +529,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(L.full(stage), phase);
-        tc_fence_after();
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(L.full(stage), phase);
+      if (plant_a || plant_b) {                      // whole warp: ones column into the landed tile
+        const int rows_valid = r_end - (r_beg + kb * kBlockK);
+        if (plant_a) plant_ones(L.a(stage) + ((ones_a - m0) >> 6) * kBoxBytes, (ones_a - m0) & 63, rows_valid, lane);
+        if (plant_b) plant_ones(L.b(stage) + ((ones_b - n0) >> 6) * kBoxBytes, (ones_b - n0) & 63, rows_valid, lane);
+        fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+      }
+      tc_fence_after();
+      if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           const uint64_t ad = make_desc_sw128(L.a(stage) + k * 2048, kBoxBytes, 1024);
@@ -353,13 +548,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
         }
         umma_commit(L.empty(stage));
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(L.tfull(0));
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
+    if (lane == 0) umma_commit(L.tfull(0));
   } else {
     const int q = warp & 3;
-    float* P = partial + (int64_t)blockIdx.z * K1 * K2;
+    float* P = partial + (int64_t)blockIdx.z * K1e * K2e;
     const int row = m0 + q * 32 + lane;
     if (num_kb > 0) {
       mbar_wait(L.tfull(0), 0);
@@ -367,12 +563,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int c0 = 0; c0 < block_n; c0 += 32) {
       uint32_t r[32];
-      if (num_kb > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
-      if (row < K1) {
+      if (num_kb > 0) { tmem_ld_32x32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r); tmem_wait_ld(); }
+      if (row < K1e) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = n0 + c0 + j;
-          if (col < K2) P[(int64_t)row * K2 + col] = (num_kb > 0) ? __uint_as_float(r[j]) : 0.f;
+          if (col < K2e) P[(int64_t)row * K2e + col] = (num_kb > 0) ? __uint_as_float(r[j]) : 0.f;
         }
       }
     }
@@ -441,9 +637,35 @@ static int launch_linear_tc_t(const CUtensorMap& ma, const CUtensorMap& mw, int 
   const int num_tiles = m_tiles * n_tiles;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   const uint32_t idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
-  linear_tc_kernel<TC><<<grid, kThreads, kSmemBytes, s>>>(ma, mw, M, K, Nout, block_n, n_tiles, num_tiles, idesc,
+  linear_tc_kernel<TC><<<grid, kLinThreads, kSmemBytes, s>>>(ma, mw, M, K, Nout, block_n, n_tiles, num_tiles, idesc,
                                                           bias, act, (TC*)C, ldc);
   return check_launch();
+}
+
+template <typename TC>
+static int launch_linear_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, int M, int K, int Nout, int block_n,
+                              int n_tiles, int stages, size_t smem, const float* bias, int act, void* C, int64_t ldc,
+                              cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(linear_ws_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  int groups = kNumSMs / n_tiles;                 // CTAs per N tile
+  if (groups > m_tiles) groups = m_tiles;
+  const uint32_t idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
+  linear_ws_kernel<TC><<<groups * n_tiles, kLinThreads, smem, s>>>(ma, mw, M, K, Nout, block_n, n_tiles, m_tiles, stages,
+                                                                    idesc, bias, act, (TC*)C, ldc);
+  return check_launch();
+}
+
+// bring-up switch: EDG_LINEAR_WS=0 forces the streaming kernel
+static bool ws_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EDG_LINEAR_WS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 int launch_linear_tc(const void* A, int64_t lda, int M, int K, const void* W, int64_t ldw, int Nout,
@@ -456,6 +678,21 @@ int launch_linear_tc(const void* A, int64_t lda, int M, int K, const void* W, in
   if (rc) return rc;
   rc = make_map_bf16(&mw, W, Nout, K, ldw, kBlockK, block_n);
   if (rc) return rc;
+  // weight-stationary variant when one N tile of the weight plus >= 4 activation stages fit in shared memory
+  {
+    const int num_kb = (K + kBlockK - 1) / kBlockK;
+    const size_t w_bytes = (size_t)num_kb * block_n * kBlockK * 2;
+    const size_t fixed = 1024 + kMaxBias * sizeof(float) + 512;
+    const size_t budget = 227 * 1024;
+    if (ws_enabled() && w_bytes + fixed + 4 * kABytes <= budget && n_tiles <= kNumSMs && M >= 4 * kBlockM) {
+      int stages = (int)((budget - fixed - w_bytes) / kABytes);
+      if (stages > kWsMaxStages) stages = kWsMaxStages;
+      const size_t smem = fixed + w_bytes + (size_t)stages * kABytes;
+      if (c_dtype == EDG_F32) return launch_linear_ws_t<float>(ma, mw, M, K, Nout, block_n, n_tiles, stages, smem, bias, act, C, ldc, s);
+      if (c_dtype == EDG_BF16) return launch_linear_ws_t<__nv_bfloat16>(ma, mw, M, K, Nout, block_n, n_tiles, stages, smem, bias, act, C, ldc, s);
+      return EDG_ERR_DTYPE;
+    }
+  }
   if (c_dtype == EDG_F32) return launch_linear_tc_t<float>(ma, mw, M, K, Nout, block_n, n_tiles, bias, act, C, ldc, s);
   if (c_dtype == EDG_BF16) return launch_linear_tc_t<__nv_bfloat16>(ma, mw, M, K, Nout, block_n, n_tiles, bias, act, C, ldc, s);
   return EDG_ERR_DTYPE;
@@ -476,33 +713,41 @@ static WgradPlan plan_wgrad_tc(int R, int K1, int K2) {
   if (p.splits < 1) p.splits = 1;
   return p;
 }
+// defined in edg_gemm_simt.cu
+void launch_split_reduce_bias(const float* partial, int splits, int K1, int K2, int K1e, int K2e, float* dW, int64_t lddw,
+                              float* dbias, int bias_of, int accumulate, cudaStream_t s);
+
 size_t wgrad_tc_workspace(int R, int K1, int K2) {
-  WgradPlan p = plan_wgrad_tc(R, K1, K2);
-  return (size_t)p.splits * K1 * K2 * sizeof(float);
+  size_t best = 0;                                      // the plan depends on where the ones row / column sits
+  for (int v = 0; v < 3; ++v) {
+    const int K1e = K1 + (v == 2), K2e = K2 + (v == 1);
+    WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
+    const size_t b = (size_t)p.splits * K1e * K2e * sizeof(float);
+    if (b > best) best = b;
+  }
+  return best;
 }
 
-// defined in edg_gemm_simt.cu
-void launch_split_reduce(const float* partial, int splits, int K1, int K2, float* dW, int64_t lddw, int accumulate,
-                         cudaStream_t s);
-
 int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, float* dW,
-                    int64_t lddw, int accumulate, float* ws, cudaStream_t s) {
+                    int64_t lddw, float* dbias, int bias_of, int accumulate, float* ws, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
       return check_launch();
     attr_set = true;
   }
-  WgradPlan p = plan_wgrad_tc(R, K1, K2);
+  const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
+  WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
   CUtensorMap ma, mb;
-  int rc = make_map_bf16(&ma, A, R, K1, lda, 64, kBlockK);
+  int rc = make_map_bf16(&ma, A, R, K1, lda, 64, kBlockK);      // true widths: columns >= K are zero-filled
   if (rc) return rc;
   rc = make_map_bf16(&mb, B, R, K2, ldb, 64, kBlockK);
   if (rc) return rc;
   const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 1, 1);
   dim3 grid(p.m_tiles, p.n_tiles, p.splits);
-  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, R, K1, K2, p.block_n, p.rows_per, idesc, ws);
-  launch_split_reduce(ws, p.splits, K1, K2, dW, lddw, accumulate, s);
+  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, R, K1e, K2e, p.block_n, p.rows_per, idesc,
+                                                     bias_of == 2 ? K1 : -1, bias_of == 1 ? K2 : -1, ws);
+  launch_split_reduce_bias(ws, p.splits, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, accumulate, s);
   return check_launch();
 }
 
