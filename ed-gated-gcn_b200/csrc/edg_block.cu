@@ -3,6 +3,7 @@
 // + softmax product ("kl"), and their backward passes.  All HBM/L2-bound row streaming:
 // 128-bit loads along the hidden dimension, one pass over the [N,D] matrix per kernel.
 #include <math.h>
+#include <stdlib.h>
 
 #include "edg_common.cuh"
 
@@ -406,6 +407,28 @@ __global__ void cast_2d_kernel(const float* __restrict__ src, int64_t lds, int R
 
 }  // namespace edg
 
+namespace edg {
+template <typename T>
+int pool_fwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
+                    int max_len, const float* gates, int V, float* pooled, int32_t* arg, cudaStream_t s);
+template <typename T>
+int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
+                     int max_len, const float* gate, const float* v, const float* c, const void* dist, int dist_i64,
+                     float* scores, float* kl_b, float* dv_unit, float* dc_unit, cudaStream_t s);
+template <typename T>
+int head_bwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
+                    int max_len, const float* gate, const float* v, const void* dist, int dist_i64, const float* scores,
+                    const float* kl_b, const float* g_kl, const float* g_scores, const float* g_pooled, const int32_t* arg,
+                    const void* g_xout, int64_t ldgx, void* dh, int64_t lddh, float* dgate, float* dv, float* dc,
+                    cudaStream_t s);
+// bring-up switch: EDG_STAGED=0 keeps the per-sentence kernels
+static bool staged_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EDG_STAGED"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+}  // namespace edg
+
 using namespace edg;
 
 #define EDG_DISPATCH_T(dtype, ...)                                \
@@ -463,13 +486,19 @@ static int pool_fwd_dispatch(const void* h, int64_t ldh, const int32_t* sent_ptr
 
 extern "C" int edg_pool_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                             int32_t D, const float* gates, int32_t V, float* pooled, int32_t* arg,
-                            edg_stream stream) {
+                            const int32_t* row_sent, int32_t N, int32_t max_len, edg_stream stream) {
   if (B < 0 || D <= 0 || V <= 0) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
   if (!h || !sent_ptr || !gates || !pooled || !arg) return EDG_ERR_ARG;
   if (!aligned16(h) || !row_pitch_ok(dtype, ldh)) return EDG_ERR_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
-  EDG_DISPATCH_T(dtype, return pool_fwd_dispatch<T>(h, ldh, sent_ptr, B, D, gates, V, pooled, arg, s);)
+  EDG_DISPATCH_T(dtype, {
+    if (staged_enabled()) {
+      const int rc = pool_fwd_staged<T>(h, ldh, sent_ptr, row_sent, N, B, D, max_len, gates, V, pooled, arg, s);
+      if (rc <= 0) return rc;
+    }
+    return pool_fwd_dispatch<T>(h, ldh, sent_ptr, B, D, gates, V, pooled, arg, s);
+  })
 }
 
 extern "C" int edg_sum_scaled(const float* in, int64_t n, float scale, float* out, edg_stream stream) {
@@ -506,7 +535,8 @@ extern "C" int edg_views_bwd(const float* pooled, const int32_t* arg, const floa
 extern "C" int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                                  int32_t D, const float* gate, const float* v, const float* c,
                                  const void* dist, int dist_i64, float* scores, float* kl_b,
-                                 float* dv_unit, float* dc_unit, edg_stream stream) {
+                                 float* dv_unit, float* dc_unit, const int32_t* row_sent, int32_t N, int32_t max_len,
+                                 edg_stream stream) {
   if (B < 0 || D <= 0) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
   if (!h || !sent_ptr || !gate || !v || !dist || !scores || !kl_b) return EDG_ERR_ARG;
@@ -517,6 +547,11 @@ extern "C" int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const in
     constexpr int E = Vec16<T>::kElems;
     const int chunks = (D + E - 1) / E;
     if (chunks > 32 * kMaxQ) return EDG_ERR_UNSUPPORTED;
+    if (staged_enabled()) {
+      const int rc = scores_kl_staged<T>(h, ldh, sent_ptr, row_sent, N, B, D, max_len, gate, v, c, dist, dist_i64, scores, kl_b,
+                                         dv_unit, dc_unit, s);
+      if (rc <= 0) return rc;
+    }
     if (dist_i64) scores_kl_fwd_kernel<T, 1><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit);
     else scores_kl_fwd_kernel<T, 0><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit);
   })
@@ -528,7 +563,7 @@ extern "C" int edg_head_bwd(const void* h, int dtype, int64_t ldh, const int32_t
                             const float* scores, const float* kl_b, const float* g_kl, const float* g_scores,
                             const float* g_pooled, const int32_t* arg, const void* g_xout, int64_t ldgx,
                             void* dh, int64_t lddh, float* dgate, float* dv, float* dc, int32_t max_len,
-                            edg_stream stream) {
+                            const int32_t* row_sent, int32_t N, edg_stream stream) {
   if (B < 0 || D <= 0 || max_len < 0) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
   if (!h || !sent_ptr || !gate) return EDG_ERR_ARG;
@@ -546,6 +581,11 @@ extern "C" int edg_head_bwd(const void* h, int dtype, int64_t ldh, const int32_t
     constexpr int E = Vec16<T>::kElems;
     const int chunks = (D + E - 1) / E;
     if (chunks > 256) return EDG_ERR_UNSUPPORTED;
+    if (staged_enabled()) {
+      const int rc = head_bwd_staged<T>(h, ldh, sent_ptr, row_sent, N, B, D, max_len, gate, v, dist, dist_i64, scores, kl_b, g_kl,
+                                        g_scores, g_pooled, arg, g_xout, ldgx, dh, lddh, dgate, dv, dc, s);
+      if (rc <= 0) return rc;
+    }
     int threads = ((chunks + 31) / 32) * 32;
     if (threads < 32) threads = 32;
     if (dist_i64) head_bwd_kernel<T, 1><<<B, threads, smem, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, dist, scores, kl_b, g_kl, g_scores, g_pooled, arg, (const T*)g_xout, ldgx, (T*)dh, lddh, dgate, dv, dc);

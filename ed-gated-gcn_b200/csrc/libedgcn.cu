@@ -4,4 +4,5 @@
 #include "edg_aggregate.cu"
 #include "edg_gemm_simt.cu"
 #include "edg_gemm_tc.cu"
+#include "edg_block_staged.cu"
 #include "edg_block.cu"

@@ -127,7 +127,7 @@ def pool_fwd(h: torch.Tensor, graph, gates: torch.Tensor):
     pooled = torch.empty((V, B, D), dtype=torch.float32, device=h.device)
     arg = torch.empty((V, B, D), dtype=torch.int32, device=h.device)
     L.call("edg_pool_fwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gates), V, L.ptr(pooled),
-           L.ptr(arg), L.stream())
+           L.ptr(arg), L.ptr(graph.row_sent), graph.n_rows, graph.max_len, L.stream())
     return pooled, arg
 
 
@@ -161,7 +161,8 @@ def scores_kl_fwd(h, graph, gate, v, c, dist, want_units: bool = False):
     dvu = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_units else None
     dcu = torch.empty((B,), dtype=torch.float32, device=h.device) if want_units else None
     L.call("edg_scores_kl_fwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(v),
-           L.ptr(c), L.ptr(dist), _dist_flag(dist), L.ptr(scores), L.ptr(kl_b), L.ptr(dvu), L.ptr(dcu), L.stream())
+           L.ptr(c), L.ptr(dist), _dist_flag(dist), L.ptr(scores), L.ptr(kl_b), L.ptr(dvu), L.ptr(dcu),
+           L.ptr(graph.row_sent), graph.n_rows, graph.max_len, L.stream())
     kl = torch.empty((), dtype=torch.float32, device=h.device)
     L.call("edg_sum_scaled", L.ptr(kl_b), B, 1.0 / B, L.ptr(kl), L.stream())
     if want_units:
@@ -180,7 +181,8 @@ def head_bwd(h, graph, gate, v, dist, scores, kl_b, g_kl, g_scores, g_pooled, ar
     L.call("edg_head_bwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(v),
            L.ptr(dist), _dist_flag(dist) if dist is not None else 0, L.ptr(scores), L.ptr(kl_b), L.ptr(g_kl),
            L.ptr(g_scores), L.ptr(g_pooled), L.ptr(arg), L.ptr(g_xout), ld(g_xout) if g_xout is not None else 0,
-           L.ptr(dh), ld(dh) if dh is not None else 0, L.ptr(dgate), L.ptr(dv), L.ptr(dc), graph.max_len, L.stream())
+           L.ptr(dh), ld(dh) if dh is not None else 0, L.ptr(dgate), L.ptr(dv), L.ptr(dc), graph.max_len,
+           L.ptr(graph.row_sent), graph.n_rows, L.stream())
     return dh, dgate, dv, dc
 
 

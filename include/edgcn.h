@@ -154,10 +154,13 @@ int edg_trigger_scatter_add(const float* da, int32_t B, int32_t D, const int32_t
                             edg_stream stream);
 
 /* bert_amir5.py:627-636,640: pooled[v,b,:] = max_t h[t,:]*gates[v,b,:] over the
- * sentence's rows, arg = global row of the maximum (first row wins ties). */
+ * sentence's rows, arg = global row of the maximum (first row wins ties).
+ * row_sent[N] + max_len (may be NULL/0) enable the shared-memory staged kernel: the rows of the sentences
+ * starting in a window are brought in by one bulk async copy instead of one dependent load per row;
+ * the same holds for edg_scores_kl_fwd and edg_head_bwd. */
 int edg_pool_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                  int32_t D, const float* gates, int32_t V, float* pooled, int32_t* arg,
-                 edg_stream stream);
+                 const int32_t* row_sent, int32_t N, int32_t max_len, edg_stream stream);
 
 /* bert_amir5.py:638: xy = sum_{v<v'} mean_b sum_d pooled[v]*pooled[v'].
  * ws: 1024 floats. */
@@ -183,7 +186,8 @@ int edg_views_bwd(const float* pooled, const int32_t* arg, const float* gates, c
 int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                       int32_t D, const float* gate, const float* v, const float* c,
                       const void* dist, int dist_i64, float* scores, float* kl_b,
-                      float* dv_unit, float* dc_unit, edg_stream stream);
+                      float* dv_unit, float* dc_unit, const int32_t* row_sent, int32_t N, int32_t max_len,
+                      edg_stream stream);
 
 /* backward of x_out = gate*h_L through scores/kl, the final max-pool and an
  * optional direct gradient on x_out:
@@ -200,7 +204,7 @@ int edg_head_bwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr,
                  const float* scores, const float* kl_b, const float* g_kl, const float* g_scores,
                  const float* g_pooled, const int32_t* arg, const void* g_xout, int64_t ldgx,
                  void* dh, int64_t lddh, float* dgate, float* dv, float* dc, int32_t max_len,
-                 edg_stream stream);
+                 const int32_t* row_sent, int32_t N, edg_stream stream);
 
 /* x_out[i,:] = gate[b(i),:]*h[i,:]  (bert_amir5.py:639), only materialised when a
  * caller asks for the per-token output. */

@@ -251,6 +251,7 @@ def test_stack_packed_rows_vs_oracle(dtype, cfg):
     import ed_gated_gcn_b200 as E
     from ed_gated_gcn_b200 import synth
     tol = tol_for(dtype)
+    torch.manual_seed(1000 + cfg["D"] + cfg["L"])       # the head (nn.Linear) initialises from the global RNG
     batch = synth.make_batch(cfg["B"], cfg["lo"], cfg["hi"], seed=cfg["D"])
     D, C, B, Lyr = cfg["D"], cfg["C"], cfg["B"], cfg["L"]
     stack = E.GatedGCNStack(D, n_layers=Lyr, n_classes=C, gate_arch=cfg["arch"], compute_dtype=dtype).to(DEV)
