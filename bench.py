@@ -182,7 +182,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     c, batch, x_host, tgt_host = make_workload(args.config, rank)
     cd = torch.bfloat16 if c["dtype"] == "bf16" else torch.float32
@@ -315,14 +316,16 @@ def run_b200(args):
     # ---- per-kernel CUDA-event pass (rank 0): which kernel dominates, and its roofline
     roof = None
     ktable = {}
+    nprof = 5
+    kt = KernelTimer()
+    torch.cuda.synchronize()
     if rank == 0:
-        kt = KernelTimer()
-        nprof = 5
-        torch.cuda.synchronize()
         _lib.HOOK = kt.hook
-        for _ in range(nprof):
-            step_resident()
-        _lib.HOOK = None
+    for _ in range(nprof):          # every rank runs these steps: they contain the gradient all-reduce
+        step_resident()
+    _lib.HOOK = None
+    torch.cuda.synchronize()
+    if rank == 0:
         ktable = kt.table(nprof)
         peaks = load_peaks()
         top_key, top = max(ktable.items(), key=lambda kv: kv[1]["ms_per_step"])
@@ -368,9 +371,15 @@ def run_b200(args):
                             "ms_per_step": round(v["ms_per_step"], 4)} for k, v in
                         sorted(ktable.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing the NCCL communicator down: destroy_process_group() can block while CUDA graphs
+        # that captured collectives are still alive, and there is nothing left to do
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------
