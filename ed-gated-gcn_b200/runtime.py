@@ -35,3 +35,46 @@ class GraphedStep:
     def __call__(self):
         self.graph.replay()
         return self.result
+
+
+class DoubleBufferedStep:
+    """Training from HOST batches with the input copy of batch i+1 hidden behind the compute of batch i.
+
+    ``n_sets`` (2) sets of static device input buffers; ``copy_in(k)`` enqueues the host->device copies of the next
+    batch into set ``k`` (it runs on a private copy stream), ``compute(k)`` is the whole step on set ``k`` and is
+    captured into one CUDA graph per set.  ``step()`` = wait for set k's copy, replay its graph, synchronise (the
+    caller reads the loss), then start refilling set k with the batch after next."""
+
+    def __init__(self, copy_in: Callable[[int], Any], compute: Callable[[int], Any], n_sets: int = 2, warmup: int = 3):
+        self.copy_in, self.n_sets = copy_in, n_sets
+        self.copy_stream = torch.cuda.Stream()
+        self.copy_done = [torch.cuda.Event() for _ in range(n_sets)]
+        self.compute_done = [torch.cuda.Event() for _ in range(n_sets)]
+        main = torch.cuda.current_stream()
+        for k in range(n_sets):                       # fill every set once before capturing
+            self._enqueue_copy(k, first=True)
+        self.copy_stream.synchronize()
+        self.graphs = [GraphedStep((lambda kk: (lambda: compute(kk)))(k), warmup=warmup) for k in range(n_sets)]
+        torch.cuda.synchronize()
+        for k in range(n_sets):
+            self.compute_done[k].record(main)
+            self._enqueue_copy(k)
+        self.i = 0
+
+    def _enqueue_copy(self, k: int, first: bool = False) -> None:
+        if not first:
+            self.copy_stream.wait_event(self.compute_done[k])     # do not overwrite inputs still being read
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_in(k)
+            self.copy_done[k].record(self.copy_stream)
+
+    def step(self):
+        k = self.i % self.n_sets
+        main = torch.cuda.current_stream()
+        main.wait_event(self.copy_done[k])
+        out = self.graphs[k]()
+        self.compute_done[k].record(main)
+        main.synchronize()                            # the caller reads this step's loss
+        self._enqueue_copy(k)                         # batch i + n_sets goes into the set just consumed
+        self.i += 1
+        return out
