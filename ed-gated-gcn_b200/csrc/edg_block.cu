@@ -42,23 +42,18 @@ template <typename T, int V>
 __global__ void __launch_bounds__(128)
 pool_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr, int B, int D, int chunks,
                 const float* __restrict__ gates, float* __restrict__ pooled, int32_t* __restrict__ arg) {
+  // same rule as pool_staged_kernel: gate-independent column maximum + first row, one multiply per view
   constexpr int E = Vec16<T>::kElems;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = (int)(idx / chunks);
   if (b >= B) return;
   const int c = (int)(idx - (int64_t)b * chunks) * E;
   const int64_t BD = (int64_t)B * D;
-  float g[V][E], best[V][E];
-  int32_t where[V][E];
   const int beg = sent_ptr[b], end = sent_ptr[b + 1];
+  float m[E];
+  int32_t where[E];
 #pragma unroll
-  for (int v = 0; v < V; ++v)
-#pragma unroll
-    for (int k = 0; k < E; ++k) {
-      g[v][k] = (c + k < D) ? __ldg(gates + v * BD + (int64_t)b * D + c + k) : 0.f;
-      best[v][k] = -INFINITY;
-      where[v][k] = beg < end ? beg : -1;
-    }
+  for (int k = 0; k < E; ++k) { m[k] = -INFINITY; where[k] = beg; }
   constexpr int U = 4;                        // rows in flight per thread (memory-level parallelism)
   for (int t = beg; t < end; t += U) {
     float f[U][E];
@@ -69,12 +64,8 @@ pool_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict_
     for (int u = 0; u < U; ++u) {
       if (t + u >= end) break;
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-          const float a = f[u][k] * g[v][k];
-          if (a > best[v][k]) { best[v][k] = a; where[v][k] = t + u; }     // strict: first row wins ties
-        }
+      for (int k = 0; k < E; ++k)
+        if (f[u][k] > m[k]) { m[k] = f[u][k]; where[k] = t + u; }       // strict: first row wins ties
     }
   }
 #pragma unroll
@@ -82,8 +73,10 @@ pool_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict_
 #pragma unroll
     for (int k = 0; k < E; ++k)
       if (c + k < D) {
-        pooled[v * BD + (int64_t)b * D + c + k] = (beg < end) ? best[v][k] : 0.f;
-        arg[v * BD + (int64_t)b * D + c + k] = where[v][k];
+        const float g = __ldg(gates + v * BD + (int64_t)b * D + c + k);
+        const int64_t o = v * BD + (int64_t)b * D + c + k;
+        pooled[o] = (beg < end) ? m[k] * g : 0.f;
+        arg[o] = (beg < end) ? (g != 0.f ? where[k] : beg) : -1;
       }
 }
 
@@ -405,6 +398,27 @@ __global__ void cast_2d_kernel(const float* __restrict__ src, int64_t lds, int R
   store_from_f32(dst, dst_dtype, (int64_t)ro * ldd + co, v);
 }
 
+// all weight copies of a step in ONE launch: entry = blockIdx.y
+constexpr int kCastBatchMax = 32;
+struct CastBatch {
+  const float* src[kCastBatchMax];
+  void* dst[kCastBatchMax];
+  int R[kCastBatchMax], C[kCastBatchMax], lds[kCastBatchMax], ldd[kCastBatchMax], transpose[kCastBatchMax];
+};
+__global__ void cast_batch_kernel(const __grid_constant__ CastBatch b, int dst_dtype) {
+  const int e = blockIdx.y;
+  const int R = b.R[e], C = b.C[e], ldd = b.ldd[e], tr = b.transpose[e];
+  const int rows_out = tr ? C : R, cols_out = tr ? R : C;
+  const float* __restrict__ src = b.src[e];
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)rows_out * ldd;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ro = (int)(idx / ldd), co = (int)(idx - (int64_t)ro * ldd);
+    float v = 0.f;
+    if (co < cols_out) v = tr ? src[(int64_t)co * b.lds[e] + ro] : src[(int64_t)ro * b.lds[e] + co];
+    store_from_f32(b.dst[e], dst_dtype, idx, v);
+  }
+}
+
 }  // namespace edg
 
 namespace edg {
@@ -630,5 +644,29 @@ extern "C" int edg_cast_2d(const float* src, int64_t lds, int32_t R, int32_t C, 
   if (ldd < cols_out) return EDG_ERR_ARG;
   if (dst_dtype != EDG_F32 && dst_dtype != EDG_BF16) return EDG_ERR_DTYPE;
   cast_2d_kernel<<<blocks_for((int64_t)rows_out * ldd, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, R, C, dst, dst_dtype, ldd, transpose);
+  return check_launch();
+}
+
+extern "C" int edg_cast_batch(int32_t n, const void* const* src, void* const* dst, const int32_t* R, const int32_t* C,
+                              const int64_t* lds, const int64_t* ldd, const int32_t* transpose, int dst_dtype,
+                              edg_stream stream) {
+  if (n < 0 || n > kCastBatchMax) return EDG_ERR_UNSUPPORTED;
+  if (n == 0) return EDG_OK;
+  if (!src || !dst || !R || !C || !lds || !ldd || !transpose) return EDG_ERR_ARG;
+  if (dst_dtype != EDG_F32 && dst_dtype != EDG_BF16) return EDG_ERR_DTYPE;
+  CastBatch b;
+  int64_t most = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!src[i] || !dst[i] || R[i] <= 0 || C[i] <= 0) return EDG_ERR_ARG;
+    const int cols_out = transpose[i] ? R[i] : C[i], rows_out = transpose[i] ? C[i] : R[i];
+    if (ldd[i] < cols_out || ldd[i] > 0x7fffffff || lds[i] > 0x7fffffff) return EDG_ERR_ARG;
+    b.src[i] = (const float*)src[i]; b.dst[i] = dst[i];
+    b.R[i] = R[i]; b.C[i] = C[i]; b.lds[i] = (int)lds[i]; b.ldd[i] = (int)ldd[i]; b.transpose[i] = transpose[i];
+    const int64_t tot = (int64_t)rows_out * ldd[i];
+    if (tot > most) most = tot;
+  }
+  int bx = (int)((most + 255) / 256);
+  if (bx > 128) bx = 128;
+  cast_batch_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(b, dst_dtype);
   return check_launch();
 }

@@ -13,9 +13,11 @@ template <int I64> __device__ __forceinline__ float sdist_at(const void* dist, i
 }
 
 // ---- gated max-pool views (bert_amir5.py:627-636, :640) -------------------------------------------
-// thread = (16-byte column chunk x, sentence lane y): the sentences of the window are dealt to the y lanes and
-// each thread walks its sentence's rows in shared memory (measured faster than splitting one sentence's rows
-// over the lanes and combining through shared memory: no block barriers on the critical path).
+// thread = (16-byte column chunk x, sentence lane y).  Gates are sigmoid outputs (> 0) and rounding is monotone,
+// so max_t fl(h_t * g) = fl((max_t h_t) * g): ONE gate-independent pass finds the column maximum m and its first
+// row; every view is then a single multiply (3 instructions per element per row instead of 4 per view).  The
+// arg-max row equals torch.max's unless two DIFFERENT values of h round to the same product, where either row is
+// an exact maximiser; a gate that underflowed to 0 makes every product 0 and the first row wins, as in torch.
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr,
@@ -31,49 +33,44 @@ pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restri
   const int c = threadIdx.x * E;
   const int64_t BD = (int64_t)B * D;
   const uint32_t xs = stg_smem_u32(win) + threadIdx.x * 16;
-  bool waited = false;
+  wait_window(&bar);
   for (int s = w.s0 + threadIdx.y; s < w.s1; s += blockDim.y) {
     const int beg = __ldg(sent_ptr + s), end = __ldg(sent_ptr + s + 1);
-    float g[V][E], best[V][E];
-    int32_t where[V][E];
+    float m[E];
+    int32_t where[E];
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-      for (int k = 0; k < E; ++k) {
-        g[v][k] = (c + k < D) ? __ldg(gates + v * BD + (int64_t)s * D + c + k) : 0.f;
-        best[v][k] = -INFINITY;
-        where[v][k] = beg < end ? beg : -1;
-      }
-    if (!waited) { wait_window(&bar); waited = true; }
-    for (int t = beg; t < end; ++t) {
+    for (int k = 0; k < E; ++k) { m[k] = -INFINITY; where[k] = beg; }
+    uint32_t addr = xs + (uint32_t)((beg - w.r0) * pitch);
+    for (int t = beg; t < end; ++t, addr += pitch) {
       float f[E];
-      SVec16<T>::load(xs + (uint32_t)((t - w.r0) * pitch), f);
+      SVec16<T>::load(addr, f);
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-          const float a = f[k] * g[v][k];
-          if (a > best[v][k]) { best[v][k] = a; where[v][k] = t; }      // strict: first row wins ties
-        }
+      for (int k = 0; k < E; ++k)
+        if (f[k] > m[k]) { m[k] = f[k]; where[k] = t; }                  // strict: first row wins ties
     }
 #pragma unroll
     for (int v = 0; v < V; ++v)
 #pragma unroll
       for (int k = 0; k < E; ++k)
         if (c + k < D) {
-          pooled[v * BD + (int64_t)s * D + c + k] = (beg < end) ? best[v][k] : 0.f;
-          arg[v * BD + (int64_t)s * D + c + k] = where[v][k];
+          const float g = __ldg(gates + v * BD + (int64_t)s * D + c + k);
+          const int64_t o = v * BD + (int64_t)s * D + c + k;
+          pooled[o] = (beg < end) ? m[k] * g : 0.f;
+          arg[o] = (beg < end) ? (g != 0.f ? where[k] : beg) : -1;
         }
   }
-  if (!waited) wait_window(&bar);        // never leave a bulk copy in flight into a dead block
 }
 
 // ---- importance scores, softmax product, and d kl / d (v, c) units (bert_amir5.py:645-648) ----------
-// blockDim = (32, 8).  All 8 warps work on ONE sentence at a time: warp y takes rows y, y+8, ... (lanes = 16-byte
-// chunks, dot product by warp shuffles); partial dv sums of the 8 warps are combined through shared memory.
+// blockDim = (32, 8); Q = 16-byte chunks per lane (ceil(chunks / 32)).  Window-wide phases, every sentence of the
+// window in parallel, three block barriers per window:
+//   P0 float(dist) of the window's rows -> smem (overlaps the bulk copy)
+//   P1 scores: warp per ROW (lanes = chunks, dot product by warp shuffles)
+//   P2 softmax statistics, kl_b and u_t = P_t (Q_t - kl_b) / B: warp per SENTENCE
+//   P3 dv_unit = gate * sum_t u_t h_t: thread = (chunk, sentence lane)
 constexpr int kSMaxQ = 4;
 
-template <typename T, int I64>
+template <typename T, int I64, int Q>
 __global__ void __launch_bounds__(256)
 scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr,
                      const int32_t* __restrict__ row_sent, int N, int B, int D, int chunks, int tile_rows, int cap_rows,
@@ -87,100 +84,96 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
   const RowWindow w = stage_window<T>(h, ldh, N, B, tile_rows, sent_ptr, row_sent, win, &bar, sh);
   if (w.r1 <= w.r0) return;
   const int pitch = (int)(ldh * (int64_t)sizeof(T));
+  const int n = w.r1 - w.r0;
   float* sc_s = reinterpret_cast<float*>(win + (size_t)cap_rows * pitch);      // [cap_rows] scores, then u_t
-  float* part = sc_s + cap_rows;                                               // [8][chunks*E] partial dv sums
+  float* dq_s = sc_s + cap_rows;                                               // [cap_rows] float(dist)
   const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
-  const int width = chunks * E;
   const uint32_t xs = stg_smem_u32(win);
+  // P0
+  for (int i = tid; i < n; i += 256) dq_s[i] = sdist_at<I64>(dist, w.r0 + i);
   wait_window(&bar);
-  for (int s = w.s0; s < w.s1; ++s) {
-    const int beg = __ldg(sent_ptr + s), end = __ldg(sent_ptr + s + 1);
-    float gq[kSMaxQ][E], wq[kSMaxQ][E];
+  // P1: one row per warp iteration; consecutive rows mostly share the sentence, so its weights stay in registers
+  {
+    int cur = -1;
+    float wq[Q][E];
+    float cb = 0.f;
+    for (int lr = warp; lr < n; lr += 8) {
+      const int s = __ldg(row_sent + w.r0 + lr);
+      if (s != cur) {
+        cur = s;
 #pragma unroll
-    for (int q = 0; q < kSMaxQ; ++q) {
-      const int c = (lane + 32 * q) * E;
+        for (int q = 0; q < Q; ++q) {
+          const int c = (lane + 32 * q) * E;
 #pragma unroll
-      for (int k = 0; k < E; ++k) {
-        const bool ok = (lane + 32 * q < chunks) && (c + k < D);
-        gq[q][k] = ok ? __ldg(gate + (int64_t)s * D + c + k) : 0.f;
-        wq[q][k] = ok ? gq[q][k] * __ldg(vvec + (int64_t)s * D + c + k) : 0.f;
+          for (int k = 0; k < E; ++k) {
+            const bool ok = (lane + 32 * q < chunks) && (c + k < D);
+            wq[q][k] = ok ? __ldg(gate + (int64_t)s * D + c + k) * __ldg(vvec + (int64_t)s * D + c + k) : 0.f;
+          }
+        }
+        cb = cvec ? __ldg(cvec + s) : 0.f;
       }
-    }
-    const float cb = cvec ? __ldg(cvec + s) : 0.f;
-    // sweep 1: scores (warp per row)
-    for (int t = beg + warp; t < end; t += 8) {
-      float acc[kSMaxQ];
+      float acc = 0.f;
 #pragma unroll
-      for (int q = 0; q < kSMaxQ; ++q) {
-        acc[q] = 0.f;
+      for (int q = 0; q < Q; ++q)
         if (lane + 32 * q < chunks) {
           float f[E];
-          SVec16<T>::load(xs + (uint32_t)((t - w.r0) * pitch + (lane + 32 * q) * 16), f);
+          SVec16<T>::load(xs + (uint32_t)(lr * pitch + (lane + 32 * q) * 16), f);
 #pragma unroll
-          for (int k = 0; k < E; ++k) acc[q] = fmaf(f[k], wq[q][k], acc[q]);
+          for (int k = 0; k < E; ++k) acc = fmaf(f[k], wq[q][k], acc);
         }
-      }
-      float tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-      tot = warp_sum(tot) + cb;
-      if (lane == 0) { sc_s[t - w.r0] = tot; scores[t] = tot; }
+      acc = warp_sum(acc) + cb;
+      if (lane == 0) { sc_s[lr] = acc; scores[w.r0 + lr] = acc; }
     }
-    __syncthreads();
-    // softmax statistics of scores and float(dist) over the sentence (every warp, redundantly: n is small)
+  }
+  __syncthreads();
+  // P2
+  const float invB = 1.0f / (float)B;
+  for (int s = w.s0 + warp; s < w.s1; s += 8) {
+    const int beg = __ldg(sent_ptr + s) - w.r0, end = __ldg(sent_ptr + s + 1) - w.r0;
     float ms = -INFINITY, mq = -INFINITY;
-    for (int t = beg + lane; t < end; t += 32) { ms = fmaxf(ms, sc_s[t - w.r0]); mq = fmaxf(mq, sdist_at<I64>(dist, t)); }
+    for (int t = beg + lane; t < end; t += 32) { ms = fmaxf(ms, sc_s[t]); mq = fmaxf(mq, dq_s[t]); }
     ms = warp_max(ms); mq = warp_max(mq);
     float zs = 0.f, zq = 0.f;
-    for (int t = beg + lane; t < end; t += 32) { zs += expf(sc_s[t - w.r0] - ms); zq += expf(sdist_at<I64>(dist, t) - mq); }
+    for (int t = beg + lane; t < end; t += 32) { zs += expf(sc_s[t] - ms); zq += expf(dq_s[t] - mq); }
     zs = warp_sum(zs); zq = warp_sum(zq);
     float kacc = 0.f;
-    for (int t = beg + lane; t < end; t += 32)
-      kacc += (expf(sc_s[t - w.r0] - ms) / zs) * (expf(sdist_at<I64>(dist, t) - mq) / zq);
+    for (int t = beg + lane; t < end; t += 32) kacc += (expf(sc_s[t] - ms) / zs) * (expf(dq_s[t] - mq) / zq);
     const float klb = warp_sum(kacc);
-    if (tid == 0) kl_b[s] = klb;
-    if (dv_unit == nullptr) { __syncthreads(); continue; }
-    __syncthreads();                       // everyone has read the scores: overwrite them with u_t
-    const float invB = 1.0f / (float)B;
-    for (int t = beg + tid; t < end; t += 256)
-      sc_s[t - w.r0] = (expf(sc_s[t - w.r0] - ms) / zs) * ((expf(sdist_at<I64>(dist, t) - mq) / zq) - klb) * invB;
-    __syncthreads();
-    // sweep 2: dv_unit[d] = gate[d] * sum_t u_t h[t,d]; warp y sums its rows, then the 8 partials are combined
-    float dvu[kSMaxQ][E];
-#pragma unroll
-    for (int q = 0; q < kSMaxQ; ++q)
-#pragma unroll
-      for (int k = 0; k < E; ++k) dvu[q][k] = 0.f;
-    for (int t = beg + warp; t < end; t += 8) {
-      const float u = sc_s[t - w.r0];
-#pragma unroll
-      for (int q = 0; q < kSMaxQ; ++q)
-        if (lane + 32 * q < chunks) {
-          float f[E];
-          SVec16<T>::load(xs + (uint32_t)((t - w.r0) * pitch + (lane + 32 * q) * 16), f);
-#pragma unroll
-          for (int k = 0; k < E; ++k) dvu[q][k] = fmaf(u, f[k], dvu[q][k]);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < kSMaxQ; ++q)
-      if (lane + 32 * q < chunks) {
-#pragma unroll
-        for (int k = 0; k < E; ++k) part[warp * width + k * chunks + (lane + 32 * q)] = dvu[q][k] * gq[q][k];
-      }
-    __syncthreads();
-    for (int j = tid; j < width; j += 256)
-      if (j < D) {
-        float tot = 0.f;
-#pragma unroll
-        for (int y = 0; y < 8; ++y) tot += part[y * width + (j % E) * chunks + j / E];
-        dv_unit[(int64_t)s * D + j] = tot;
-      }
-    if (warp == 0 && dc_unit) {
+    if (lane == 0) kl_b[s] = klb;
+    if (dv_unit) {
       float dcu = 0.f;
-      for (int t = beg + lane; t < end; t += 32) dcu += sc_s[t - w.r0];
+      for (int t = beg + lane; t < end; t += 32) {
+        const float u = (expf(sc_s[t] - ms) / zs) * ((expf(dq_s[t] - mq) / zq) - klb) * invB;
+        sc_s[t] = u;
+        dcu += u;
+      }
       dcu = warp_sum(dcu);
-      if (lane == 0) dc_unit[s] = dcu;
+      if (lane == 0 && dc_unit) dc_unit[s] = dcu;
     }
-    __syncthreads();
+  }
+  if (dv_unit == nullptr) return;
+  __syncthreads();
+  // P3
+  const int ylanes = 256 / chunks;
+  const int x = tid % chunks, y = tid / chunks;
+  if (y < ylanes) {
+    const int c = x * E;
+    for (int s = w.s0 + y; s < w.s1; s += ylanes) {
+      const int beg = __ldg(sent_ptr + s) - w.r0, end = __ldg(sent_ptr + s + 1) - w.r0;
+      float dvu[E];
+#pragma unroll
+      for (int k = 0; k < E; ++k) dvu[k] = 0.f;
+      for (int t = beg; t < end; ++t) {
+        const float u = sc_s[t];
+        float f[E];
+        SVec16<T>::load(xs + (uint32_t)(t * pitch + x * 16), f);
+#pragma unroll
+        for (int k = 0; k < E; ++k) dvu[k] = fmaf(u, f[k], dvu[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < E; ++k)
+        if (c + k < D) dv_unit[(int64_t)s * D + c + k] = dvu[k] * __ldg(gate + (int64_t)s * D + c + k);
+    }
   }
 }
 
@@ -237,45 +230,60 @@ head_bwd_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __re
   }
   __syncthreads();
   wait_window(&bar);
-  // phase 2: thread = (16-byte column chunk x, sentence lane y); the sentence's vectors stay in registers
+  // phase 2: thread = (16-byte column chunk x, sentence lane y).  With sf = sum_t ds_t h_t (per column):
+  //   dh_t = ds_t * (g v)  [+ g gp on the arg-max row]      dv = g * sf      dgate = v * sf + gp * h_arg
+  // so the row loop is 2 instructions per element; the arg-max row is patched afterwards (same thread wrote it).
   const int c = threadIdx.x * E;
   const uint32_t xs = stg_smem_u32(win) + threadIdx.x * 16;
   for (int s = w.s0 + threadIdx.y; s < w.s1; s += blockDim.y) {
     const int beg = __ldg(sent_ptr + s), end = __ldg(sent_ptr + s + 1);
-    float g[E], vv[E], gp[E], ag[E], av[E];
-    int32_t where[E];
+    float g[E], vv[E], gv[E], sf[E], xg[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) {
       const bool ok = c + k < D;
       const int64_t o = (int64_t)s * D + c + k;
       g[k] = ok ? __ldg(gate + o) : 0.f;
       vv[k] = (ok && vvec) ? __ldg(vvec + o) : 0.f;
-      gp[k] = (ok && g_pooled) ? __ldg(g_pooled + o) : 0.f;
-      where[k] = (ok && g_pooled) ? __ldg(arg + o) : -1;
-      ag[k] = 0.f; av[k] = 0.f;
+      gv[k] = g[k] * vv[k];
+      sf[k] = 0.f; xg[k] = 0.f;
     }
-    for (int t = beg; t < end; ++t) {
-      float f[E], gx[E], o[E];
-      SVec16<T>::load(xs + (uint32_t)((t - w.r0) * pitch), f);
-      if (g_xout) Vec16<T>::load(g_xout + (int64_t)t * ldgx + c, gx);
+    uint32_t addr = xs + (uint32_t)((beg - w.r0) * pitch);
+    for (int t = beg; t < end; ++t, addr += pitch) {
+      float f[E], o[E];
+      SVec16<T>::load(addr, f);
       const float dst = ds_s[t - w.r0];
+      if (g_xout) {                                  // optional direct gradient on x_out = g * h
+        float gx[E];
+        Vec16<T>::load(g_xout + (int64_t)t * ldgx + c, gx);
 #pragma unroll
-      for (int k = 0; k < E; ++k) {
-        float coef = dst * vv[k];
-        if (where[k] == t) coef += gp[k];
-        if (g_xout) coef += gx[k];
-        o[k] = g[k] * coef;
-        ag[k] = fmaf(f[k], coef, ag[k]);
-        av[k] = fmaf(dst * f[k], g[k], av[k]);
+        for (int k = 0; k < E; ++k) { o[k] = fmaf(dst, gv[k], g[k] * gx[k]); xg[k] = fmaf(f[k], gx[k], xg[k]); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < E; ++k) o[k] = dst * gv[k];
       }
+#pragma unroll
+      for (int k = 0; k < E; ++k) sf[k] = fmaf(dst, f[k], sf[k]);
       if (dh) Vec16<T>::store(dh + (int64_t)t * lddh + c, o);
     }
 #pragma unroll
     for (int k = 0; k < E; ++k)
       if (c + k < D) {
         const int64_t o = (int64_t)s * D + c + k;
-        if (dgate) dgate[o] = ag[k];
-        if (dv) dv[o] = av[k];
+        float dg = fmaf(vv[k], sf[k], xg[k]);
+        if (g_pooled) {
+          const float gp = __ldg(g_pooled + o);
+          const int wrow = __ldg(arg + o);
+          if (wrow >= 0) {
+            const T* hp = reinterpret_cast<const T*>(win + (size_t)(wrow - w.r0) * pitch) + c + k;
+            dg = fmaf(gp, to_f32(*hp), dg);
+            if (dh) {
+              T* p = dh + (int64_t)wrow * lddh + c + k;
+              *p = from_f32<T>(to_f32(*p) + g[k] * gp);
+            }
+          }
+        }
+        if (dgate) dgate[o] = dg;
+        if (dv) dv[o] = g[k] * sf[k];
       }
   }
 }
@@ -330,6 +338,20 @@ int pool_fwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const i
   return check_launch();
 }
 
+template <typename T, int I64, int Q>
+static int launch_scores_q(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
+                           int chunks, const WindowPlan& p, size_t smem, const float* gate, const float* v, const float* c,
+                           const void* dist, float* scores, float* kl_b, float* dv_unit, float* dc_unit, cudaStream_t s) {
+  static size_t seen = 0;
+  int rc = opt_in_smem(scores_staged_kernel<T, I64, Q>, smem, &seen);
+  if (rc) return rc;
+  const unsigned blocks = (unsigned)((N + p.tile_rows - 1) / p.tile_rows);
+  scores_staged_kernel<T, I64, Q><<<blocks, dim3(32, 8), smem, s>>>((const T*)h, ldh, sent_ptr, row_sent, N, B, D, chunks,
+                                                                   p.tile_rows, p.cap_rows, gate, v, c, dist, scores, kl_b,
+                                                                   dv_unit, dc_unit);
+  return check_launch();
+}
+
 template <typename T>
 int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
                      int max_len, const float* gate, const float* v, const float* c, const void* dist, int dist_i64,
@@ -337,25 +359,22 @@ int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const 
   constexpr int E = Vec16<T>::kElems;
   const int chunks = (D + E - 1) / E;
   if (!row_sent || max_len <= 0 || chunks > 32 * kSMaxQ) return 1;
-  const size_t part_bytes = (size_t)8 * chunks * E * sizeof(float);
-  const WindowPlan p = plan_window((size_t)ldh * sizeof(T), max_len, 4, part_bytes);
+  const WindowPlan p = plan_window((size_t)ldh * sizeof(T), max_len, 8);
   if (p.tile_rows < 8) return 1;
-  const size_t smem = p.smem_rows + (size_t)p.cap_rows * sizeof(float) + part_bytes;
-  const unsigned blocks = (unsigned)((N + p.tile_rows - 1) / p.tile_rows);
-  static size_t seen[2] = {0, 0};
-  int rc;
-  if (dist_i64) {
-    rc = opt_in_smem(scores_staged_kernel<T, 1>, smem, &seen[1]);
-    if (rc) return rc;
-    scores_staged_kernel<T, 1><<<blocks, dim3(32, 8), smem, s>>>((const T*)h, ldh, sent_ptr, row_sent, N, B, D, chunks, p.tile_rows,
-                                                                p.cap_rows, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit);
-  } else {
-    rc = opt_in_smem(scores_staged_kernel<T, 0>, smem, &seen[0]);
-    if (rc) return rc;
-    scores_staged_kernel<T, 0><<<blocks, dim3(32, 8), smem, s>>>((const T*)h, ldh, sent_ptr, row_sent, N, B, D, chunks, p.tile_rows,
-                                                                p.cap_rows, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit);
+  const size_t smem = p.smem_rows + (size_t)p.cap_rows * 2 * sizeof(float);
+  const int Q = (chunks + 31) / 32;
+#define EDG_SC(QQ)                                                                                                       \
+  return dist_i64 ? launch_scores_q<T, 1, QQ>(h, ldh, sent_ptr, row_sent, N, B, D, chunks, p, smem, gate, v, c, dist, scores, \
+                                              kl_b, dv_unit, dc_unit, s)                                                 \
+                  : launch_scores_q<T, 0, QQ>(h, ldh, sent_ptr, row_sent, N, B, D, chunks, p, smem, gate, v, c, dist, scores, \
+                                              kl_b, dv_unit, dc_unit, s);
+  switch (Q) {
+    case 1: EDG_SC(1)
+    case 2: EDG_SC(2)
+    case 3: EDG_SC(3)
+    default: EDG_SC(4)
   }
-  return check_launch();
+#undef EDG_SC
 }
 
 template <typename T>

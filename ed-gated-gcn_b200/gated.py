@@ -71,6 +71,14 @@ class _GatedStackFn(torch.autograd.Function):
         # layout and autograd can keep it without a copy)
         ctx.x_padded = x.shape[1] != D
         xr = ops.as_rows(x[:, :D] if ctx.x_padded else x, cd)
+        # every compute-dtype weight copy of the step (both orientations: forward and backward operands) in one launch
+        flat_w = [w for (w, _) in gcn_p] + [w for gp in gate_p for (w, _) in gp]
+        casted = ops.cast_weights_batch([(w, True) for w in flat_w] + [(w, False) for w in flat_w], cd)
+        nW = len(flat_w)
+        w_t = {id(w): casted[i] for i, w in enumerate(flat_w)}            # transposed copies
+        w_n = {id(w): casted[nW + i] for i, w in enumerate(flat_w)}       # same-orientation copies
+        ctx.w_t = [casted[i] for i in range(nW)]
+        ctx.w_n = [casted[nW + i] for i in range(nW)]
         # ---- trigger vector and the gate MLPs (bert_amir5.py:615-622)
         a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
         gates = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
@@ -79,7 +87,7 @@ class _GatedStackFn(torch.autograd.Function):
             s = s0
             acts = [s0]
             for i, (w, b) in enumerate(gate_p[g]):
-                wk = ops.cast_weight(w, cd, transpose=False)                    # nn.Linear [out,in] is K-major
+                wk = w_n[id(w)]                                                 # nn.Linear [out,in] is K-major
                 last = i == pairs - 1
                 s = ops.linear(s, wk, b.detach().float().contiguous(), act=L.ACT_SIGMOID,
                                out_dtype=torch.float32 if last else cd, out=gates[g] if last else None)
@@ -91,7 +99,7 @@ class _GatedStackFn(torch.autograd.Function):
         ms, hs = [], []
         for (w, b) in gcn_p:
             m = ops.aggregate(h, graph, mode=0)
-            wt = ops.cast_weight(w, cd, transpose=True)
+            wt = w_t[id(w)]                                                     # [out,in]: K-major B operand
             h = ops.linear(m, wt, b.detach().float().contiguous() if b is not None else None,
                            act=L.ACT_RELU if cfg["relu"] else L.ACT_NONE)
             ms.append(m)
@@ -207,7 +215,7 @@ class _GatedStackFn(torch.autograd.Function):
                 dh = ops.as_rows(dh * (hs[l] > 0), cd)
             dW, db = ops.wgrad(ms[l], dh, bias_of=2)
             grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db.to(b.dtype)
-            wk = ops.cast_weight(w, cd, transpose=False)
+            wk = ctx.w_n[l]                                                     # [in,out] = B operand of dh W^T
             dm = ops.linear(dh, wk, None)
             dh = ops.aggregate(dm, graph, mode=1)
         dx = dh
@@ -222,7 +230,7 @@ class _GatedStackFn(torch.autograd.Function):
                 dW, db = ops.wgrad(dz, acts[i], bias_of=1)                      # [out,in], [out]
                 grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
                 grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
-                wt = ops.cast_weight(w, cd, transpose=True)                     # [in,out]
+                wt = ctx.w_t[Lyr + g * pairs + i]                               # [in,out]
                 if i > 0 or lead:
                     ds = ops.linear(dz, wt, None)
                     dz = ops.sigmoid_bwd(acts[i], ds, cd if i > 0 else torch.float32)

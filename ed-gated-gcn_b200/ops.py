@@ -97,6 +97,37 @@ def cast_weight(w: torch.Tensor, dtype: torch.dtype, transpose: bool) -> torch.T
     return out
 
 
+def cast_weights_batch(items, dtype: torch.dtype):
+    """``items`` = [(fp32 weight [R,C], transpose?)]: all compute-dtype copies in one kernel launch.
+    Returns the row matrices in the same order (views of one flat allocation)."""
+    import ctypes
+    n = len(items)
+    ws = []
+    for w, _ in items:
+        w = w.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        ws.append(w)
+    shapes = [((w.shape[1], w.shape[0]) if tr else tuple(w.shape)) for w, (_, tr) in zip(ws, items)]
+    lds = [row_pitch(co, dtype) for _, co in shapes]
+    sizes = [_round_up(ro * l, 64) for (ro, _), l in zip(shapes, lds)]       # keep every slice 128-byte aligned
+    flat = torch.empty(sum(sizes), dtype=dtype, device=ws[0].device)
+    outs, off = [], 0
+    for (ro, co), l, sz in zip(shapes, lds, sizes):
+        outs.append(flat[off:off + ro * l].view(ro, l)[:, :co])
+        off += sz
+    out = []
+    for i0 in range(0, n, 32):
+        m = min(32, n - i0)
+        P, I32, I64 = ctypes.c_void_p * m, ctypes.c_int32 * m, ctypes.c_int64 * m
+        sl = slice(i0, i0 + m)
+        L.call("edg_cast_batch", m, P(*[w.data_ptr() for w in ws[sl]]), P(*[o.data_ptr() for o in outs[sl]]),
+               I32(*[w.shape[0] for w in ws[sl]]), I32(*[w.shape[1] for w in ws[sl]]),
+               I64(*[w.stride(0) for w in ws[sl]]), I64(*lds[sl]), I32(*[int(tr) for _, tr in items[sl]]),
+               L.dt(dtype), L.stream())
+    return outs
+
+
 def colsum(x: torch.Tensor) -> torch.Tensor:
     R, C = x.shape
     out = torch.empty((C,), dtype=torch.float32, device=x.device)

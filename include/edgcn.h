@@ -138,6 +138,12 @@ int edg_wgrad(const void* A, int64_t lda, int32_t K1, const void* B, int64_t ldb
 int edg_cast_2d(const float* src, int64_t lds, int32_t R, int32_t C, void* dst, int dst_dtype,
                 int64_t ldd, int transpose, edg_stream stream);
 
+/* The same for up to 32 weights in ONE launch (all compute-dtype copies a training step needs).
+ * The arrays are HOST arrays of length n (device pointers inside src/dst). */
+int edg_cast_batch(int32_t n, const void* const* src, void* const* dst, const int32_t* R, const int32_t* C,
+                   const int64_t* lds, const int64_t* ldd, const int32_t* transpose, int dst_dtype,
+                   edg_stream stream);
+
 /* ------------------------------------------------------------------------- */
 /* Gated block (models/bert_amir5.py:615-648)                                 */
 /* ------------------------------------------------------------------------- */

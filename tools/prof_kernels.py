@@ -30,7 +30,7 @@ def run():
     flush.zero_()
     pooled, arg = ops.pool_fwd(h, graph, gates)
     flush.zero_()
-    scores, kl_b, kl = ops.scores_kl_fwd(h, graph, gates[1], v, cvec, dist)
+    scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(h, graph, gates[1], v, cvec, dist, want_units=True)
     flush.zero_()
     gk = torch.ones((), device=dev)
     dh, dg, _, _ = ops.head_bwd(h, graph, gates[1], v, dist, scores, kl_b, gk, None, pooled[1].contiguous(), arg[1].contiguous(), None, True, False)
