@@ -8,7 +8,7 @@
 // DRAM traffic is one read + one write of the [N,D] matrix plus 16 B/row of CSR.
 #include <stdlib.h>
 
-#include "edg_common.cuh"
+#include "edg_staged.cuh"
 
 namespace edg {
 
@@ -244,7 +244,7 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
     cap_rows = (int)((200 * 1024) / (pitch + 24));
     tile_rows = cap_rows - max_len + 1;
   }
-  const bool staged = agg_variant() == 3 && sent_ptr && row_sent && B > 0 && max_len > 0 && tile_rows >= 8;
+  const bool staged = agg_variant() >= 3 && sent_ptr && row_sent && B > 0 && max_len > 0 && tile_rows >= 8;
   if (!staged) {
     const int64_t total = (int64_t)N * chunks;
     const unsigned blocks = (unsigned)((total + 255) / 256);

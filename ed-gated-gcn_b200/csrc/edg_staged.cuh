@@ -73,6 +73,8 @@ template <> struct SVec16<__nv_bfloat16> {
   }
 };
 
+// (A persistent one-block-per-SM variant with a 3-stage ring of windows was measured and rejected: 56-74 us vs
+// 42-44 us for aggregation at C2 -- with ~70-row windows the block-wide barriers outweigh the hidden prologue.)
 // host side: window geometry for a row pitch (bytes) and the longest sentence; tile_rows < 8 = do not stage
 struct WindowPlan { int tile_rows, cap_rows; size_t smem_rows; };
 inline WindowPlan plan_window(size_t pitch_bytes, int max_len, size_t extra_per_row = 0, size_t fixed_extra = 0) {
