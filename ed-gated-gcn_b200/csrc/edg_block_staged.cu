@@ -197,10 +197,12 @@ head_bwd_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __re
   float* ds_s = reinterpret_cast<float*>(win + (size_t)cap_rows * pitch);      // [cap_rows] d loss / d scores
   const int nthreads = blockDim.x * blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int lane = tid & 31, wid = tid >> 5, nwarps = (nthreads + 31) >> 5;
+  // only FULL warps take part in phase 1 (its reductions use full-mask shuffles); the block's last, partial
+  // warp skips it.  The host launches this kernel only when the block holds at least one full warp.
+  const int lane = tid & 31, wid = tid >> 5, nwarps = nthreads >> 5;
   const bool have_s = (scores != nullptr) && (g_kl != nullptr || g_scores != nullptr);
   // phase 1 (overlaps the bulk copy): ds for every row of the window, one warp per sentence
-  for (int s = w.s0 + wid; s < w.s1; s += nwarps) {
+  for (int s = w.s0 + wid; wid < nwarps && s < w.s1; s += nwarps) {
     const int beg = __ldg(sent_ptr + s), end = __ldg(sent_ptr + s + 1);
     float tot = 0.f;
     if (have_s) {
@@ -389,6 +391,10 @@ int head_bwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const i
   const dim3 blk = chunk_block(chunks);
   const WindowPlan p = plan_window((size_t)ldh * sizeof(T), max_len, 4);
   if (p.tile_rows < 8) return 1;
+  {
+    const dim3 blk = chunk_block(chunks);
+    if (blk.x * blk.y < 32) return 1;              // phase 1 needs one full warp
+  }
   const size_t smem = p.smem_rows + (size_t)p.cap_rows * sizeof(float);
   const unsigned blocks = (unsigned)((N + p.tile_rows - 1) / p.tile_rows);
   static size_t seen[2] = {0, 0};
