@@ -100,6 +100,15 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version = 1):
 //   [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 |
 //   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;                                 // layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
@@ -470,6 +479,24 @@ linear_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 constexpr int kBoxBytes = 64 * 64 * 2;   // 8 KB
 
+// 32 consecutive fp32 of one partial-sum row: 128-bit stores when the row pitch allows, scalar otherwise
+__device__ __forceinline__ void store_partial_chunk(float* __restrict__ prow, int col0, int K2e, const uint32_t (&r)[32], bool valid) {
+  if ((K2e & 3) == 0 && col0 + 32 <= K2e) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 v = valid ? make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(prow + col0 + j) = v;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col < K2e) prow[col] = valid ? __uint_as_float(r[j]) : 0.f;
+    }
+  }
+}
+
 // Bias gradients ride along for free: `ones_a` >= 0 plants a column of ones at A column `ones_a` (= K1), so
 // output row K1 is the column sum of B; `ones_b` >= 0 does the same on the B side (output column K2 = column
 // sums of A).  The ones are written into the landed smem tile (swizzled address) right before the MMAs.
@@ -564,13 +591,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int c0 = 0; c0 < block_n; c0 += 32) {
       uint32_t r[32];
       if (num_kb > 0) { tmem_ld_32x32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r); tmem_wait_ld(); }
-      if (row < K1e) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          if (col < K2e) P[(int64_t)row * K2e + col] = (num_kb > 0) ? __uint_as_float(r[j]) : 0.f;
-        }
-      }
+      if (row < K1e) store_partial_chunk(P + (int64_t)row * K2e, n0 + c0, K2e, r, num_kb > 0);
     }
   }
   tc_fence_before();
@@ -578,6 +599,131 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad_tall : one CTA owns ALL M tiles (K1 <= 384) of one N tile (<= 160 columns) for its row range, so the
+// A operand (K1 columns) is read once per N tile and the B operand once overall: 210 MB of L2->SM traffic
+// at C2 instead of 343 MB for the [128 x 192] tiles of wgrad_tc (which is L2-bandwidth bound).
+//   stage (64 rows): A = 2*m_tiles boxes [64 rows x 64 cols] SW128, B = block_n/32 boxes [64 rows x 32 cols] SW64
+//   TMEM: accumulator of M tile mt at columns mt*block_n (m_tiles*block_n <= 512)
+// ---------------------------------------------------------------------------------------------
+constexpr int kTallStages = 3;
+constexpr int kTallMaxM = 3;
+constexpr int kTallABytes = kTallMaxM * 2 * kBoxBytes;       // 48 KB
+constexpr int kTallBBox = 64 * 32 * 2;                       // 4 KB
+constexpr int kTallBBytes = 5 * kTallBBox;                   // 20 KB (block_n <= 160)
+constexpr int kTallStageBytes = kTallABytes + kTallBBytes;   // 68 KB
+constexpr size_t kTallSmem = 1024 + (size_t)kTallStages * kTallStageBytes + 256;
+
+__device__ __forceinline__ void plant_ones_sw64(uint32_t box_base, int col_in_box, int rows_valid, int lane) {
+  // box = [64 rows x 32 bf16] with 64-byte rows, 16-byte chunks XOR-swizzled by ((row >> 1) & 3)
+  const int chunk = col_in_box >> 3, within = (col_in_box & 7) * 2;
+  for (int r = lane; r < 64; r += 32) {
+    const uint32_t addr = box_base + r * 64 + (((chunk ^ ((r >> 1) & 3)) << 4) | within);
+    const uint16_t v = (r < rows_valid) ? 0x3F80 : 0;
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tall_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  int R, int K1e, int K2e, int m_tiles, int block_n, int rows_per, uint32_t idesc, int ones_a, int ones_b,
+                  float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto sa = [&](int st) { return base + st * kTallStageBytes; };
+  auto sb = [&](int st) { return base + st * kTallStageBytes + kTallABytes; };
+  const uint32_t bars = base + kTallStages * kTallStageBytes;
+  auto full = [&](int st) { return bars + 8 * st; };
+  auto empty = [&](int st) { return bars + 8 * (kTallStages + st); };
+  const uint32_t tfull = bars + 8 * (2 * kTallStages);
+  const uint32_t tmem_slot = bars + 8 * (2 * kTallStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * block_n;
+  const int r_beg = blockIdx.y * rows_per;
+  const int r_end = min(R, r_beg + rows_per);
+  const int num_kb = (r_end > r_beg) ? (r_end - r_beg + kBlockK - 1) / kBlockK : 0;
+  const int a_boxes = 2 * m_tiles, b_boxes = block_n / 32;
+  const bool plant_a = ones_a >= 0;
+  const bool plant_b = ones_b >= n0 && ones_b < n0 + block_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kTallStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t stage_tx = (uint32_t)a_boxes * kBoxBytes + (uint32_t)b_boxes * kTallBBox;
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty(stage), phase ^ 1);
+        mbar_expect_tx(full(stage), stage_tx);
+        const int r0 = r_beg + kb * kBlockK;
+        for (int j = 0; j < a_boxes; ++j) tma_load_2d(sa(stage) + j * kBoxBytes, &map_a, full(stage), 64 * j, r0);
+        for (int j = 0; j < b_boxes; ++j) tma_load_2d(sb(stage) + j * kTallBBox, &map_b, full(stage), n0 + 32 * j, r0);
+        if (++stage == kTallStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(full(stage), phase);
+      if (plant_a || plant_b) {
+        const int rows_valid = r_end - (r_beg + kb * kBlockK);
+        if (plant_a) plant_ones(sa(stage) + (ones_a >> 6) * kBoxBytes, ones_a & 63, rows_valid, lane);
+        if (plant_b) plant_ones_sw64(sb(stage) + ((ones_b - n0) >> 5) * kTallBBox, (ones_b - n0) & 31, rows_valid, lane);
+        fence_proxy_async();
+        __syncwarp();
+      }
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t bd = make_desc(sb(stage) + k * 1024, kTallBBox, 512, 4);
+          for (int mt = 0; mt < m_tiles; ++mt) {
+            const uint64_t ad = make_desc(sa(stage) + mt * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024, 2);
+            umma_bf16(tmem_base + mt * block_n, ad, bd, idesc, (kb | k) != 0);
+          }
+        }
+        umma_commit(empty(stage));
+      }
+      __syncwarp();
+      if (++stage == kTallStages) { stage = 0; phase ^= 1; }
+    }
+    if (lane == 0) umma_commit(tfull);
+  } else {
+    const int q = warp & 3;
+    float* P = partial + (int64_t)blockIdx.y * K1e * K2e;
+    if (num_kb > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    for (int mt = 0; mt < m_tiles; ++mt) {
+      const int row = mt * kBlockM + q * 32 + lane;
+      for (int c0 = 0; c0 < block_n; c0 += 32) {
+        uint32_t r[32];
+        if (num_kb > 0) { tmem_ld_32x32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + mt * block_n + c0, r); tmem_wait_ld(); }
+        if (row < K1e) store_partial_chunk(P + (int64_t)row * K2e, n0 + c0, K2e, r, num_kb > 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -602,7 +748,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 row-major [rows, cols] (pitch ld elements), box = [box_rows, box_cols], 128B swizzle, OOB -> 0
 static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
-                         int box_rows) {
+                         int box_rows, bool swizzle64 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return EDG_ERR_CUDA;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -610,7 +756,8 @@ static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? EDG_OK : EDG_ERR_CUDA;
 }
@@ -717,8 +864,37 @@ static WgradPlan plan_wgrad_tc(int R, int K1, int K2) {
 void launch_split_reduce_bias(const float* partial, int splits, int K1, int K2, int K1e, int K2e, float* dW, int64_t lddw,
                               float* dbias, int bias_of, int accumulate, cudaStream_t s);
 
+struct TallPlan { bool ok; int m_tiles, block_n, n_tiles, splits, rows_per; };
+static TallPlan plan_wgrad_tall(int R, int K1e, int K2e) {
+  TallPlan p;
+  p.m_tiles = (K1e + kBlockM - 1) / kBlockM;
+  p.ok = p.m_tiles <= kTallMaxM && R >= 64 * kNumSMs;          // big activations only; small ones keep wgrad_tc
+  p.block_n = 160;
+  while (p.block_n > 32 && (p.block_n - 32) * 1 >= K2e) p.block_n -= 32;
+  if (p.m_tiles * p.block_n > kTmemCols) p.ok = false;
+  p.n_tiles = (K2e + p.block_n - 1) / p.block_n;
+  int want = kNumSMs / p.n_tiles;
+  if (want < 1) want = 1;
+  p.rows_per = (((R + want - 1) / want) + kBlockK - 1) / kBlockK * kBlockK;
+  p.splits = (R + p.rows_per - 1) / p.rows_per;
+  return p;
+}
+static bool tall_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EDG_WGRAD_TALL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 size_t wgrad_tc_workspace(int R, int K1, int K2) {
-  size_t best = 0;                                      // the plan depends on where the ones row / column sits
+  size_t best = 0;
+  for (int v = 0; v < 3; ++v) {
+    const int K1e = K1 + (v == 2), K2e = K2 + (v == 1);
+    TallPlan t = plan_wgrad_tall(R, K1e, K2e);
+    if (t.ok) {
+      const size_t b = (size_t)t.splits * K1e * K2e * sizeof(float);
+      if (b > best) best = b;
+    }
+  }                                      // the plan depends on where the ones row / column sits
   for (int v = 0; v < 3; ++v) {
     const int K1e = K1 + (v == 2), K2e = K2 + (v == 1);
     WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
@@ -737,6 +913,26 @@ int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t l
     attr_set = true;
   }
   const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
+  const TallPlan t = plan_wgrad_tall(R, K1e, K2e);
+  if (t.ok && tall_enabled()) {
+    static bool tall_attr = false;
+    if (!tall_attr) {
+      if (cudaFuncSetAttribute(wgrad_tall_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTallSmem) != cudaSuccess)
+        return check_launch();
+      tall_attr = true;
+    }
+    CUtensorMap ma, mb;
+    int rc = make_map_bf16(&ma, A, R, K1, lda, 64, kBlockK);
+    if (rc) return rc;
+    rc = make_map_bf16(&mb, B, R, K2, ldb, 32, kBlockK, /*swizzle64=*/true);
+    if (rc) return rc;
+    const uint32_t idesc = make_idesc_bf16(kBlockM, t.block_n, 1, 1);
+    wgrad_tall_kernel<<<dim3(t.n_tiles, t.splits), kThreads, kTallSmem, s>>>(ma, mb, R, K1e, K2e, t.m_tiles, t.block_n,
+                                                                            t.rows_per, idesc, bias_of == 2 ? K1 : -1,
+                                                                            bias_of == 1 ? K2 : -1, ws);
+    launch_split_reduce_bias(ws, t.splits, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, accumulate, s);
+    return check_launch();
+  }
   WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
   CUtensorMap ma, mb;
   int rc = make_map_bf16(&ma, A, R, K1, lda, 64, kBlockK);      // true widths: columns >= K are zero-filled

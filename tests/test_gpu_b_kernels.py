@@ -72,7 +72,7 @@ def test_linear(dtype, shape, act):
 
 @pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
 @pytest.mark.parametrize("shape", [(50, 16, 16), (1000, 300, 300), (4096, 256, 256), (3000, 768, 768), (129, 300, 40),
-                                   (64, 8, 304)])
+                                   (64, 8, 304), (20000, 300, 300), (16000, 256, 128), (9600, 100, 24), (12000, 384, 160)])
 def test_wgrad(dtype, shape):
     from ed_gated_gcn_b200 import ops
     R, K1, K2 = shape
