@@ -14,10 +14,13 @@ template <typename T>
 __global__ void trigger_gather_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __restrict__ sent_ptr,
                                       const int32_t* __restrict__ anchor, int B, int D, float* __restrict__ raw,
                                       T* __restrict__ act, int64_t ldact, int lead_sigmoid) {
+  // covers [B, ldact]: the padding columns of `act` are written as zeros
+  const int W = act ? (int)ldact : D;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = (int)(idx / D);
+  const int b = (int)(idx / W);
   if (b >= B) return;
-  const int d = (int)(idx - (int64_t)b * D);
+  const int d = (int)(idx - (int64_t)b * W);
+  if (d >= D) { act[(int64_t)b * ldact + d] = from_f32<T>(0.f); return; }
   const int64_t row = (int64_t)sent_ptr[b] + anchor[b];
   const float v = to_f32(x[row * ldx + d]);
   if (raw) raw[(int64_t)b * D + d] = v;
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(256)
 views_bwd_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ arg, const float* __restrict__ gates,
                  const T* __restrict__ h, int64_t ldh, int V, int B, int D, const float* __restrict__ g_xy,
                  const float* __restrict__ g_pooled, T* __restrict__ dh, int64_t lddh, float* __restrict__ dgates,
-                 int accumulate) {
+                 int acc_view) {
   const int64_t BD = (int64_t)B * D;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= BD) return;
@@ -140,7 +143,7 @@ views_bwd_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ a
       T* p = dh + (int64_t)r * lddh + d;                 // this thread owns column d of sentence b
       *p = from_f32<T>(to_f32(*p) + dp * gates[v * BD + i]);
     }
-    dgates[v * BD + i] = accumulate ? dgates[v * BD + i] + dgv : dgv;
+    dgates[v * BD + i] = (v == acc_view) ? dgates[v * BD + i] + dgv : dgv;    // acc_view already holds d gate_L
   }
 }
 
@@ -376,14 +379,20 @@ gate_rows_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict
 
 __global__ void sigmoid_bwd_kernel(const void* __restrict__ y, int y_dtype, int64_t ldy, const void* __restrict__ dy,
                                    int dy_dtype, int64_t lddy, int R, int C, void* __restrict__ dz, int dz_dtype,
-                                   int64_t lddz) {
+                                   int64_t lddz, int accumulate) {
+  // covers the whole [R, lddz] allocation: padding columns are written as zeros (no separate memset)
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = (int)(idx / C);
+  const int W = (int)lddz;
+  const int r = (int)(idx / W);
   if (r >= R) return;
-  const int c = (int)(idx - (int64_t)r * C);
-  const float yv = load_as_f32(y, y_dtype, (int64_t)r * ldy + c);
-  const float g = load_as_f32(dy, dy_dtype, (int64_t)r * lddy + c);
-  store_from_f32(dz, dz_dtype, (int64_t)r * lddz + c, g * yv * (1.f - yv));
+  const int c = (int)(idx - (int64_t)r * W);
+  float v = 0.f;
+  if (c < C) {
+    const float yv = load_as_f32(y, y_dtype, (int64_t)r * ldy + c);
+    v = load_as_f32(dy, dy_dtype, (int64_t)r * lddy + c) * yv * (1.f - yv);
+    if (accumulate) v += load_as_f32(dz, dz_dtype, (int64_t)r * lddz + c);
+  }
+  store_from_f32(dz, dz_dtype, (int64_t)r * lddz + c, v);
 }
 
 __global__ void cast_2d_kernel(const float* __restrict__ src, int64_t lds, int R, int C, void* __restrict__ dst,
@@ -459,7 +468,7 @@ extern "C" int edg_trigger_gather(const void* x, int dtype, int64_t ldx, const i
   if (B == 0) return EDG_OK;
   if (!x || !sent_ptr || !anchor) return EDG_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  EDG_DISPATCH_T(dtype, trigger_gather_kernel<T><<<blocks_for((int64_t)B * D, 256), 256, 0, s>>>(
+  EDG_DISPATCH_T(dtype, trigger_gather_kernel<T><<<blocks_for((int64_t)B * (act ? ldact : D), 256), 256, 0, s>>>(
       (const T*)x, ldx, sent_ptr, anchor, B, D, raw, (T*)act, ldact, lead_sigmoid);)
   return check_launch();
 }
@@ -535,14 +544,14 @@ extern "C" int edg_diversity_fwd(const float* pooled, int32_t V, int32_t B, int3
 
 extern "C" int edg_views_bwd(const float* pooled, const int32_t* arg, const float* gates, const void* h,
                              int dtype, int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy,
-                             const float* g_pooled, void* dh, int64_t lddh, float* dgates, int accumulate_dgates,
+                             const float* g_pooled, void* dh, int64_t lddh, float* dgates, int acc_view,
                              edg_stream stream) {
   if (V <= 0 || B < 0 || D <= 0) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
   if (!pooled || !arg || !gates || !h || !dh || !dgates) return EDG_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   EDG_DISPATCH_T(dtype, views_bwd_kernel<T><<<blocks_for((int64_t)B * D, 256), 256, 0, s>>>(
-      pooled, arg, gates, (const T*)h, ldh, V, B, D, g_xy, g_pooled, (T*)dh, lddh, dgates, accumulate_dgates);)
+      pooled, arg, gates, (const T*)h, ldh, V, B, D, g_xy, g_pooled, (T*)dh, lddh, dgates, acc_view);)
   return check_launch();
 }
 
@@ -629,11 +638,12 @@ extern "C" int edg_gate_rows(const void* h, int dtype, int64_t ldh, const int32_
 
 extern "C" int edg_sigmoid_bwd(const void* y, int y_dtype, int64_t ldy, const void* dy, int dy_dtype,
                                int64_t lddy, int32_t R, int32_t C, void* dz, int dz_dtype, int64_t lddz,
-                               edg_stream stream) {
+                               int accumulate, edg_stream stream) {
   if (R < 0 || C <= 0) return EDG_ERR_ARG;
   if (R == 0) return EDG_OK;
   if (!y || !dy || !dz) return EDG_ERR_ARG;
-  sigmoid_bwd_kernel<<<blocks_for((int64_t)R * C, 256), 256, 0, (cudaStream_t)stream>>>(y, y_dtype, ldy, dy, dy_dtype, lddy, R, C, dz, dz_dtype, lddz);
+  if (lddz < C) return EDG_ERR_ARG;
+  sigmoid_bwd_kernel<<<blocks_for((int64_t)R * lddz, 256), 256, 0, (cudaStream_t)stream>>>(y, y_dtype, ldy, dy, dy_dtype, lddy, R, C, dz, dz_dtype, lddz, accumulate);
   return check_launch();
 }
 

@@ -198,18 +198,20 @@ class _GatedStackFn(torch.autograd.Function):
         if gp_head is not None:
             gp_total = gp_head.float() if gp_total is None else gp_total + gp_head.float()
         # ---- pass B over h_L: dh_L, dgate_L
-        dh, dgL, _, _ = ops.head_bwd(hL, graph, gL, v.detach().contiguous() if need_scores else None, dist,
-                                     scores if need_scores else None, kl_b, g_kl, g_scores,
-                                     gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
-                                     want_dh=True, want_dv=False)
-        dgates = torch.zeros((Lyr, B, D), dtype=torch.float32, device=dev)
-        dgates[Lyr - 1].copy_(dgL)
+        dgates = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
+        views_active = g_xy is not None and Lyr > 1
+        if not views_active and Lyr > 1:
+            dgates[:Lyr - 1].zero_()                                  # no diversity gradient: the other gates get none
+        dh, _, _, _ = ops.head_bwd(hL, graph, gL, v.detach().contiguous() if need_scores else None, dist,
+                                   scores if need_scores else None, kl_b, g_kl, g_scores,
+                                   gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
+                                   want_dh=True, want_dv=False, dgate_out=dgates[Lyr - 1])
         # ---- GCN chain backward (gcn.py:33-45)
         grads_out: List[Optional[torch.Tensor]] = [None] * ctx.n_params
         for l in range(Lyr - 1, -1, -1):
-            if l == 0 and g_xy is not None and Lyr > 1:
+            if l == 0 and views_active:
                 # gated views of h_1 feed xy (:627-638): add their gradient before leaving layer 1
-                ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, accumulate=True)
+                ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
             w, b = params[2 * l], params[2 * l + 1]
             if cfg["relu"]:
                 dh = ops.as_rows(dh * (hs[l] > 0), cd)
@@ -220,23 +222,33 @@ class _GatedStackFn(torch.autograd.Function):
             dh = ops.aggregate(dm, graph, mode=1)
         dx = dh
         # ---- gate MLP backward (bert_amir5.py:562-571)
-        da = torch.zeros((B, D), dtype=torch.float32, device=dev) if ga_head is None else ga_head.float().clone()
+        # the last Sigmoid of every gate in one launch (gates / dgates are [V*B, D] row blocks)
+        dz_all = ops.sigmoid_bwd(gates.view(Lyr * B, D), dgates.view(Lyr * B, D), cd)
+        da = ga_head.float().contiguous() if ga_head is not None else None
+        if da is not None and not da.is_contiguous():
+            da = da.contiguous()
         o = 2 * Lyr
         for g in range(Lyr):
             acts = ctx.gate_saved[g]
-            dz = ops.sigmoid_bwd(gates[g], dgates[g], cd)                       # through the last Sigmoid
+            dz = dz_all[g * B:(g + 1) * B]
             for i in range(pairs - 1, -1, -1):
                 w, b = params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]
                 dW, db = ops.wgrad(dz, acts[i], bias_of=1)                      # [out,in], [out]
                 grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
                 grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
                 wt = ctx.w_t[Lyr + g * pairs + i]                               # [in,out]
-                if i > 0 or lead:
+                if i > 0:
                     ds = ops.linear(dz, wt, None)
-                    dz = ops.sigmoid_bwd(acts[i], ds, cd if i > 0 else torch.float32)
+                    dz = ops.sigmoid_bwd(acts[i], ds, cd)
+                elif lead:
+                    ds = ops.linear(dz, wt, None)
+                    if da is None:
+                        da = ops.sigmoid_bwd(acts[0], ds, torch.float32, out=torch.empty((B, D), dtype=torch.float32, device=dev))
+                    else:
+                        ops.sigmoid_bwd(acts[0], ds, torch.float32, out=da, accumulate=True)
                 else:
-                    dz = ops.linear(dz, wt, None, out_dtype=torch.float32)
-            da += dz
+                    dlast = ops.linear(dz, wt, None, out_dtype=torch.float32)
+                    da = dlast if da is None else da + dlast
         ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
         grads_out[-2], grads_out[-1] = d_fcw, d_fcb
         if ctx.x_padded:        # hand back the whole [N, pitch] allocation (padding columns are finite)

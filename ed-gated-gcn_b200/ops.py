@@ -140,7 +140,7 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
 def trigger_gather(x: torch.Tensor, graph, anchor: torch.Tensor, lead_sigmoid: bool, want_raw: bool = True):
     B, D = graph.n_graphs, x.shape[1]
     raw = torch.empty((B, D), dtype=torch.float32, device=x.device) if want_raw else None
-    act = alloc_rows(B, D, x.dtype, x.device, zero=True)
+    act = alloc_rows(B, D, x.dtype, x.device)               # the kernel zeroes the padding columns
     L.call("edg_trigger_gather", L.ptr(x), L.dt(x), ld(x), L.ptr(graph.sent_ptr), L.ptr(anchor), B, D, L.ptr(raw),
            L.ptr(act), ld(act), int(lead_sigmoid), L.stream())
     return raw, act
@@ -170,10 +170,10 @@ def diversity_fwd(pooled: torch.Tensor) -> torch.Tensor:
     return xy
 
 
-def views_bwd(pooled, arg, gates, h, g_xy, g_pooled, dh, dgates, accumulate: bool) -> None:
+def views_bwd(pooled, arg, gates, h, g_xy, g_pooled, dh, dgates, acc_view: int = -1) -> None:
     V, B, D = pooled.shape
     L.call("edg_views_bwd", L.ptr(pooled), L.ptr(arg), L.ptr(gates), L.ptr(h), L.dt(h), ld(h), V, B, D, L.ptr(g_xy),
-           L.ptr(g_pooled), L.ptr(dh), ld(dh), L.ptr(dgates), int(accumulate), L.stream())
+           L.ptr(g_pooled), L.ptr(dh), ld(dh), L.ptr(dgates), int(acc_view), L.stream())
 
 
 def _dist_flag(dist: torch.Tensor) -> int:
@@ -202,11 +202,12 @@ def scores_kl_fwd(h, graph, gate, v, c, dist, want_units: bool = False):
 
 
 def head_bwd(h, graph, gate, v, dist, scores, kl_b, g_kl, g_scores, g_pooled, arg, g_xout, want_dh: bool,
-             want_dv: bool):
+             want_dv: bool, dgate_out: Optional[torch.Tensor] = None):
     B, D = gate.shape
     N = h.shape[0]
     dh = alloc_rows(N, D, h.dtype, h.device) if want_dh else None
-    dgate = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_dh else None
+    dgate = (dgate_out if dgate_out is not None else torch.empty((B, D), dtype=torch.float32, device=h.device)) \
+        if want_dh else None
     dv = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_dv else None
     dc = torch.empty((B,), dtype=torch.float32, device=h.device) if want_dv else None
     L.call("edg_head_bwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(v),
@@ -225,9 +226,11 @@ def gate_rows(h, graph, gate, out_dtype):
     return out
 
 
-def sigmoid_bwd(y: torch.Tensor, dy: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+def sigmoid_bwd(y: torch.Tensor, dy: torch.Tensor, out_dtype: torch.dtype, out: Optional[torch.Tensor] = None,
+                accumulate: bool = False) -> torch.Tensor:
+    """dz (+)= dy * y * (1 - y); the kernel also zeroes dz's padding columns."""
     R, C = y.shape
-    dz = alloc_rows(R, C, out_dtype, y.device, zero=True)
+    dz = out if out is not None else alloc_rows(R, C, out_dtype, y.device)
     L.call("edg_sigmoid_bwd", L.ptr(y), L.dt(y), ld(y), L.ptr(dy), L.dt(dy), ld(dy), R, C, L.ptr(dz), L.dt(dz),
-           ld(dz), L.stream())
+           ld(dz), int(accumulate), L.stream())
     return dz

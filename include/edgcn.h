@@ -176,11 +176,12 @@ int edg_diversity_fwd(const float* pooled, int32_t V, int32_t B, int32_t D, floa
 /* backward of the pooled views and the diversity term: with
  * dp[v] = g_xy/B * sum_{v'!=v} pooled[v'] (+ g_pooled[v] when given),
  *   dh[arg[v,b,d], d] += dp[v,b,d]*gates[v,b,d]   (added into dh)
- *   dgates[v,b,d]     (+)= dp[v,b,d]*h[arg[v,b,d], d]
+ *   dgates[v,b,d]      = dp[v,b,d]*h[arg[v,b,d], d]   (added to the existing value for v == acc_view,
+ *                        which already holds d gate_L from edg_head_bwd; -1 = overwrite everywhere)
  * g_xy is a device scalar (NULL = 0). */
 int edg_views_bwd(const float* pooled, const int32_t* arg, const float* gates, const void* h,
                   int dtype, int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy,
-                  const float* g_pooled, void* dh, int64_t lddh, float* dgates, int accumulate_dgates,
+                  const float* g_pooled, void* dh, int64_t lddh, float* dgates, int acc_view,
                   edg_stream stream);
 
 /* bert_amir5.py:645-648 in collapsed form:
@@ -218,10 +219,11 @@ int edg_gate_rows(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr
                   int32_t D, const float* gate, void* out, int out_dtype, int64_t ldo,
                   edg_stream stream);
 
-/* elementwise helpers of the gate MLP backward: dz = dy*y*(1-y) (nn.Sigmoid). */
+/* elementwise helper of the gate MLP backward: dz (+)= dy*y*(1-y) (nn.Sigmoid); writes the whole
+ * [R, lddz] allocation (padding columns = 0). */
 int edg_sigmoid_bwd(const void* y, int y_dtype, int64_t ldy, const void* dy, int dy_dtype,
                     int64_t lddy, int32_t R, int32_t C, void* dz, int dz_dtype, int64_t lddz,
-                    edg_stream stream);
+                    int accumulate, edg_stream stream);
 
 /* out[0] = scale * sum(in[0..n))   (deterministic; used for the batch means). */
 int edg_sum_scaled(const float* in, int64_t n, float scale, float* out, edg_stream stream);
