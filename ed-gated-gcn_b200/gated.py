@@ -117,8 +117,11 @@ class _GatedStackFn(torch.autograd.Function):
             p_leaf = pooled.detach().requires_grad_(True)
             logits = logits_fn(a_leaf, p_leaf)
             lg = logits.float()
-            v = lg @ fc_w[:, :D].float()                                           # [B,D]
-            c = (lg * (a_leaf @ fc_w[:, D:].float().t() + fc_b.float())).sum(1)    # [B]
+            # scores[b,t] = x_out[b,t,:] . v_b + c_b with [v_b | va_b] = logits_b @ fc.weight  (one skinny GEMM) and
+            # c_b = a_b . va_b + logits_b . fc.bias  (= logits_b . (Wfc[:, D:] a_b + bfc))
+            vva = lg @ fc_w.float()                                                # [B,2D]
+            v = vva[:, :D]
+            c = (a_leaf * vva[:, D:]).sum(1) + lg @ fc_b.float()                   # [B]
         # ---- importance scores and the softmax product (:645-648)
         # (also d kl/d v, d kl/d c per unit gradient: saves the backward pass one sweep over h_L)
         scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hs[-1], graph, gL, v.detach().contiguous(),
@@ -190,10 +193,9 @@ class _GatedStackFn(torch.autograd.Function):
                     p.grad = g if p.grad is None else p.grad + g
             if dv is not None:
                 lg = logits.detach().float()
-                # v = lg @ Wx, c = sum(lg * (a Wa^T + b)): explicit fp32 formulas for the fc gradients
-                t = lg * dc[:, None]                                           # [B,C]
-                d_fcw = torch.cat([lg.t() @ dv, t.t() @ a_leaf.detach()], dim=1).to(fc_w.dtype)
-                d_fcb = t.sum(0).to(fc_b.dtype)
+                # [v | va] = lg @ Wfc, c = a . va + lg . bfc: explicit fp32 formulas for the fc gradients (one GEMM)
+                d_fcw = (lg.t() @ torch.cat([dv, dc[:, None] * a_leaf.detach()], dim=1)).to(fc_w.dtype)
+                d_fcb = (dc @ lg).to(fc_b.dtype)
         gp_total = g_pooled
         if gp_head is not None:
             gp_total = gp_head.float() if gp_total is None else gp_total + gp_head.float()
