@@ -33,9 +33,16 @@ pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restri
   const int c = threadIdx.x * E;
   const int64_t BD = (int64_t)B * D;
   const uint32_t xs = stg_smem_u32(win) + threadIdx.x * 16;
-  wait_window(&bar);
+  bool waited = false;
   for (int s = w.s0 + threadIdx.y; s < w.s1; s += blockDim.y) {
     const int beg = __ldg(sent_ptr + s), end = __ldg(sent_ptr + s + 1);
+    // the gate vectors do not depend on the window: issue their loads BEFORE blocking on the bulk copy
+    float g[V][E];
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int k = 0; k < E; ++k) g[v][k] = (c + k < D) ? __ldg(gates + v * BD + (int64_t)s * D + c + k) : 0.f;
+    if (!waited) { wait_window(&bar); waited = true; }
     float m[E];
     int32_t where[E];
 #pragma unroll
@@ -53,12 +60,12 @@ pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restri
 #pragma unroll
       for (int k = 0; k < E; ++k)
         if (c + k < D) {
-          const float g = __ldg(gates + v * BD + (int64_t)s * D + c + k);
           const int64_t o = v * BD + (int64_t)s * D + c + k;
-          pooled[o] = (beg < end) ? m[k] * g : 0.f;
-          arg[o] = (beg < end) ? (g != 0.f ? where[k] : beg) : -1;
+          pooled[o] = (beg < end) ? m[k] * g[v][k] : 0.f;
+          arg[o] = (beg < end) ? (g[v][k] != 0.f ? where[k] : beg) : -1;
         }
   }
+  if (!waited) wait_window(&bar);        // never leave a bulk copy in flight into a dead block
 }
 
 // ---- importance scores, softmax product, and d kl / d (v, c) units (bert_amir5.py:645-648) ----------
@@ -69,6 +76,7 @@ pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restri
 //   P2 softmax statistics, kl_b and u_t = P_t (Q_t - kl_b) / B: warp per SENTENCE
 //   P3 dv_unit = gate * sum_t u_t h_t: thread = (chunk, sentence lane)
 constexpr int kSMaxQ = 4;
+constexpr int kWCache = 8;      // sentences per window whose gate*v vector is cached in shared memory
 
 template <typename T, int I64, int Q>
 __global__ void __launch_bounds__(256)
@@ -87,10 +95,21 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
   const int n = w.r1 - w.r0;
   float* sc_s = reinterpret_cast<float*>(win + (size_t)cap_rows * pitch);      // [cap_rows] scores, then u_t
   float* dq_s = sc_s + cap_rows;                                               // [cap_rows] float(dist)
+  int32_t* rs_s = reinterpret_cast<int32_t*>(dq_s + cap_rows);                 // [cap_rows] sentence of each row
+  float* w_s = reinterpret_cast<float*>(rs_s + cap_rows);                      // [kWCache][chunks*E] gate*v of the first sentences
   const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+  const int width = chunks * E;
   const uint32_t xs = stg_smem_u32(win);
-  // P0
-  for (int i = tid; i < n; i += 256) dq_s[i] = sdist_at<I64>(dist, w.r0 + i);
+  // P0 (overlaps the bulk copy): small per-row / per-sentence data -> shared memory, coalesced
+  for (int i = tid; i < n; i += 256) { dq_s[i] = sdist_at<I64>(dist, w.r0 + i); rs_s[i] = __ldg(row_sent + w.r0 + i); }
+  {
+    const int ns = min(w.s1 - w.s0, kWCache);
+    for (int i = tid; i < ns * width; i += 256) {
+      const int si = i / width, d = i - si * width;
+      w_s[i] = d < D ? __ldg(gate + (int64_t)(w.s0 + si) * D + d) * __ldg(vvec + (int64_t)(w.s0 + si) * D + d) : 0.f;
+    }
+  }
+  __syncthreads();
   wait_window(&bar);
   // P1: one row per warp iteration; consecutive rows mostly share the sentence, so its weights stay in registers
   {
@@ -98,16 +117,18 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
     float wq[Q][E];
     float cb = 0.f;
     for (int lr = warp; lr < n; lr += 8) {
-      const int s = __ldg(row_sent + w.r0 + lr);
+      const int s = rs_s[lr];
       if (s != cur) {
         cur = s;
+        const int si = s - w.s0;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const int c = (lane + 32 * q) * E;
 #pragma unroll
           for (int k = 0; k < E; ++k) {
             const bool ok = (lane + 32 * q < chunks) && (c + k < D);
-            wq[q][k] = ok ? __ldg(gate + (int64_t)s * D + c + k) * __ldg(vvec + (int64_t)s * D + c + k) : 0.f;
+            if (si < kWCache) wq[q][k] = ok ? w_s[si * width + c + k] : 0.f;
+            else wq[q][k] = ok ? __ldg(gate + (int64_t)s * D + c + k) * __ldg(vvec + (int64_t)s * D + c + k) : 0.f;
           }
         }
         cb = cvec ? __ldg(cvec + s) : 0.f;
@@ -230,25 +251,36 @@ head_bwd_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __re
     }
     if (lane == 0 && dc) dc[s] = tot;
   }
-  __syncthreads();
-  wait_window(&bar);
+  // (the block barrier that publishes ds_s and the wait on the window sit inside phase 2, after its prefetches)
   // phase 2: thread = (16-byte column chunk x, sentence lane y).  With sf = sum_t ds_t h_t (per column):
   //   dh_t = ds_t * (g v)  [+ g gp on the arg-max row]      dv = g * sf      dgate = v * sf + gp * h_arg
-  // so the row loop is 2 instructions per element; the arg-max row is patched afterwards (same thread wrote it).
+  // Every per-sentence vector is loaded before blocking on the window; h_arg comes from shared memory.
   const int c = threadIdx.x * E;
   const uint32_t xs = stg_smem_u32(win) + threadIdx.x * 16;
-  for (int s = w.s0 + threadIdx.y; s < w.s1; s += blockDim.y) {
-    const int beg = __ldg(sent_ptr + s), end = __ldg(sent_ptr + s + 1);
-    float g[E], vv[E], gv[E], sf[E], xg[E];
+  float g[E], vv[E], gp[E];
+  int32_t where[E];
+  int beg = 0, end = 0;
+  auto load_sentence = [&](int s) {
+    beg = __ldg(sent_ptr + s); end = __ldg(sent_ptr + s + 1);
 #pragma unroll
     for (int k = 0; k < E; ++k) {
       const bool ok = c + k < D;
       const int64_t o = (int64_t)s * D + c + k;
       g[k] = ok ? __ldg(gate + o) : 0.f;
       vv[k] = (ok && vvec) ? __ldg(vvec + o) : 0.f;
-      gv[k] = g[k] * vv[k];
-      sf[k] = 0.f; xg[k] = 0.f;
+      gp[k] = (ok && g_pooled) ? __ldg(g_pooled + o) : 0.f;
+      where[k] = (ok && g_pooled) ? __ldg(arg + o) : -1;
     }
+  };
+  int s = w.s0 + threadIdx.y;
+  if (s < w.s1) load_sentence(s);          // in flight while the block waits below
+  __syncthreads();                         // publishes ds_s (phase 1)
+  wait_window(&bar);
+  for (bool first = true; s < w.s1; s += blockDim.y, first = false) {
+    if (!first) load_sentence(s);
+    float gv[E], ggp[E], sf[E], xg[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) { gv[k] = g[k] * vv[k]; ggp[k] = g[k] * gp[k]; sf[k] = 0.f; xg[k] = 0.f; }
     uint32_t addr = xs + (uint32_t)((beg - w.r0) * pitch);
     for (int t = beg; t < end; ++t, addr += pitch) {
       float f[E], o[E];
@@ -264,7 +296,10 @@ head_bwd_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __re
         for (int k = 0; k < E; ++k) o[k] = dst * gv[k];
       }
 #pragma unroll
-      for (int k = 0; k < E; ++k) sf[k] = fmaf(dst, f[k], sf[k]);
+      for (int k = 0; k < E; ++k) {
+        sf[k] = fmaf(dst, f[k], sf[k]);
+        if (where[k] == t) o[k] += ggp[k];           // the arg-max row also receives the pooled gradient
+      }
       if (dh) Vec16<T>::store(dh + (int64_t)t * lddh + c, o);
     }
 #pragma unroll
@@ -272,17 +307,9 @@ head_bwd_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __re
       if (c + k < D) {
         const int64_t o = (int64_t)s * D + c + k;
         float dg = fmaf(vv[k], sf[k], xg[k]);
-        if (g_pooled) {
-          const float gp = __ldg(g_pooled + o);
-          const int wrow = __ldg(arg + o);
-          if (wrow >= 0) {
-            const T* hp = reinterpret_cast<const T*>(win + (size_t)(wrow - w.r0) * pitch) + c + k;
-            dg = fmaf(gp, to_f32(*hp), dg);
-            if (dh) {
-              T* p = dh + (int64_t)wrow * lddh + c + k;
-              *p = from_f32<T>(to_f32(*p) + g[k] * gp);
-            }
-          }
+        if (where[k] >= 0) {
+          const T* hp = reinterpret_cast<const T*>(win + (size_t)(where[k] - w.r0) * pitch) + c + k;
+          dg = fmaf(gp[k], to_f32(*hp), dg);
         }
         if (dgate) dgate[o] = dg;
         if (dv) dv[o] = g[k] * sf[k];
@@ -361,9 +388,10 @@ int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const 
   constexpr int E = Vec16<T>::kElems;
   const int chunks = (D + E - 1) / E;
   if (!row_sent || max_len <= 0 || chunks > 32 * kSMaxQ) return 1;
-  const WindowPlan p = plan_window((size_t)ldh * sizeof(T), max_len, 8);
+  const size_t wcache = (size_t)kWCache * chunks * E * sizeof(float);
+  const WindowPlan p = plan_window((size_t)ldh * sizeof(T), max_len, 12, wcache);
   if (p.tile_rows < 8) return 1;
-  const size_t smem = p.smem_rows + (size_t)p.cap_rows * 2 * sizeof(float);
+  const size_t smem = p.smem_rows + (size_t)p.cap_rows * 3 * sizeof(float) + wcache;
   const int Q = (chunks + 31) / 32;
 #define EDG_SC(QQ)                                                                                                       \
   return dist_i64 ? launch_scores_q<T, 1, QQ>(h, ldh, sent_ptr, row_sent, N, B, D, chunks, p, smem, gate, v, c, dist, scores, \
