@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -328,9 +328,9 @@ def run_b200(args):
         sampler.start()
     ms_total = timed(run_resident, args.steps, args.warmup)
     launches = kernels_per_step * args.steps
-    clocks = sampler.stop() if rank == 0 else None
     loss_val = float(run_resident().item())
     ms_e2e = timed(run_e2e, args.steps, max(3, args.warmup // 2))
+    clocks = sampler.stop() if rank == 0 else None          # sampled across both timed regions
 
     graphs_total = batch.n_graphs * world
     if world > 1:
