@@ -170,7 +170,8 @@ __device__ __forceinline__ void softmax_stats(const float* scores, const void* d
   zs = warp_sum(zs); zq = warp_sum(zq);
 }
 
-constexpr int kMaxQ = 4;     // 16-byte chunks per lane: D <= 32*4*E (1024 for bf16, 512 for fp32)
+// 16-byte chunks per lane: 32 fp32 values per lane either way, i.e. D <= 1024 for both dtypes
+template <typename T> struct ScoresQ { static constexpr int value = 32 / Vec16<T>::kElems; };
 
 template <typename T, int I64>
 __global__ void __launch_bounds__(128)
@@ -179,6 +180,7 @@ scores_kl_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
                      const float* __restrict__ cvec, const void* __restrict__ dist, float* __restrict__ scores,
                      float* __restrict__ kl_b, float* __restrict__ dv_unit, float* __restrict__ dc_unit) {
   constexpr int E = Vec16<T>::kElems;
+  constexpr int kMaxQ = ScoresQ<T>::value;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
@@ -569,7 +571,7 @@ extern "C" int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const in
   EDG_DISPATCH_T(dtype, {
     constexpr int E = Vec16<T>::kElems;
     const int chunks = (D + E - 1) / E;
-    if (chunks > 32 * kMaxQ) return EDG_ERR_UNSUPPORTED;
+    if (chunks > 32 * ScoresQ<T>::value) return EDG_ERR_UNSUPPORTED;
     if (staged_enabled()) {
       const int rc = scores_kl_staged<T>(h, ldh, sent_ptr, row_sent, N, B, D, max_len, gate, v, c, dist, dist_i64, scores, kl_b,
                                          dv_unit, dc_unit, s);

@@ -243,8 +243,11 @@ def test_stack_matches_full_reference_forward_backward(dtype):
 @pytest.mark.parametrize("cfg", [dict(L=2, arch="sig-2", D=300, C=34, B=32, lo=5, hi=50),     # config C1
                                  dict(L=3, arch="3", D=64, C=7, B=9, lo=1, hi=20),
                                  dict(L=1, arch="2", D=32, C=2, B=5, lo=2, hi=9),
-                                 dict(L=4, arch="sig-3", D=128, C=5, B=6, lo=30, hi=90)],
-                         ids=["C1", "L3", "L1", "L4"])
+                                 dict(L=4, arch="sig-3", D=128, C=5, B=6, lo=30, hi=90),
+                                 # config-4 shape: sentences too long for a shared-memory window (per-sentence / flat
+                                 # kernels), D = 768 (streaming tcgen05 GEMM, 7 M tiles in wgrad), a hub of degree ~n/2
+                                 dict(L=2, arch="sig-2", D=768, C=5, B=4, lo=200, hi=512, skewed=True)],
+                         ids=["C1", "L3", "L1", "L4", "C4long"])
 def test_stack_packed_rows_vs_oracle(dtype, cfg):
     """Packed layout (no pad rows): the oracle is run per sentence with T = n_b, which is the
     same convention (SURVEY hard part 2)."""
@@ -252,7 +255,7 @@ def test_stack_packed_rows_vs_oracle(dtype, cfg):
     from ed_gated_gcn_b200 import synth
     tol = tol_for(dtype)
     torch.manual_seed(1000 + cfg["D"] + cfg["L"])       # the head (nn.Linear) initialises from the global RNG
-    batch = synth.make_batch(cfg["B"], cfg["lo"], cfg["hi"], seed=cfg["D"])
+    batch = synth.make_batch(cfg["B"], cfg["lo"], cfg["hi"], seed=cfg["D"], skewed=cfg.get("skewed", False))
     D, C, B, Lyr = cfg["D"], cfg["C"], cfg["B"], cfg["L"]
     stack = E.GatedGCNStack(D, n_layers=Lyr, n_classes=C, gate_arch=cfg["arch"], compute_dtype=dtype).to(DEV)
     gen = torch.Generator().manual_seed(3)
