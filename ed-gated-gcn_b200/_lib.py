@@ -35,6 +35,9 @@ SIGNATURES = {
     "edg_linear": (c_int, [_P, c_int, _L, _I, _I, _P, _L, _I, _P, c_int, _P, c_int, _L, _P]),
     "edg_wgrad_workspace": (_Z, [_I, _I, _I, c_int]),
     "edg_wgrad": (c_int, [_P, _L, _I, _P, _L, _I, c_int, _I, _P, _L, _P, c_int, c_int, _P, _Z, _P]),
+    "edg_wgrad_batch_workspace": (_Z, [_I, _I, _I, _I]),
+    "edg_wgrad_batch": (c_int, [_I, _P, _L, _I, _P, _L, _I, c_int, _I, _P, _L, _P, c_int, _P, _Z, _P]),
+    "edg_mlp_chain": (c_int, [c_int, _I, _I, _P, _L, _P, _I, _I, _P]),
     "edg_cast_2d": (c_int, [_P, _L, _I, _I, _P, c_int, _L, c_int, _P]),
     "edg_cast_batch": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "edg_trigger_gather": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _P, _P, _L, c_int, _P]),
@@ -43,14 +46,29 @@ SIGNATURES = {
     "edg_diversity_fwd": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "edg_views_bwd": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _L, _P, c_int, _P]),
     "edg_scores_kl_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "edg_fc_head_fwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _P, _P, _P]),
+    "edg_fc_head_bwd_workspace": (_Z, [_I, _I, _I]),
+    "edg_fc_head_bwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _P, _P, _P, _I, _I, _I, _P, _L, _P, _P, _L, _P, _P, _Z, _P]),
     "edg_head_bwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _L,
                              _P, _L, _P, _P, _P, _I, _P, _I, _P]),
+    "edg_segment_mean": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _P, c_int, _L, _P]),
+    "edg_segment_mean_bwd": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _P, _L, _I, _P]),
+    "edg_lr_pool_fwd": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "edg_lr_pool_bwd": (c_int, [_P, _P, _I, _I, _P, c_int, _L, _P]),
     "edg_gate_rows": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, c_int, _L, _P]),
     "edg_sigmoid_bwd": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, c_int, _L, c_int, _P]),
     "edg_sum_scaled": (c_int, [_P, _L, _F, _P, _P]),
     "edg_colsum_workspace": (_Z, [_I, _I]),
     "edg_colsum": (c_int, [_P, c_int, _L, _I, _I, _P, c_int, _P, _Z, _P]),
 }
+
+
+
+class ChainStage(ctypes.Structure):
+    """``edg_chain_stage`` of include/edgcn.h (one Linear of one gate chain)."""
+    _fields_ = [("w", c_void_p), ("ldw", c_int64), ("bias", c_void_p), ("y", c_void_p), ("ldy", c_int64),
+                ("out", c_void_p), ("ldo", c_int64), ("out_dtype", c_int)]
+
 
 _lib = None
 
@@ -91,7 +109,7 @@ def _kernels_of(name: str, args) -> int:
         return 2 + (2 if args[11] else 0)
     if name == "edg_csr_from_heads":
         return 3
-    if name in ("edg_csr_from_dense_count", "edg_diversity_fwd", "edg_colsum"):
+    if name in ("edg_csr_from_dense_count", "edg_diversity_fwd", "edg_colsum", "edg_fc_head_bwd", "edg_wgrad_batch"):
         return 2
     if name == "edg_pool_fwd":
         return (args[7] + 3) // 4

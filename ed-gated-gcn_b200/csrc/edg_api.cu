@@ -28,6 +28,9 @@ int launch_linear_tc(const void* A, int64_t lda, int M, int K, const void* W, in
 int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, float* dW,
                     int64_t lddw, float* dbias, int bias_of, int accumulate, float* ws, cudaStream_t s);
 size_t wgrad_tc_workspace(int R, int K1, int K2);
+int launch_wgrad_tc_batch(int n, const void* const* A, int64_t lda, int K1, const void* const* B, int64_t ldb, int K2, int R,
+                          float* const* dW, int64_t lddw, float* const* dbias, int bias_of, float* ws, cudaStream_t s);
+size_t wgrad_tc_batch_workspace(int n, int R, int K1, int K2);
 
 // Bring-up switch for the GPU tests only: EDG_FORCE_SIMT=1 routes bf16 GEMMs through the FFMA
 // kernels so a tcgen05 result can be cross-checked on the same inputs.  Not a product path.
@@ -124,4 +127,26 @@ extern "C" int edg_wgrad(const void* A, int64_t lda, int32_t K1, const void* B, 
     rc = edg_colsum(X, dtype, ldx, R, Cc, dbias, accumulate, cws, edg_colsum_workspace(R, Cc), stream);
   }
   return rc;
+}
+
+extern "C" size_t edg_wgrad_batch_workspace(int32_t n, int32_t R, int32_t K1, int32_t K2) {
+  if (n <= 0 || R <= 0 || K1 <= 0 || K2 <= 0) return 16;
+  return wgrad_tc_batch_workspace(n, R, K1, K2) + 256;
+}
+
+extern "C" int edg_wgrad_batch(int32_t n, const void* const* A, int64_t lda, int32_t K1, const void* const* B, int64_t ldb,
+                               int32_t K2, int dtype, int32_t R, float* const* dW, int64_t lddw, float* const* dbias,
+                               int bias_of, void* ws, size_t ws_bytes, edg_stream stream) {
+  if (n <= 0 || R <= 0 || K1 <= 0 || K2 <= 0 || !A || !B || !dW || lddw < K2 || !ws) return EDG_ERR_ARG;
+  if (bias_of < 0 || bias_of > 2 || (bias_of && !dbias)) return EDG_ERR_ARG;
+  if (dtype != EDG_BF16) return EDG_ERR_DTYPE;              // the fp32-parity mode keeps one launch per problem
+  if (n > 8) return EDG_ERR_UNSUPPORTED;
+  if (lda < K1 || ldb < K2) return EDG_ERR_ARG;
+  if (!aligned16(ws) || !row_pitch_ok(dtype, lda) || !row_pitch_ok(dtype, ldb)) return EDG_ERR_ALIGN;
+  for (int i = 0; i < n; ++i) {
+    if (!A[i] || !B[i] || !dW[i] || (bias_of && !dbias[i])) return EDG_ERR_ARG;
+    if (!aligned16(A[i]) || !aligned16(B[i])) return EDG_ERR_ALIGN;
+  }
+  if (ws_bytes < edg_wgrad_batch_workspace(n, R, K1, K2)) return EDG_ERR_WORKSPACE;
+  return launch_wgrad_tc_batch(n, A, lda, K1, B, ldb, K2, R, dW, lddw, dbias, bias_of, (float*)ws, (cudaStream_t)stream);
 }

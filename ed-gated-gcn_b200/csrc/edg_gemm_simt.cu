@@ -206,6 +206,32 @@ void launch_split_reduce_bias(const float* partial, int splits, int K1, int K2, 
                                                                          bias_of, accumulate);
 }
 
+// the same for n problems in one launch: blockIdx.y = problem, slabs [problem][split][K1e][K2e]
+struct ReduceBatchPtrs { float* dW[8]; float* dbias[8]; };
+__global__ void split_reduce_bias_batch_kernel(const float* __restrict__ partial, int splits, int K1, int K2, int K1e, int K2e,
+                                               const __grid_constant__ ReduceBatchPtrs ptrs, int64_t lddw, int bias_of) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = (int64_t)K1e * K2e;
+  if (idx >= tot) return;
+  const int p = blockIdx.y;
+  const float* base = partial + (int64_t)p * splits * tot;
+  const int m = (int)(idx / K2e), n = (int)(idx - (int64_t)m * K2e);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += base[(int64_t)z * tot + idx];
+  if (m < K1 && n < K2) ptrs.dW[p][(int64_t)m * lddw + n] = s;
+  else if (bias_of == 2 && m == K1 && n < K2) ptrs.dbias[p][n] = s;
+  else if (bias_of == 1 && n == K2 && m < K1) ptrs.dbias[p][m] = s;
+}
+
+void launch_split_reduce_bias_batch(const float* partial, int n, int splits, int K1, int K2, int K1e, int K2e,
+                                    float* const* dW, int64_t lddw, float* const* dbias, int bias_of, cudaStream_t s) {
+  ReduceBatchPtrs ptrs;
+  for (int i = 0; i < 8; ++i) { ptrs.dW[i] = i < n ? dW[i] : nullptr; ptrs.dbias[i] = (i < n && dbias) ? dbias[i] : nullptr; }
+  const int64_t tot = (int64_t)K1e * K2e;
+  split_reduce_bias_batch_kernel<<<dim3((unsigned)((tot + 255) / 256), n), 256, 0, s>>>(partial, splits, K1, K2, K1e, K2e, ptrs,
+                                                                                        lddw, bias_of);
+}
+
 void launch_split_reduce(const float* partial, int splits, int K1, int K2, float* dW, int64_t lddw, int accumulate,
                          cudaStream_t s) {
   const int64_t tot = (int64_t)K1 * K2;

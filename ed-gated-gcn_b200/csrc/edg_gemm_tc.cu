@@ -11,6 +11,7 @@
 // of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "edg_common.cuh"
 
@@ -798,16 +799,16 @@ __device__ __forceinline__ void plant_ones(uint32_t box_base, int col_in_box, in
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                int R, int K1e, int K2e, int block_n, int rows_per, uint32_t idesc, int ones_a, int ones_b,
-                float* __restrict__ partial) {
+// body shared by the single-problem kernel and the batched one (`split` = row range, `slot` = partial-sum slab)
+__device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& map_a, const CUtensorMap& map_b, int split, int slot,
+                                              int R, int K1e, int K2e, int block_n, int rows_per, uint32_t idesc,
+                                              int ones_a, int ones_b, float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout L;
   L.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * block_n;
-  const int r_beg = blockIdx.z * rows_per;
+  const int r_beg = split * rows_per;
   const int r_end = min(R, r_beg + rows_per);
   const int num_kb = (r_end > r_beg) ? (r_end - r_beg + kBlockK - 1) / kBlockK : 0;
   const int n_boxes = block_n / 64;
@@ -870,7 +871,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (lane == 0) umma_commit(L.tfull(0));
   } else {
     const int q = warp & 3;
-    float* P = partial + (int64_t)blockIdx.z * K1e * K2e;
+    float* P = partial + (int64_t)slot * K1e * K2e;
     const int row = m0 + q * 32 + lane;
     if (num_kb > 0) {
       mbar_wait(L.tfull(0), 0);
@@ -888,6 +889,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                int R, int K1e, int K2e, int block_n, int rows_per, uint32_t idesc, int ones_a, int ones_b,
+                float* __restrict__ partial) {
+  wgrad_tc_body(map_a, map_b, blockIdx.z, blockIdx.z, R, K1e, K2e, block_n, rows_per, idesc, ones_a, ones_b, partial);
+}
+
+// Several same-shaped weight gradients in ONE launch (the Linears of the gate MLPs: 4 problems of
+// [D x B] x [B x D] at C2): blockIdx.z = problem * splits + split; slab z of `partial` is problem-major.
+constexpr int kWgradBatchMax = 8;
+struct WgradBatchMaps {
+  CUtensorMap a[kWgradBatchMax];
+  CUtensorMap b[kWgradBatchMax];
+};
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_batch_kernel(const __grid_constant__ WgradBatchMaps maps, int splits, int R, int K1e, int K2e, int block_n,
+                      int rows_per, uint32_t idesc, int ones_a, int ones_b, float* __restrict__ partial) {
+  const int p = blockIdx.z / splits, split = blockIdx.z - p * splits;
+  wgrad_tc_body(maps.a[p], maps.b[p], split, blockIdx.z, R, K1e, K2e, block_n, rows_per, idesc, ones_a, ones_b, partial);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1329,6 +1351,54 @@ int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t l
   wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, R, K1e, K2e, p.block_n, p.rows_per, idesc,
                                                      bias_of == 2 ? K1 : -1, bias_of == 1 ? K2 : -1, ws);
   launch_split_reduce_bias(ws, p.splits, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, accumulate, s);
+  return check_launch();
+}
+
+// defined in edg_gemm_simt.cu
+void launch_split_reduce_bias_batch(const float* partial, int n, int splits, int K1, int K2, int K1e, int K2e,
+                                    float* const* dW, int64_t lddw, float* const* dbias, int bias_of, cudaStream_t s);
+
+size_t wgrad_tc_batch_workspace(int n, int R, int K1, int K2) {
+  size_t best = 0;
+  for (int v = 0; v < 3; ++v) {
+    const int K1e = K1 + (v == 2), K2e = K2 + (v == 1);
+    WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
+    const size_t b = (size_t)p.splits * K1e * K2e * sizeof(float);
+    if (b > best) best = b;
+  }
+  return best * (size_t)n;
+}
+
+int launch_wgrad_tc_batch(int n, const void* const* A, int64_t lda, int K1, const void* const* B, int64_t ldb, int K2, int R,
+                          float* const* dW, int64_t lddw, float* const* dbias, int bias_of, float* ws, cudaStream_t s) {
+  if (n > kWgradBatchMax) return EDG_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_tc_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
+  WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
+  // the problems share the SMs: fewer row splits per problem keep the partial-sum traffic down
+  int splits = (kNumSMs + p.m_tiles * p.n_tiles * n - 1) / (p.m_tiles * p.n_tiles * n);
+  if (splits > p.splits) splits = p.splits;
+  if (splits < 1) splits = 1;
+  const int rows_per = (((R + splits - 1) / splits) + kBlockK - 1) / kBlockK * kBlockK;
+  splits = (R + rows_per - 1) / rows_per;
+  WgradBatchMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < n; ++i) {
+    int rc = make_map_bf16(&maps.a[i], A[i], R, K1, lda, 64, kBlockK);
+    if (rc) return rc;
+    rc = make_map_bf16(&maps.b[i], B[i], R, K2, ldb, 64, kBlockK);
+    if (rc) return rc;
+  }
+  const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 1, 1);
+  dim3 grid(p.m_tiles, p.n_tiles, splits * n);
+  wgrad_tc_batch_kernel<<<grid, kThreads, kSmemBytes, s>>>(maps, splits, R, K1e, K2e, p.block_n, rows_per, idesc,
+                                                           bias_of == 2 ? K1 : -1, bias_of == 1 ? K2 : -1, ws);
+  launch_split_reduce_bias_batch(ws, n, splits, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, s);
   return check_launch();
 }
 

@@ -18,6 +18,7 @@ reference block.  CUDA only; no fallback.
 """
 from __future__ import annotations
 
+import os
 from collections import namedtuple
 from typing import Callable, List, Optional, Sequence
 
@@ -36,6 +37,15 @@ GATE_ARCHS = {
     "3": (False, 3),        # BertAmir/BertAmir4    bert_amir.py:31-36
     "sig-3": (True, 3),     # BertAmir2             bert_amir.py:180-187
 }
+
+
+
+def _chain_ok(cd: torch.dtype, D: int, n_gates: int, pairs: int) -> bool:
+    """The fused gate-MLP kernel (``edg_mlp_chain``) covers bf16, D <= 320, <= 4 gates, <= 3 Linears per gate;
+    everything else runs one ``edg_linear`` per layer.  EDG_MLP_CHAIN=0 forces the per-layer kernels (bring-up)."""
+    return (cd == torch.bfloat16 and 16 <= D <= ops.MLP_CHAIN_MAX_D and n_gates <= ops.MLP_CHAIN_MAX_GROUPS
+            and pairs <= ops.MLP_CHAIN_MAX_STAGES and os.environ.get("EDG_MLP_CHAIN", "1") != "0")
+
 
 StackOutput = namedtuple("StackOutput", ["logits", "xy", "kl", "scores", "pooled", "x_out", "pooled_arg", "view_arg"])
 
@@ -83,7 +93,23 @@ class _GatedStackFn(torch.autograd.Function):
         a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
         gates = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
         gate_saved = []
-        for g in range(Lyr):
+        use_chain = _chain_ok(cd, D, Lyr, pairs)
+        ctx.use_chain = use_chain
+        if use_chain:
+            # every Linear+Sigmoid of every gate in ONE launch (activation tile resident in shared memory)
+            stages = []
+            for g in range(Lyr):
+                acts, st = [s0], []
+                for i, (w, b) in enumerate(gate_p[g]):
+                    last = i == pairs - 1
+                    out = gates[g] if last else ops.alloc_rows(B, D, cd, x.device)
+                    st.append(dict(w=w_n[id(w)], bias=b.detach().float().contiguous(), out=out))
+                    if not last:
+                        acts.append(out)
+                stages.append(st)
+                gate_saved.append(acts)
+            ops.mlp_chain(0, [s0] * Lyr, stages, B, D)
+        for g in range(Lyr if not use_chain else 0):
             s = s0
             acts = [s0]
             for i, (w, b) in enumerate(gate_p[g]):
@@ -111,27 +137,25 @@ class _GatedStackFn(torch.autograd.Function):
         gL = gates[Lyr - 1]
         pooled, p_arg = ops.pool_fwd(hs[-1], graph, gL.unsqueeze(0))
         pooled, p_arg = pooled[0], p_arg[0]
-        # ---- classifier head on the host (torch autograd, tiny [B,*] tensors)  (:643, :645 collapsed)
+        # ---- classifier head: logits_fn is the model's own dense head (host torch, :643); the per-sentence
+        # operands of the collapsed scores, [v_b | va_b] = logits_b @ fc.weight and
+        # c_b = a_b . va_b + logits_b . fc.bias  (= logits_b . (Wfc[:, D:] a_b + bfc)), are one kernel
         with torch.enable_grad():
             a_leaf = a_raw.detach().requires_grad_(True)
             p_leaf = pooled.detach().requires_grad_(True)
             logits = logits_fn(a_leaf, p_leaf)
-            lg = logits.float()
-            # scores[b,t] = x_out[b,t,:] . v_b + c_b with [v_b | va_b] = logits_b @ fc.weight  (one skinny GEMM) and
-            # c_b = a_b . va_b + logits_b . fc.bias  (= logits_b . (Wfc[:, D:] a_b + bfc))
-            vva = lg @ fc_w.float()                                                # [B,2D]
-            v = vva[:, :D]
-            c = (a_leaf * vva[:, D:]).sum(1) + lg @ fc_b.float()                   # [B]
+        lg = logits.detach().float().contiguous()
+        fcw32, fcb32 = fc_w.detach().float().contiguous(), fc_b.detach().float().contiguous()
+        v, c = ops.fc_head_fwd(lg, fcw32, fcb32, a_raw)
         # ---- importance scores and the softmax product (:645-648)
         # (also d kl/d v, d kl/d c per unit gradient: saves the backward pass one sweep over h_L)
-        scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hs[-1], graph, gL, v.detach().contiguous(),
-                                                       c.detach().contiguous(), dist, want_units=True)
+        scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hs[-1], graph, gL, v, c, dist, want_units=True)
         ctx.kl_units = (dvu, dcu)
         x_out = ops.gate_rows(hs[-1], graph, gL, cd) if cfg["return_x_out"] else None
 
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not zero tensors
         ctx.cfg = cfg
-        ctx.head = (a_leaf, p_leaf, logits, v, c)
+        ctx.head = (a_leaf, p_leaf, logits, lg, a_raw, v)
         ctx.gate_saved = gate_saved
         ctx.n_params = len(params)
         ctx.x_dtype = x.dtype
@@ -155,7 +179,7 @@ class _GatedStackFn(torch.autograd.Function):
         params = saved[7 + 2 * Lyr:]
         B, N, D = graph.n_graphs, graph.n_rows, xr.shape[1]
         dev = xr.device
-        a_leaf, p_leaf, logits, v, c = ctx.head
+        a_leaf, p_leaf, logits, lg, a_raw, v = ctx.head
         gL = gates[Lyr - 1]
         hL = hs[-1]
 
@@ -166,36 +190,34 @@ class _GatedStackFn(torch.autograd.Function):
         if g_xout is not None:
             g_xout = ops.as_rows(g_xout, cd)
         need_scores = g_kl is not None or g_scores is not None
-        # ---- pass A over h_L: dv, dc (inputs of the host head's backward)
-        dv = dc = None
-        if need_scores and g_scores is None:
-            dv, dc = ctx.kl_units[0] * g_kl, ctx.kl_units[1] * g_kl          # precomputed in the forward sweep
-        elif need_scores:
-            _, _, dv, dc = ops.head_bwd(hL, graph, gL, v.detach().contiguous(), dist, scores, kl_b, g_kl, g_scores,
-                                        None, None, None, want_dh=False, want_dv=True)
-        # ---- host head backward: logits_fn, v, c  ->  d a, d pooled, and .grad of the head's own parameters
-        outs, grads = [], []
-        if g_logits is not None:
-            outs.append(logits); grads.append(g_logits.to(logits.dtype))
-        if dv is not None:
-            outs += [v, c]; grads += [dv, dc]
+        # ---- d v, d c: the per-unit gradients of the forward sweep times d kl, or (when scores itself carries
+        # gradient) pass A over h_L
         fc_w, fc_b = params[-2], params[-1]
-        d_fcw = d_fcb = None
+        d_fcw = d_fcb = da_fc = None
+        g_lg = g_logits.float() if g_logits is not None else None
+        if need_scores:
+            if g_scores is None:
+                dv_in, dc_in, scale = ctx.kl_units[0], ctx.kl_units[1], g_kl
+            else:
+                _, _, dv_in, dc_in = ops.head_bwd(hL, graph, gL, v, dist, scores, kl_b, g_kl, g_scores,
+                                                  None, None, None, want_dh=False, want_dv=True)
+                scale = None
+            # backward of [v | va] = logits @ fc.weight, c = a . va + logits . fc.bias  (one kernel + a reduction)
+            d_lg, da_fc, d_fcw, d_fcb = ops.fc_head_bwd(lg, fc_w.detach().float().contiguous(),
+                                                        fc_b.detach().float().contiguous(), a_raw, dv_in, dc_in, scale)
+            d_fcw, d_fcb = d_fcw.to(fc_w.dtype), d_fcb.to(fc_b.dtype)
+            g_lg = d_lg if g_lg is None else g_lg + d_lg
+        # ---- host head backward through logits_fn: d a, d pooled, and .grad of the parameters it closes over
         ga_head = gp_head = None
-        if outs:
-            # one sweep through the host head graph: d a, d pooled, and the gradients of the
-            # parameters logits_fn closes over (e.g. self.dense), which are delivered to .grad here
+        if g_lg is not None and logits.requires_grad:
             cap = [p for p in cfg["head_params"] if p.requires_grad]
-            res = torch.autograd.grad(outs, [a_leaf, p_leaf] + cap, grads, allow_unused=True)
+            res = torch.autograd.grad([logits], [a_leaf, p_leaf] + cap, [g_lg.to(logits.dtype)], allow_unused=True)
             ga_head, gp_head = res[0], res[1]
             for p, g in zip(cap, res[2:]):
                 if g is not None:
                     p.grad = g if p.grad is None else p.grad + g
-            if dv is not None:
-                lg = logits.detach().float()
-                # [v | va] = lg @ Wfc, c = a . va + lg . bfc: explicit fp32 formulas for the fc gradients (one GEMM)
-                d_fcw = (lg.t() @ torch.cat([dv, dc[:, None] * a_leaf.detach()], dim=1)).to(fc_w.dtype)
-                d_fcb = (dc @ lg).to(fc_b.dtype)
+        if da_fc is not None:
+            ga_head = da_fc if ga_head is None else ga_head.float() + da_fc
         gp_total = g_pooled
         if gp_head is not None:
             gp_total = gp_head.float() if gp_total is None else gp_total + gp_head.float()
@@ -204,7 +226,7 @@ class _GatedStackFn(torch.autograd.Function):
         views_active = g_xy is not None and Lyr > 1
         if not views_active and Lyr > 1:
             dgates[:Lyr - 1].zero_()                                  # no diversity gradient: the other gates get none
-        dh, _, _, _ = ops.head_bwd(hL, graph, gL, v.detach().contiguous() if need_scores else None, dist,
+        dh, _, _, _ = ops.head_bwd(hL, graph, gL, v if need_scores else None, dist,
                                    scores if need_scores else None, kl_b, g_kl, g_scores,
                                    gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
                                    want_dh=True, want_dv=False, dgate_out=dgates[Lyr - 1])
@@ -230,7 +252,37 @@ class _GatedStackFn(torch.autograd.Function):
         if da is not None and not da.is_contiguous():
             da = da.contiguous()
         o = 2 * Lyr
-        for g in range(Lyr):
+        if ctx.use_chain:
+            # d z chain of every gate in ONE launch, then every weight gradient in one batched launch
+            da_parts = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
+            dz_in = [[None] * pairs for _ in range(Lyr)]      # gradient at the pre-activation output of Linear i
+            stages = []
+            for g in range(Lyr):
+                acts = ctx.gate_saved[g]
+                dz_in[g][pairs - 1] = dz_all[g * B:(g + 1) * B]
+                st = []
+                for i in range(pairs - 1, -1, -1):
+                    wt = ctx.w_t[Lyr + g * pairs + i]                           # [in,out]: row n = input column n
+                    if i > 0:
+                        out = ops.alloc_rows(B, D, cd, dev)
+                        dz_in[g][i - 1] = out
+                        st.append(dict(w=wt, y=acts[i], out=out))
+                    else:
+                        st.append(dict(w=wt, y=acts[0] if lead else None, out=da_parts[g]))
+                stages.append(st)
+            ops.mlp_chain(1, [dz_in[g][pairs - 1] for g in range(Lyr)], stages, B, D)
+            idx = [(g, i) for g in range(Lyr) for i in range(pairs)]
+            for c0 in range(0, len(idx), 8):
+                part = idx[c0:c0 + 8]
+                dWs, dbs = ops.wgrad_batch([dz_in[g][i] for g, i in part], [ctx.gate_saved[g][i] for g, i in part],
+                                           bias_of=1)
+                for (g, i), dW, db in zip(part, dWs, dbs):
+                    w, b = params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]
+                    grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
+                    grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
+            da_gate = da_parts.sum(0) if Lyr > 1 else da_parts[0]
+            da = da_gate if da is None else da + da_gate
+        for g in range(Lyr if not ctx.use_chain else 0):
             acts = ctx.gate_saved[g]
             dz = dz_all[g * B:(g + 1) * B]
             for i in range(pairs - 1, -1, -1):

@@ -85,6 +85,54 @@ def wgrad(a: torch.Tensor, b: torch.Tensor, bias_of: int = 0):
     return dW, db
 
 
+def wgrad_batch(a_list, b_list, bias_of: int = 0):
+    """``a_i.T @ b_i`` (+ column sums) for several same-shaped bf16 problems in one launch.
+    Returns ([dW_i], [db_i])."""
+    import ctypes
+    n = len(a_list)
+    R, K1 = a_list[0].shape
+    K2 = b_list[0].shape[1]
+    dev = a_list[0].device
+    lda, ldb = ld(a_list[0]), ld(b_list[0])
+    for a, b in zip(a_list, b_list):
+        assert a.shape == (R, K1) and b.shape == (R, K2) and ld(a) == lda and ld(b) == ldb and a.dtype == b.dtype
+    dW = torch.empty((n, K1, K2), dtype=torch.float32, device=dev)
+    nb = K1 if bias_of == 1 else K2
+    db = torch.empty((n, nb), dtype=torch.float32, device=dev) if bias_of else None
+    nbytes = L.load().edg_wgrad_batch_workspace(n, R, K1, K2)
+    ws = torch.empty((nbytes + 255) // 4, dtype=torch.float32, device=dev)
+    P = ctypes.c_void_p * n
+    L.call("edg_wgrad_batch", n, P(*[a.data_ptr() for a in a_list]), lda, K1, P(*[b.data_ptr() for b in b_list]), ldb, K2,
+           L.dt(a_list[0]), R, P(*[dW[i].data_ptr() for i in range(n)]), K2,
+           P(*[db[i].data_ptr() for i in range(n)]) if bias_of else None, bias_of, L.ptr(ws), ws.numel() * 4, L.stream())
+    return [dW[i] for i in range(n)], ([db[i] for i in range(n)] if bias_of else [None] * n)
+
+
+MLP_CHAIN_MAX_D = 320
+MLP_CHAIN_MAX_GROUPS = 4
+MLP_CHAIN_MAX_STAGES = 3
+
+
+def mlp_chain(mode: int, a0_list, stages, M: int, D: int) -> None:
+    """One launch for ``len(a0_list)`` chains of Linear layers (see ``edg_mlp_chain``).
+    ``stages[g][s]`` = dict(w=, bias=None, y=None, out=None) of tensors."""
+    import ctypes
+    n_groups, n_stages = len(a0_list), len(stages[0])
+    arr = (L.ChainStage * (n_groups * n_stages))()
+    for g in range(n_groups):
+        for s_i, st in enumerate(stages[g]):
+            e = arr[g * n_stages + s_i]
+            w, y, out, bias = st["w"], st.get("y"), st.get("out"), st.get("bias")
+            e.w, e.ldw = w.data_ptr(), ld(w)
+            e.bias = bias.data_ptr() if bias is not None else None
+            e.y, e.ldy = (y.data_ptr(), ld(y)) if y is not None else (None, 0)
+            e.out, e.ldo = (out.data_ptr(), ld(out)) if out is not None else (None, 0)
+            e.out_dtype = L.dt(out) if out is not None else 0
+    P = ctypes.c_void_p * n_groups
+    L.call("edg_mlp_chain", mode, n_groups, n_stages, P(*[a.data_ptr() for a in a0_list]), ld(a0_list[0]), arr, M, D,
+           L.stream())
+
+
 def cast_weight(w: torch.Tensor, dtype: torch.dtype, transpose: bool) -> torch.Tensor:
     """fp32 master weight ``[R,C]`` -> compute-dtype ``[R,C]`` or ``[C,R]`` row matrix."""
     w = w.detach()
@@ -199,6 +247,35 @@ def scores_kl_fwd(h, graph, gate, v, c, dist, want_units: bool = False):
     if want_units:
         return scores, kl_b, kl, dvu, dcu
     return scores, kl_b, kl
+
+
+def fc_head_fwd(logits: torch.Tensor, fc_w: torch.Tensor, fc_b: torch.Tensor, a: torch.Tensor):
+    """``[v | va] = logits @ fc_w``, ``c = a . va + logits . fc_b`` (fp32): v [B,D], c [B]."""
+    B, C = logits.shape
+    D = a.shape[1]
+    v = torch.empty((B, D), dtype=torch.float32, device=a.device)
+    c = torch.empty((B,), dtype=torch.float32, device=a.device)
+    L.call("edg_fc_head_fwd", L.ptr(logits), ld(logits), L.ptr(fc_w), ld(fc_w), L.ptr(fc_b), L.ptr(a), ld(a), B, D, C,
+           L.ptr(v), L.ptr(c), L.stream())
+    return v, c
+
+
+def fc_head_bwd(logits, fc_w, fc_b, a, dv, dc, scale: Optional[torch.Tensor] = None):
+    """Backward of :func:`fc_head_fwd` -> d_logits [B,C], d_a [B,D], d_fc_w [C,2D], d_fc_b [C]
+    (``dv``/``dc`` are multiplied by the device scalar ``scale`` when given)."""
+    B, C = logits.shape
+    D = a.shape[1]
+    dev = a.device
+    d_lg = torch.empty((B, C), dtype=torch.float32, device=dev)
+    d_a = torch.empty((B, D), dtype=torch.float32, device=dev)
+    d_w = torch.empty((C, 2 * D), dtype=torch.float32, device=dev)
+    d_b = torch.empty((C,), dtype=torch.float32, device=dev)
+    nbytes = L.load().edg_fc_head_bwd_workspace(B, D, C)
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+    L.call("edg_fc_head_bwd", L.ptr(logits), ld(logits), L.ptr(fc_w), ld(fc_w), L.ptr(fc_b), L.ptr(a), ld(a),
+           L.ptr(dv), L.ptr(dc), L.ptr(scale), B, D, C, L.ptr(d_lg), ld(d_lg), L.ptr(d_a), L.ptr(d_w), ld(d_w),
+           L.ptr(d_b), L.ptr(ws), ws.numel() * 4, L.stream())
+    return d_lg, d_a, d_w, d_b
 
 
 def head_bwd(h, graph, gate, v, dist, scores, kl_b, g_kl, g_scores, g_pooled, arg, g_xout, want_dh: bool,

@@ -133,6 +133,39 @@ int edg_wgrad(const void* A, int64_t lda, int32_t K1, const void* B, int64_t ldb
               int dtype, int32_t R, float* dW, int64_t lddw, float* dbias, int bias_of,
               int accumulate, void* ws, size_t ws_bytes, edg_stream stream);
 
+/* n (<= 8) same-shaped weight gradients dW[i][K1,K2] = A[i][R,K1]^T * B[i][R,K2] (+ dbias[i], bias_of as in
+ * edg_wgrad) in ONE launch + one reduction: the Linears of the gate MLPs.  bf16 operands only (EDG_ERR_DTYPE
+ * otherwise: use edg_wgrad per problem).  A, B, dW, dbias are HOST arrays of device pointers; all problems
+ * share lda / ldb / lddw.  Results are overwritten.  ws: edg_wgrad_batch_workspace() bytes. */
+size_t edg_wgrad_batch_workspace(int32_t n, int32_t R, int32_t K1, int32_t K2);
+int edg_wgrad_batch(int32_t n, const void* const* A, int64_t lda, int32_t K1, const void* const* B, int64_t ldb,
+                    int32_t K2, int dtype, int32_t R, float* const* dW, int64_t lddw, float* const* dbias,
+                    int bias_of, void* ws, size_t ws_bytes, edg_stream stream);
+
+/* The gate MLPs (bert_amir5.py:562-571, :621-622) as one launch per direction: n_groups (<= 4) independent
+ * chains (one per gate) of n_stages (<= 3) Linear(D,D) layers over the same M rows, D <= 320, bf16 tensor
+ * cores with fp32 accumulation; the activation tile never leaves shared memory between the Linears.
+ *   mode 0 (forward):  A_{s+1} = sigmoid(A_s W_s^T + bias_s)
+ *   mode 1 (backward): A_{s+1} = (A_s W_s^T) * y_s (1 - y_s)     (y_s = NULL: no factor)
+ * a0[g]: bf16 [M, lda] input of chain g.  stages: HOST array [n_groups * n_stages] (group-major):
+ *   w    bf16 [D, ldw], row n = the weights producing output column n, K contiguous (forward: nn.Linear
+ *        weight [out,in]; backward: its transpose [in,out]);
+ *   bias fp32 [D] or NULL (forward);  y bf16 [M, ldy] or NULL (backward);
+ *   out  global copy of the stage output, bf16 or fp32 [M, ldo], or NULL; bf16 copies get zero padding columns.
+ * Returns EDG_ERR_UNSUPPORTED for shapes outside these limits (callers then run edg_linear per layer). */
+typedef struct {
+  const void* w;
+  int64_t ldw;
+  const float* bias;
+  const void* y;
+  int64_t ldy;
+  void* out;
+  int64_t ldo;
+  int out_dtype;
+} edg_chain_stage;
+int edg_mlp_chain(int mode, int32_t n_groups, int32_t n_stages, const void* const* a0, int64_t lda,
+                  const edg_chain_stage* stages, int32_t M, int32_t D, edg_stream stream);
+
 /* fp32 [R,C] master weight -> compute-dtype copy, optionally transposed, padding
  * columns up to ldd zero-filled. */
 int edg_cast_2d(const float* src, int64_t lds, int32_t R, int32_t C, void* dst, int dst_dtype,
@@ -196,6 +229,26 @@ int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent
                       float* dv_unit, float* dc_unit, const int32_t* row_sent, int32_t N, int32_t max_len,
                       edg_stream stream);
 
+/* bert_amir5.py:645-646 collapsed: the per-sentence operands of the importance scores,
+ *   [v_b | va_b] = logits_b @ fc.weight   (fc.weight [C, 2D], nn.Linear layout; C <= 64),
+ *   c_b          = a_b . va_b + logits_b . fc.bias,
+ * so that scores[b,t] = x_out[b,t,:] . v_b + c_b  (edg_scores_kl_fwd).  All fp32.  v [B,D], c [B]. */
+int edg_fc_head_fwd(const float* logits, int64_t ldl, const float* fc_w, int64_t ldw, const float* fc_b,
+                    const float* a, int64_t lda, int32_t B, int32_t D, int32_t C, float* v, float* c,
+                    edg_stream stream);
+
+/* backward of edg_fc_head_fwd.  dv [B,D], dc [B] (both multiplied by the device scalar *scale when scale != NULL:
+ * the per-unit gradients of edg_scores_kl_fwd times the upstream d kl):
+ *   d_logits[b,:] = [dv_b | dc_b a_b] @ fc.weight^T + dc_b fc.bias        (overwritten, [B, lddl])
+ *   d_a[b,:]      = dc_b va_b                                             (overwritten, [B, D])
+ *   d_fc_w        = logits^T @ [dv | dc a],  d_fc_b = logits^T dc         (overwritten; fixed summation order)
+ * ws: edg_fc_head_bwd_workspace() bytes. */
+size_t edg_fc_head_bwd_workspace(int32_t B, int32_t D, int32_t C);
+int edg_fc_head_bwd(const float* logits, int64_t ldl, const float* fc_w, int64_t ldw, const float* fc_b,
+                    const float* a, int64_t lda, const float* dv, const float* dc, const float* scale,
+                    int32_t B, int32_t D, int32_t C, float* d_logits, int64_t lddl, float* d_a,
+                    float* d_fc_w, int64_t lddw, float* d_fc_b, void* ws, size_t ws_bytes, edg_stream stream);
+
 /* backward of x_out = gate*h_L through scores/kl, the final max-pool and an
  * optional direct gradient on x_out:
  *   ds[i]   = g_kl/B * P_i*(Q_i - kl_b) + g_scores[i]
@@ -232,6 +285,32 @@ int edg_sum_scaled(const float* in, int64_t n, float scale, float* out, edg_stre
 size_t edg_colsum_workspace(int32_t R, int32_t C);
 int edg_colsum(const void* x, int dtype, int64_t ldx, int32_t R, int32_t C, float* out,
                int accumulate, void* ws, size_t ws_bytes, edg_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* Neighbours of the path on the packed layout                  */
+/* ------------------------------------------------------------------------- */
+
+/* N1. Word-piece -> word averaging: `torch.bmm(transform, x)` of bert_amir5.py:600 (also bert_ed.py:50,
+ * bertdm.py:166) with the transform of data_utils.py:438-451 (entries 1/l over the l contiguous word pieces of a
+ * word) as a segment mean:  y[i] = sum_{j < seg_len[i]} fl32(1/seg_len[i]) * x[seg_start[i] + j].
+ * x [P, ldx] packed word-piece rows ([CLS]/[SEP]/padding pieces simply belong to no segment), y [N, ldy]
+ * packed word rows.  A word without pieces gives a zero row. */
+int edg_segment_mean(const void* x, int dtype, int64_t ldx, const int32_t* seg_start, const int32_t* seg_len,
+                     int32_t N, int32_t D, void* y, int y_dtype, int64_t ldy, edg_stream stream);
+/* its adjoint: dx[seg_start[i] + j] = fl32(1/seg_len[i]) * dy[i]; every other row of dx [P, lddx] is zeroed. */
+int edg_segment_mean_bwd(const void* dy, int dtype, int64_t lddy, const int32_t* seg_start, const int32_t* seg_len,
+                         int32_t N, int32_t D, void* dx, int64_t lddx, int32_t P, edg_stream stream);
+
+/* N4. BertDM's dynamic pooling (bertdm.py:116-140 masks, :174-185 pooling): pooled[b] = [max over tokens
+ * t <= anchor | max over tokens anchor < t < n] of `x*mask + 1`, minus 1, the maximum running over all T_pad
+ * padded positions as in the reference (masked positions contribute 0).  pooled fp32 [B, 2D], arg int32 [B, 2D]
+ * = global row of the maximum, -1 where a masked zero won (no gradient).  T_pad = the batch's padded length
+ * (max sentence length, bertdm.py:148). */
+int edg_lr_pool_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, const int32_t* anchor,
+                    int32_t B, int32_t D, int32_t T_pad, float* pooled, int32_t* arg, edg_stream stream);
+/* dh[arg[b,j], j mod D] += g[b,j] for arg >= 0  (dh is accumulated into). */
+int edg_lr_pool_bwd(const float* g, const int32_t* arg, int32_t B, int32_t D, void* dh, int dtype, int64_t lddh,
+                    edg_stream stream);
 
 #ifdef __cplusplus
 }

@@ -230,6 +230,46 @@ def golden_block55(BertAmir55) -> None:
     print("block55.npz", {k: v.shape for k, v in out.items() if k[:2] not in ("p_", "g_")})
 
 
+def golden_bertdm(BertDM) -> None:
+    """The WHOLE ``BertDM.forward`` (models/bertdm.py:142-199) with a stub BERT: transform bmm, get_mask, left/right
+    pooling, trigger-row gather.  The tensor entering ``self.dense`` (= cat[anchor_rep, pooledL-1, pooledR-1] in
+    eval mode) is captured with a pre-hook, and its gradient w.r.t. the BERT output for a probe direction."""
+    from oracle import ref_oracle as O
+    rng = np.random.default_rng(77)
+    g = torch.Generator().manual_seed(77)
+    B, D = 7, 768                                    # bertdm.py:190 hard-codes 768 * n_layer
+    lengths = np.array([9, 1, 12, 5, 12, 3, 7])
+    anchor = np.array([0, 0, 11, 2, 5, 2, 6])        # first / last / interior triggers
+    pieces = [rng.integers(1, 4, size=n).tolist() for n in lengths]
+    transform = torch.FloatTensor([O.wordpiece_transform_ref(p) for p in pieces])        # collate_fn, data_utils.py:371
+    bert_len = torch.LongTensor([sum(p) + 2 for p in pieces])                             # [CLS] + pieces + [SEP]
+    Lmax = int(bert_len.max())
+    bert_x = torch.randn(B, Lmax, D, generator=g)
+    bert_x[3, 2:4] = -1.5 - bert_x[3, 2:4].abs()     # a left span that is negative everywhere: the masked zero wins
+    bert_x.requires_grad_(True)
+
+    class StubBert(torch.nn.Module):
+        def forward(self, ids, seg, output_all_encoded_layers=True):
+            return [bert_x], torch.zeros(B, D)
+
+    opt = types.SimpleNamespace(device="cpu", n_layer=1, dropout=0.25, bert_dim=768, polarities_dim=5)
+    model = BertDM(StubBert(), opt).eval()
+    cap = {}
+    model.dense.register_forward_pre_hook(lambda mod, inp: cap.__setitem__("dense_in", inp[0]))
+    inputs = {"cls_text_sep_length": bert_len, "sentence_length": torch.LongTensor(lengths),
+              "cls_text_sep_indices": torch.zeros(B, 120, dtype=torch.long),
+              "cls_text_sep_segments_ids": torch.zeros(B, 120, dtype=torch.long),
+              "anchor_index": torch.LongTensor(anchor), "transform": transform}
+    model(inputs)
+    probe = torch.randn(B, 3 * D, generator=g)
+    (dx,) = torch.autograd.grad(cap["dense_in"], bert_x, probe)
+    out = dict(transform=transform.numpy()[:, :int(lengths.max()), :Lmax], bert_x=bert_x.detach().numpy(),
+               lengths=lengths, anchor=anchor, bert_len=bert_len.numpy(), dense_in=cap["dense_in"].detach().numpy(),
+               probe=probe.numpy(), d_bert_x=dx.numpy())
+    np.savez_compressed(os.path.join(GOLD, "bertdm.npz"), **out)
+    print("bertdm.npz", {k: v.shape for k, v in out.items()})
+
+
 def main() -> None:
     os.makedirs(GOLD, exist_ok=True)
     _install_stubs()
@@ -239,6 +279,8 @@ def main() -> None:
     golden_gcn_layer(GraphConvolution)
     golden_tree_dist(data_utils.get_dist_to_target)
     golden_block55(BertAmir55)
+    from models.bertdm import BertDM                   # reference, unmodified
+    golden_bertdm(BertDM)
 
 
 if __name__ == "__main__":

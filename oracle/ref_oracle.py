@@ -296,3 +296,52 @@ def aggregation_only_ref(x: torch.Tensor, adj: torch.Tensor) -> torch.Tensor:
     """The aggregation half of gcn.py:35,41 alone (config 5): adj @ x / (rowsum+1)."""
     a = adj.to(x.dtype)
     return (a @ x) / (a.sum(dim=2, keepdim=True) + 1)
+
+
+# ---------------------------------------------------------------------------
+# N1 -- word-piece -> word averaging (data_utils.py:438-451, bert_amir5.py:600)
+# ---------------------------------------------------------------------------
+def wordpiece_transform_ref(piece_counts: Sequence[int], ori_ml: int = 100, bert_ml: int = 120) -> List[List[float]]:
+    """data_utils.py:438-451: ``transform[i][offset + j] = 1 / l`` for the ``l`` word pieces of word ``i``;
+    ``offset`` starts at 1 (the [CLS] piece) and advances by ``l``.  Python floats (doubles) -- they become
+    fp32 when ``collate_fn`` wraps them in ``torch.FloatTensor`` (data_utils.py:371)."""
+    transform = [[0.0] * bert_ml for _ in range(ori_ml)]
+    offset = 1
+    for i, l in enumerate(piece_counts):
+        for j in range(l):
+            transform[i][offset + j] = 1 / l
+        offset += l
+    return transform
+
+
+def wordpiece_bmm_ref(transform: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """bert_amir5.py:600 / bertdm.py:166: ``torch.bmm(transform, x)`` with transform [B,T,L], x [B,L,D]."""
+    return torch.bmm(transform, x)
+
+
+# ---------------------------------------------------------------------------
+# N4 -- BertDM dynamic pooling (models/bertdm.py:116-140, :168-185)
+# ---------------------------------------------------------------------------
+def bertdm_masks_ref(T: int, anchor_index: torch.Tensor, length: torch.Tensor):
+    """bertdm.py:116-140 (get_mask): maskL = [t < anchor+1], maskR = [t > anchor] * [t < length], each [1,B,T]."""
+    m = torch.arange(T).repeat(anchor_index.shape[0], 1)
+    a = anchor_index.unsqueeze(dim=1)
+    maskL = (m < (a + 1)).float().unsqueeze(dim=0)
+    maskR = (m > a).float().unsqueeze(dim=0)
+    maskS = (m < length.unsqueeze(dim=1)).float().unsqueeze(dim=0)
+    return maskL, maskR * maskS
+
+
+def bertdm_pool_ref(transform_x: torch.Tensor, anchor_index: torch.Tensor, sentence_length: torch.Tensor) -> torch.Tensor:
+    """bertdm.py:168-185: x [B,T,D] -> cat(max_t(x*maskL + 1), max_t(x*maskR + 1)) - 1, [B,2D]."""
+    T = transform_x.shape[1]
+    transpose_x = transform_x.transpose(1, 2).transpose(0, 1)          # [D,B,T]
+    maskL, maskR = bertdm_masks_ref(T, anchor_index, sentence_length)
+    L = (transpose_x * maskL).transpose(0, 1)                           # [B,D,T]
+    R = (transpose_x * maskR).transpose(0, 1)
+    L = L + torch.ones_like(L)
+    R = R + torch.ones_like(R)
+    pooledL, _ = L.max(dim=2)
+    pooledR, _ = R.max(dim=2)
+    x = torch.cat((pooledL, pooledR), 1)
+    return x - torch.ones_like(x)

@@ -156,3 +156,113 @@ def test_scores_kl(dtype, i64):
         want = (torch.softmax(s, 0) * q).sum()
         assert abs(kl_b[b].item() - want.item()) < 2e-6
     assert abs(kl.item() - kl_b.double().mean().item()) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(4096, 300, 34), (37, 256, 2), (1, 16, 1), (130, 768, 34), (64, 300, 64)])
+def test_fc_head_forward_backward(shape):
+    """[v | va] = logits @ fc.weight, c = a.va + logits.fc.bias (bert_amir5.py:645-646 collapsed) and its
+    backward, against the torch formulation in fp64."""
+    from ed_gated_gcn_b200 import ops
+    B, D, C = shape
+    g = torch.Generator().manual_seed(B + D + C)
+    lg, W, bfc = torch.randn(B, C, generator=g), torch.randn(C, 2 * D, generator=g) / C ** 0.5, torch.randn(C, generator=g)
+    a, dv, dc = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g), torch.randn(B, generator=g)
+    v, c = ops.fc_head_fwd(lg.to(DEV), W.to(DEV), bfc.to(DEV), a.to(DEV))
+    lgd, Wd, bd, ad = (t.double().requires_grad_(True) for t in (lg, W, bfc, a))
+    vva = lgd @ Wd
+    v_ref = vva[:, :D]
+    c_ref = (ad * vva[:, D:]).sum(1) + lgd @ bd
+    assert rel(v, v_ref) < 1e-6 and rel(c, c_ref) < 1e-6
+    for scale in (None, 0.37):
+        s = 1.0 if scale is None else scale
+        want = torch.autograd.grad([v_ref, c_ref], [lgd, ad, Wd, bd], [s * dv.double(), s * dc.double()], retain_graph=True)
+        sc = None if scale is None else torch.tensor(scale, device=DEV)
+        got = ops.fc_head_bwd(lg.to(DEV), W.to(DEV), bfc.to(DEV), a.to(DEV), dv.to(DEV), dc.to(DEV), sc)
+        for name, x, y in zip(["d_logits", "d_a", "d_fc_w", "d_fc_b"], got, want):
+            assert rel(x, y) < 2e-6, (name, shape, scale)
+
+
+@pytest.mark.parametrize("D", [300, 256, 200, 64, 320])
+@pytest.mark.parametrize("B", [4096, 77])
+@pytest.mark.parametrize("pairs", [2, 3])
+def test_mlp_chain_forward_backward(D, B, pairs):
+    """The fused gate-MLP launch against torch on the same bf16-rounded operands (fp32 accumulation)."""
+    from ed_gated_gcn_b200 import ops
+    bf = torch.bfloat16
+    G = 2
+    g = torch.Generator().manual_seed(D + B + pairs)
+    s0 = ops.as_rows(torch.rand(B, D, generator=g).to(DEV), bf)
+    Ws = [[ops.as_rows((torch.randn(D, D, generator=g) * 2 / D ** 0.5).to(DEV), bf) for _ in range(pairs)] for _ in range(G)]
+    bs = [[torch.randn(D, generator=g).to(DEV) for _ in range(pairs)] for _ in range(G)]
+    gates = torch.empty(G, B, D, device=DEV)
+    acts = [[s0] for _ in range(G)]
+    stages = []
+    for k in range(G):
+        st = []
+        for i in range(pairs):
+            last = i == pairs - 1
+            out = gates[k] if last else ops.alloc_rows(B, D, bf, DEV)
+            st.append(dict(w=Ws[k][i], bias=bs[k][i], out=out))
+            if not last:
+                acts[k].append(out)
+        stages.append(st)
+    ops.mlp_chain(0, [s0] * G, stages, B, D)
+    for k in range(G):
+        s = s0.float()
+        for i in range(pairs):
+            s = torch.sigmoid(s @ Ws[k][i].float().t() + bs[k][i])
+            if i < pairs - 1:
+                got = acts[k][i + 1]
+                assert rel(got.float(), s) < 6e-3, ("act", D, B, k, i)
+                base = got.as_strided((B, got.stride(0)), (got.stride(0), 1))
+                assert (base[:, D:] == 0).all()                      # padding columns stay zero
+                s = got.float()                                       # the kernel feeds the rounded tile forward
+        assert rel(gates[k], s) < 2e-5, ("gate", D, B, k)
+    # backward chain: dz_last -> ... -> d a, with sigmoid' of the saved activations
+    dz = [ops.as_rows(torch.randn(B, D, generator=g).to(DEV), bf) for _ in range(G)]
+    Wt = [[ops.as_rows(Ws[k][i].float().t().contiguous(), bf) for i in range(pairs)] for k in range(G)]
+    da = torch.empty(G, B, D, device=DEV)
+    mids = [[None] * pairs for _ in range(G)]
+    stages = []
+    for k in range(G):
+        st = []
+        for i in range(pairs - 1, -1, -1):
+            if i > 0:
+                out = ops.alloc_rows(B, D, bf, DEV)
+                mids[k][i - 1] = out
+                st.append(dict(w=Wt[k][i], y=acts[k][i], out=out))
+            else:
+                st.append(dict(w=Wt[k][0], y=acts[k][0] if k == 0 else None, out=da[k]))
+        stages.append(st)
+    ops.mlp_chain(1, dz, stages, B, D)
+    for k in range(G):
+        d = dz[k].float()
+        for i in range(pairs - 1, -1, -1):
+            ds = d @ Wt[k][i].float().t()
+            if i > 0:
+                y = acts[k][i].float()
+                want = ds * y * (1 - y)
+                assert rel(mids[k][i - 1].float(), want) < 6e-3, ("dz", D, B, k, i)
+                d = mids[k][i - 1].float()
+            else:
+                y = acts[k][0].float()
+                want = ds * y * (1 - y) if k == 0 else ds
+                assert rel(da[k], want) < 2e-5, ("da", D, B, k)
+
+
+@pytest.mark.parametrize("shape", [(4096, 300, 300, 4), (130, 256, 256, 2), (1000, 64, 200, 8), (4096, 300, 300, 1)])
+def test_wgrad_batch(shape):
+    from ed_gated_gcn_b200 import ops
+    R, K1, K2, n = shape
+    g = torch.Generator().manual_seed(R + n)
+    a = [ops.as_rows(torch.randn(R, K1, generator=g).to(DEV), torch.bfloat16) for _ in range(n)]
+    b = [ops.as_rows(torch.randn(R, K2, generator=g).to(DEV), torch.bfloat16) for _ in range(n)]
+    for bias_of in (0, 1, 2):
+        dWs, dbs = ops.wgrad_batch(a, b, bias_of=bias_of)
+        for i in range(n):
+            ad, bd = a[i].float().double(), b[i].float().double()
+            assert rel(dWs[i], ad.t() @ bd) < 2e-6
+            if bias_of == 1:
+                assert rel(dbs[i], ad.sum(0)) < 2e-6
+            if bias_of == 2:
+                assert rel(dbs[i], bd.sum(0)) < 2e-6

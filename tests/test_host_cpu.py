@@ -163,3 +163,64 @@ def test_two_rank_gloo_gradient_average_equals_single_process(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env))
     codes = [p.wait(timeout=240) for p in procs]
     assert codes == [0, 0]
+
+
+def _reference_items(batch, pieces, ori_ml=60, bert_ml=90):
+    """Per-sentence item dicts shaped like the reference datasets build them (data_utils.py:362-379, 438-490)."""
+    from oracle import ref_oracle as O
+    items = []
+    for b, h in enumerate(batch.heads_list()):
+        n = len(h)
+        adj = O.dense_adjacency_from_heads(h, ori_ml)
+        dist = O.pad_distance(O.tree_distance_bfs(h, int(batch.anchor[b])), ori_ml, "max+1")
+        items.append({"dependency_graph": adj.tolist(), "anchor_index": int(batch.anchor[b]), "sentence_length": n,
+                      "dist_to_target": dist, "transform": O.wordpiece_transform_ref(pieces[b], ori_ml, bert_ml),
+                      "cls_text_sep_length": sum(pieces[b]) + 2, "polarity": b % 3})
+    return items
+
+
+def test_packed_wire_format_from_reference_items():
+    """collate_packed over reference-format items: the heads it extracts give the same CSR as
+    the dense matrix, distances / segments survive, and the payload is ~16 B/token instead of ~90 KB/sentence."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import synth
+    from oracle import ref_oracle as O
+    batch = synth.make_batch(12, 1, 40, seed=21)
+    rng = np.random.default_rng(5)
+    pieces = [rng.integers(1, 4, size=int(n)).tolist() for n in batch.lengths]
+    items = _reference_items(batch, pieces)
+    pb = E.collate_packed(items)
+    assert pb.n_graphs == 12 and pb.n_rows == batch.n_rows and pb.max_len == int(batch.lengths.max())
+    assert np.array_equal(pb.sent_ptr.numpy(), batch.sent_ptr) and np.array_equal(pb.anchor.numpy(), batch.anchor)
+    for b, h in enumerate(batch.heads_list()):
+        lo, hi = batch.sent_ptr[b], batch.sent_ptr[b + 1]
+        got = pb.heads[lo:hi].numpy()
+        n = len(h)
+        # any orientation of the same undirected tree yields the same symmetric pattern
+        assert np.array_equal(O.dense_adjacency_from_heads(got, n), O.dense_adjacency_from_heads(h, n))
+        assert pb.dist[lo:hi].tolist() == O.tree_distance_bfs(h, int(batch.anchor[b]))
+        # segments: word i = pieces [1 + sum(pieces[:i]), +pieces[i]) of the sentence's own [CLS] .. [SEP] rows
+        start = pb.seg_start[lo:hi].numpy() - int(pb.piece_ptr[b])
+        assert start.tolist() == (1 + np.concatenate([[0], np.cumsum(pieces[b])[:-1]])).tolist()
+        assert pb.seg_len[lo:hi].tolist() == pieces[b]
+    assert int(pb.piece_ptr[-1]) == sum(sum(p) + 2 for p in pieces)
+    dense_bytes = 12 * (60 * 60 * 4 + 60 * 90 * 4 + 60 * 8)
+    assert pb.nbytes() < dense_bytes / 50
+    with pytest.raises(ValueError):
+        cyc = np.eye(4, dtype=np.int64)
+        for i, j in ((0, 1), (1, 2), (2, 0)):
+            cyc[i, j] = cyc[j, i] = 1
+        E.heads_from_adjacency(cyc, 4)
+
+
+def test_segments_from_dense_transform_host_logic():
+    from ed_gated_gcn_b200 import segment
+    from ed_gated_gcn_b200._lib import EdgError
+    from oracle import ref_oracle as O
+    t = torch.tensor([O.wordpiece_transform_ref([2, 1, 3], 5, 9), O.wordpiece_transform_ref([1], 5, 9)])
+    s, n = segment.segments_from_transform(t)
+    assert n.view(2, 5).tolist() == [[2, 1, 3, 0, 0], [1, 0, 0, 0, 0]]
+    assert s.view(2, 5)[0, :3].tolist() == [1, 3, 4] and int(s.view(2, 5)[1, 0]) == 9 + 1
+    bad = t.clone(); bad[0, 0, 5] = 0.5                       # not a contiguous run of 1/len
+    with pytest.raises(EdgError):
+        segment.segments_from_transform(bad)

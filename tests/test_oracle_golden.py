@@ -110,3 +110,22 @@ def test_block_matches_full_reference_forward_backward():
             assert p.grad.abs().max() < 1e-9 and np.abs(z["g_" + name]).max() < 1e-9
             continue
         assert rel_err(p.grad, z["g_" + name]) < 1e-5, name
+
+
+def test_bertdm_block_matches_reference_fixture(golden_dir):
+    """N1 + N4: the restated word-piece bmm and BertDM left/right pooling reproduce the tensor the
+    reference's own BertDM.forward feeds to its classifier, and its gradient, bit for bit."""
+    z = np.load(os.path.join(golden_dir, "bertdm.npz"))
+    transform, bert_x = torch.from_numpy(z["transform"]), torch.from_numpy(z["bert_x"]).requires_grad_(True)
+    anchor, lengths = torch.from_numpy(z["anchor"]), torch.from_numpy(z["lengths"])
+    x = O.wordpiece_bmm_ref(transform, bert_x)
+    pooled = O.bertdm_pool_ref(x, anchor, lengths)
+    anchor_rep = x[torch.arange(x.shape[0]), anchor]                    # bertdm.py:186-193 (masked_select)
+    dense_in = torch.cat((anchor_rep, pooled), 1)
+    assert torch.equal(dense_in, torch.from_numpy(z["dense_in"]))
+    (dx,) = torch.autograd.grad(dense_in, bert_x, torch.from_numpy(z["probe"]))
+    assert rel_err(dx, z["d_bert_x"]) < 1e-6
+    # the transform the fixture was built with is the one data_utils.py:438-451 produces
+    for b in range(transform.shape[0]):
+        nz = (transform[b] != 0)
+        assert nz.sum(1)[: int(lengths[b])].min() >= 1 and nz[int(lengths[b]):].sum() == 0
