@@ -29,10 +29,23 @@ template <> __device__ __forceinline__ void store_chunk<__nv_bfloat16, 4>(__nv_b
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
 }
 
+// Optional epilogue of the adjoint pass: y[patch_arg[b,d], d] += patch_val[b,d] -- the gradient that the gated
+// max-pool views of layer 1 (bert_amir5.py:627-636) route to their arg-max rows, folded into the kernel that
+// produces d h_1 instead of a separate scattered read-modify-write pass (edg_views_patch builds the two arrays).
+struct AggPatch { const int32_t* arg; const float* val; const int32_t* row_sent; int D; };
+
+template <int E>
+__device__ __forceinline__ void apply_patch(const AggPatch& p, int row, int c, float (&acc)[E]) {
+  const int64_t o = (int64_t)__ldg(p.row_sent + row) * p.D + c;
+#pragma unroll
+  for (int k = 0; k < E; ++k)
+    if (c + k < p.D && __ldg(p.arg + o + k) == row) acc[k] += __ldg(p.val + o + k);
+}
+
 template <typename TI, typename TO, int MODE>
 __global__ void __launch_bounds__(256)
 aggregate_flat_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int N, int chunks,
-                 const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col) {
+                 const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, AggPatch patch) {
   constexpr int E = Vec16<TI>::kElems;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int row = (int)(idx / chunks);
@@ -75,6 +88,7 @@ aggregate_flat_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y,
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = acc[k] / den;
   }
+  if (patch.arg) apply_patch<E>(patch, row, c, acc);
   store_chunk<TO, E>(y + (int64_t)row * ldy + c, acc);
 }
 
@@ -91,7 +105,7 @@ __device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32
 template <typename TI, typename TO, int MODE>
 __device__ __noinline__ void aggregate_rows_global(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy,
                                                    int r0, int r1, const int32_t* __restrict__ row_ptr,
-                                                   const int32_t* __restrict__ col) {
+                                                   const int32_t* __restrict__ col, const AggPatch& patch) {
   constexpr int E = Vec16<TI>::kElems;
   const int c = threadIdx.x * E;
   for (int row = r0 + threadIdx.y; row < r1; row += blockDim.y) {
@@ -112,6 +126,7 @@ __device__ __noinline__ void aggregate_rows_global(const TI* __restrict__ x, int
 #pragma unroll
       for (int k = 0; k < E; ++k) acc[k] *= inv;
     }
+    if (patch.arg) apply_patch<E>(patch, row, c, acc);
     store_chunk<TO, E>(y + (int64_t)row * ldy + c, acc);
   }
 }
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(256)
 aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int N, int B,
                         int tile_rows, int cap_rows, const int32_t* __restrict__ sent_ptr,
                         const int32_t* __restrict__ row_sent, const int32_t* __restrict__ row_ptr,
-                        const int32_t* __restrict__ col) {
+                        const int32_t* __restrict__ col, AggPatch patch) {
   constexpr int E = Vec16<TI>::kElems;
   extern __shared__ __align__(128) uint8_t agg_smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -156,7 +171,7 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
   const int r0 = range[0], r1 = range[1], n = r1 - r0;
   if (n <= 0) return;
   if (n > cap_rows) {                               // nothing was staged
-    aggregate_rows_global<TI, TO, MODE>(x, ldx, y, ldy, r0, r1, row_ptr, col);
+    aggregate_rows_global<TI, TO, MODE>(x, ldx, y, ldy, r0, r1, row_ptr, col, patch);
     return;
   }
   // the tile's slice of the CSR (as tile-local ids) and 1/(deg+1) go to shared memory while the bulk copy flies
@@ -176,7 +191,7 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
     }
   }
   if (!fits) {                                      // dense-ish graph: keep the staged copy unused, gather from global
-    aggregate_rows_global<TI, TO, MODE>(x, ldx, y, ldy, r0, r1, row_ptr, col);
+    aggregate_rows_global<TI, TO, MODE>(x, ldx, y, ldy, r0, r1, row_ptr, col, patch);
     return;
   }
   // ---- hot loop: shared memory only -------------------------------------------------------------------
@@ -216,6 +231,7 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
 #pragma unroll
       for (int k = 0; k < E; ++k) acc[k] *= inv;
     }
+    if (patch.arg) apply_patch<E>(patch, r0 + lr, (int)threadIdx.x * E, acc);
     store_chunk<TO, E>(yrow, acc);
   }
 }
@@ -230,7 +246,7 @@ static int agg_variant() {
 template <typename TI, typename TO>
 static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, int N, int D,
                             const int32_t* row_ptr, const int32_t* col, int mode, const int32_t* sent_ptr,
-                            const int32_t* row_sent, int B, int max_len, cudaStream_t s) {
+                            const int32_t* row_sent, int B, int max_len, const AggPatch& patch, cudaStream_t s) {
   constexpr int E = Vec16<TI>::kElems;
   const int chunks = (D + E - 1) / E;
   if (ldx < (int64_t)chunks * E || ldy < (int64_t)chunks * E) return EDG_ERR_ALIGN;
@@ -248,8 +264,8 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
   if (!staged) {
     const int64_t total = (int64_t)N * chunks;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (mode == 0) aggregate_flat_kernel<TI, TO, 0><<<blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col);
-    else aggregate_flat_kernel<TI, TO, 1><<<blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col);
+    if (mode == 0) aggregate_flat_kernel<TI, TO, 0><<<blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col, patch);
+    else aggregate_flat_kernel<TI, TO, 1><<<blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col, patch);
     return check_launch();
   }
   int rpb = 256 / chunks;
@@ -262,10 +278,10 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
   static size_t attr0 = 0, attr1 = 0;         // largest dynamic smem opted into so far (per instantiation)
   if (mode == 0) {
     if (smem > attr0) { if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch(); attr0 = smem; }
-    k0<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col);
+    k0<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col, patch);
   } else {
     if (smem > attr1) { if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch(); attr1 = smem; }
-    k1<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col);
+    k1<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col, patch);
   }
   return check_launch();
 }
@@ -274,18 +290,37 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
 
 using namespace edg;
 
+static int aggregate_entry(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
+                           int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
+                           const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
+                           const int32_t* patch_arg, const float* patch_val, edg_stream stream) {
+  if (N < 0 || D <= 0 || (mode != 0 && mode != 1)) return EDG_ERR_ARG;
+  if (N == 0) return EDG_OK;
+  if (!x || !y || !row_ptr || !col) return EDG_ERR_ARG;
+  if ((patch_arg != nullptr) != (patch_val != nullptr)) return EDG_ERR_ARG;
+  if (patch_arg && !row_sent) return EDG_ERR_ARG;
+  if (!aligned16(x) || !aligned16(y) || !row_pitch_ok(x_dtype, ldx) || !row_pitch_ok(y_dtype, ldy)) return EDG_ERR_ALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  AggPatch patch{patch_arg, patch_val, row_sent, D};
+  if (x_dtype == EDG_BF16 && y_dtype == EDG_BF16) return launch_aggregate<__nv_bfloat16, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch, s);
+  if (x_dtype == EDG_F32 && y_dtype == EDG_F32) return launch_aggregate<float, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch, s);
+  if (x_dtype == EDG_F32 && y_dtype == EDG_BF16) return launch_aggregate<float, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch, s);
+  if (x_dtype == EDG_BF16 && y_dtype == EDG_F32) return launch_aggregate<__nv_bfloat16, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch, s);
+  return EDG_ERR_DTYPE;
+}
+
 extern "C" int edg_aggregate(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
                              int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
                              const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
                              edg_stream stream) {
-  if (N < 0 || D <= 0 || (mode != 0 && mode != 1)) return EDG_ERR_ARG;
-  if (N == 0) return EDG_OK;
-  if (!x || !y || !row_ptr || !col) return EDG_ERR_ARG;
-  if (!aligned16(x) || !aligned16(y) || !row_pitch_ok(x_dtype, ldx) || !row_pitch_ok(y_dtype, ldy)) return EDG_ERR_ALIGN;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == EDG_BF16 && y_dtype == EDG_BF16) return launch_aggregate<__nv_bfloat16, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, s);
-  if (x_dtype == EDG_F32 && y_dtype == EDG_F32) return launch_aggregate<float, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, s);
-  if (x_dtype == EDG_F32 && y_dtype == EDG_BF16) return launch_aggregate<float, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, s);
-  if (x_dtype == EDG_BF16 && y_dtype == EDG_F32) return launch_aggregate<__nv_bfloat16, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, s);
-  return EDG_ERR_DTYPE;
+  return aggregate_entry(x, x_dtype, ldx, y, y_dtype, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, nullptr,
+                         nullptr, stream);
+}
+
+extern "C" int edg_aggregate_patched(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
+                                     int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
+                                     const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
+                                     const int32_t* patch_arg, const float* patch_val, edg_stream stream) {
+  return aggregate_entry(x, x_dtype, ldx, y, y_dtype, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch_arg,
+                         patch_val, stream);
 }

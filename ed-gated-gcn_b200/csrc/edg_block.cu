@@ -147,6 +147,44 @@ views_bwd_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ a
   }
 }
 
+// The same gradients WITHOUT touching dh: what the views send to their arg-max rows is written as one
+// (row, value) pair per (sentence, column) for the aggregation kernel that produces dh to add on the fly
+// (edg_aggregate_patched).  The views share their arg-max row (the gated maximum is the gate times the plain
+// column maximum for positive gates); a view whose gate is exactly 0 points elsewhere but contributes 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+views_patch_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ arg, const float* __restrict__ gates,
+                   const T* __restrict__ h, int64_t ldh, int V, int B, int D, const float* __restrict__ g_xy,
+                   const float* __restrict__ g_pooled, int32_t* __restrict__ patch_arg, float* __restrict__ patch_val,
+                   float* __restrict__ dgates, int acc_view) {
+  const int64_t BD = (int64_t)B * D;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BD) return;
+  const int d = (int)(i % D);
+  const float gxy = g_xy ? (__ldg(g_xy) / (float)B) : 0.f;
+  float tot = 0.f;
+  for (int v = 0; v < V; ++v) tot += pooled[v * BD + i];
+  int prow = -1;
+  float pval = 0.f;
+  for (int v = 0; v < V; ++v) {
+    float dp = gxy * (tot - pooled[v * BD + i]);
+    if (g_pooled) dp += g_pooled[v * BD + i];
+    const int r = arg[v * BD + i];
+    float dgv = 0.f;
+    if (r >= 0) {
+      dgv = dp * to_f32(h[(int64_t)r * ldh + d]);
+      const float contrib = dp * gates[v * BD + i];
+      if (contrib != 0.f) {
+        if (prow < 0) prow = r;
+        if (r == prow) pval += contrib;
+      }
+    }
+    dgates[v * BD + i] = (v == acc_view) ? dgates[v * BD + i] + dgv : dgv;
+  }
+  patch_arg[i] = prow;
+  patch_val[i] = pval;
+}
+
 // ---- importance scores + softmax product ("kl") ---------------------------------
 template <int I64> __device__ __forceinline__ float dist_at(const void* dist, int64_t i) {
   return I64 ? (float)reinterpret_cast<const long long*>(dist)[i] : (float)reinterpret_cast<const int32_t*>(dist)[i];
@@ -554,6 +592,18 @@ extern "C" int edg_views_bwd(const float* pooled, const int32_t* arg, const floa
   cudaStream_t s = (cudaStream_t)stream;
   EDG_DISPATCH_T(dtype, views_bwd_kernel<T><<<blocks_for((int64_t)B * D, 256), 256, 0, s>>>(
       pooled, arg, gates, (const T*)h, ldh, V, B, D, g_xy, g_pooled, (T*)dh, lddh, dgates, acc_view);)
+  return check_launch();
+}
+
+extern "C" int edg_views_patch(const float* pooled, const int32_t* arg, const float* gates, const void* h, int dtype,
+                               int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy, const float* g_pooled,
+                               int32_t* patch_arg, float* patch_val, float* dgates, int acc_view, edg_stream stream) {
+  if (V <= 0 || B < 0 || D <= 0) return EDG_ERR_ARG;
+  if (B == 0) return EDG_OK;
+  if (!pooled || !arg || !gates || !h || !patch_arg || !patch_val || !dgates) return EDG_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  EDG_DISPATCH_T(dtype, views_patch_kernel<T><<<blocks_for((int64_t)B * D, 256), 256, 0, s>>>(
+      pooled, arg, gates, (const T*)h, ldh, V, B, D, g_xy, g_pooled, patch_arg, patch_val, dgates, acc_view);)
   return check_launch();
 }
 

@@ -233,9 +233,6 @@ class _GatedStackFn(torch.autograd.Function):
         # ---- GCN chain backward (gcn.py:33-45)
         grads_out: List[Optional[torch.Tensor]] = [None] * ctx.n_params
         for l in range(Lyr - 1, -1, -1):
-            if l == 0 and views_active:
-                # gated views of h_1 feed xy (:627-638): add their gradient before leaving layer 1
-                ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
             w, b = params[2 * l], params[2 * l + 1]
             if cfg["relu"]:
                 dh = ops.as_rows(dh * (hs[l] > 0), cd)
@@ -243,7 +240,12 @@ class _GatedStackFn(torch.autograd.Function):
             grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db.to(b.dtype)
             wk = ctx.w_n[l]                                                     # [in,out] = B operand of dh W^T
             dm = ops.linear(dh, wk, None)
-            dh = ops.aggregate(dm, graph, mode=1)
+            patch = None
+            if l == 1 and views_active:
+                # gated views of h_1 feed xy (:627-638): what they send to their arg-max rows is added while the
+                # adjoint aggregation writes d h_1 (no separate scattered pass)
+                patch = ops.views_patch(v_pooled, v_arg, gates, hs[0], g_xy, None, dgates, acc_view=Lyr - 1)
+            dh = ops.aggregate(dm, graph, mode=1, patch=patch)
         dx = dh
         # ---- gate MLP backward (bert_amir5.py:562-571)
         # the last Sigmoid of every gate in one launch (gates / dgates are [V*B, D] row blocks)

@@ -48,10 +48,17 @@ def ld(t: torch.Tensor) -> int:
 
 
 # ---------------------------------------------------------------------------
-def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype] = None, patch=None) -> torch.Tensor:
+    """``patch`` = (patch_arg int32 [B,D], patch_val fp32 [B,D]) from :func:`views_patch`: added to the rows it
+    names while the output is produced."""
     N, D = x.shape
     # the kernel walks 16-byte chunks of the INPUT dtype, so the output pitch must cover the same columns
     out = alloc_rows(N, D, out_dtype or x.dtype, x.device, min_ld=row_pitch(D, x.dtype))
+    if patch is not None:
+        L.call("edg_aggregate_patched", L.ptr(x), L.dt(x), ld(x), L.ptr(out), L.dt(out), ld(out), N, D,
+               L.ptr(graph.row_ptr), L.ptr(graph.col), mode, L.ptr(graph.sent_ptr), L.ptr(graph.row_sent),
+               graph.n_graphs, graph.max_len, L.ptr(patch[0]), L.ptr(patch[1]), L.stream())
+        return out
     L.call("edg_aggregate", L.ptr(x), L.dt(x), ld(x), L.ptr(out), L.dt(out), ld(out), N, D,
            L.ptr(graph.row_ptr), L.ptr(graph.col), mode, L.ptr(graph.sent_ptr), L.ptr(graph.row_sent),
            graph.n_graphs, graph.max_len, L.stream())
@@ -222,6 +229,17 @@ def views_bwd(pooled, arg, gates, h, g_xy, g_pooled, dh, dgates, acc_view: int =
     V, B, D = pooled.shape
     L.call("edg_views_bwd", L.ptr(pooled), L.ptr(arg), L.ptr(gates), L.ptr(h), L.dt(h), ld(h), V, B, D, L.ptr(g_xy),
            L.ptr(g_pooled), L.ptr(dh), ld(dh), L.ptr(dgates), int(acc_view), L.stream())
+
+
+def views_patch(pooled, arg, gates, h, g_xy, g_pooled, dgates, acc_view: int = -1):
+    """Backward of the gated views + diversity term without touching dh: writes dgates and returns
+    (patch_arg, patch_val) for :func:`aggregate` (``patch=``)."""
+    V, B, D = pooled.shape
+    patch_arg = torch.empty((B, D), dtype=torch.int32, device=pooled.device)
+    patch_val = torch.empty((B, D), dtype=torch.float32, device=pooled.device)
+    L.call("edg_views_patch", L.ptr(pooled), L.ptr(arg), L.ptr(gates), L.ptr(h), L.dt(h), ld(h), V, B, D, L.ptr(g_xy),
+           L.ptr(g_pooled), L.ptr(patch_arg), L.ptr(patch_val), L.ptr(dgates), int(acc_view), L.stream())
+    return patch_arg, patch_val
 
 
 def _dist_flag(dist: torch.Tensor) -> int:

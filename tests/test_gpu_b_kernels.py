@@ -266,3 +266,32 @@ def test_wgrad_batch(shape):
                 assert rel(dbs[i], ad.sum(0)) < 2e-6
             if bias_of == 2:
                 assert rel(dbs[i], bd.sum(0)) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+@pytest.mark.parametrize("long_sentences", [False, True])
+def test_views_patch_folded_into_adjoint_aggregation(dtype, long_sentences):
+    """edg_views_patch + edg_aggregate_patched == edg_aggregate followed by edg_views_bwd (same dh, same dgates)."""
+    from ed_gated_gcn_b200 import ops
+    batch, g = _batch_graph(6 if long_sentences else 45, 300 if long_sentences else 1, 700 if long_sentences else 40, seed=17)
+    D, V, B = 72, 2, batch.n_graphs
+    gen = torch.Generator().manual_seed(3)
+    h = ops.as_rows(torch.randn(batch.n_rows, D, generator=gen).to(DEV), dtype)
+    dm = ops.as_rows(torch.randn(batch.n_rows, D, generator=gen).to(DEV), dtype)
+    gates = (torch.rand(V, B, D, generator=gen) + 0.05).to(DEV)
+    gates[1, 2, :7] = 0.0                                       # an exactly-zero gate: other arg row, zero contribution
+    pooled, arg = ops.pool_fwd(h, g, gates)
+    g_xy = torch.tensor(0.7, device=DEV)
+    base = torch.randn(V, B, D, generator=gen).to(DEV)
+    # reference order: aggregate, then the scattered read-modify-write
+    dh_a = ops.aggregate(dm, g, mode=1, out_dtype=torch.float32)
+    dg_a = base.clone()
+    ops.views_bwd(pooled, arg, gates, h, g_xy, None, dh_a, dg_a, acc_view=1)
+    dg_b = base.clone()
+    patch = ops.views_patch(pooled, arg, gates, h, g_xy, None, dg_b, acc_view=1)
+    dh_b = ops.aggregate(dm, g, mode=1, out_dtype=torch.float32, patch=patch)
+    assert torch.equal(dg_a, dg_b)
+    assert rel(dh_b, dh_a) < 1e-6
+    # and in the compute dtype (one rounding instead of two)
+    dh_c = ops.aggregate(dm, g, mode=1, patch=patch)
+    assert rel(dh_c.float(), dh_a) < (1e-6 if dtype == torch.float32 else 6e-3)
