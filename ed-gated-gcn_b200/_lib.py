@@ -32,7 +32,7 @@ SIGNATURES = {
     "edg_tree_dist": (c_int, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "edg_dist_pad": (c_int, [_P, _P, _I, _I, c_int, _P, _P]),
     "edg_aggregate": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, _P, c_int, _P, _P, _I, _I, _P]),
-    "edg_aggregate_patched": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, _P, c_int, _P, _P, _I, _I, _P, _P, _P]),
+    "edg_aggregate_patched": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, _P, c_int, _P, _P, _I, _I, _P, _P, _I, _P]),
     "edg_linear": (c_int, [_P, c_int, _L, _I, _I, _P, _L, _I, _P, c_int, _P, c_int, _L, _P]),
     "edg_wgrad_workspace": (_Z, [_I, _I, _I, c_int]),
     "edg_wgrad": (c_int, [_P, _L, _I, _P, _L, _I, c_int, _I, _P, _L, _P, c_int, c_int, _P, _Z, _P]),
@@ -43,10 +43,10 @@ SIGNATURES = {
     "edg_cast_batch": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "edg_trigger_gather": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _P, _P, _L, c_int, _P]),
     "edg_trigger_scatter_add": (c_int, [_P, _I, _I, _P, _P, _P, c_int, _L, _P]),
-    "edg_pool_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _I, _P, _P, _P, _I, _I, _P]),
+    "edg_pool_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P]),
     "edg_diversity_fwd": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "edg_views_bwd": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _L, _P, c_int, _P]),
-    "edg_views_patch": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _P, _P, c_int, _P]),
+    "edg_views_patch": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, c_int, _P]),
     "edg_scores_kl_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _I, _I, _P]),
     "edg_fc_head_fwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "edg_fc_head_bwd_workspace": (_Z, [_I, _I, _I]),

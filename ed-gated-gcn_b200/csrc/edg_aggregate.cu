@@ -32,14 +32,28 @@ template <> __device__ __forceinline__ void store_chunk<__nv_bfloat16, 4>(__nv_b
 // Optional epilogue of the adjoint pass: y[patch_arg[b,d], d] += patch_val[b,d] -- the gradient that the gated
 // max-pool views of layer 1 (bert_amir5.py:627-636) route to their arg-max rows, folded into the kernel that
 // produces d h_1 instead of a separate scattered read-modify-write pass (edg_views_patch builds the two arrays).
-struct AggPatch { const int32_t* arg; const float* val; const int32_t* row_sent; int D; };
+struct AggPatch { const int16_t* loc; const float* val; const int32_t* row_sent; const int32_t* sent_ptr; int D, ldp; };
 
+// loc = sentence-local row index per (sentence, column) or -1, pitch ldp (multiple of 8): one 8- or 16-byte load
+// covers the thread's E columns
 template <int E>
 __device__ __forceinline__ void apply_patch(const AggPatch& p, int row, int c, float (&acc)[E]) {
-  const int64_t o = (int64_t)__ldg(p.row_sent + row) * p.D + c;
+  const int b = __ldg(p.row_sent + row);
+  const int lr = row - __ldg(p.sent_ptr + b);
+  const int64_t o = (int64_t)b * p.ldp + c;
+  uint32_t w[E / 2];
+  if (E == 8) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.loc + o));
+    w[0] = q.x; w[1] = q.y; w[E / 2 - 2] = q.z; w[E / 2 - 1] = q.w;
+  } else {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p.loc + o));
+    w[0] = q.x; w[1] = q.y;
+  }
 #pragma unroll
-  for (int k = 0; k < E; ++k)
-    if (c + k < p.D && __ldg(p.arg + o + k) == row) acc[k] += __ldg(p.val + o + k);
+  for (int k = 0; k < E; ++k) {
+    const int l = (int)(int16_t)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu));
+    if (l == lr) acc[k] += __ldg(p.val + o + k);
+  }
 }
 
 template <typename TI, typename TO, int MODE>
@@ -88,7 +102,7 @@ aggregate_flat_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y,
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = acc[k] / den;
   }
-  if (patch.arg) apply_patch<E>(patch, row, c, acc);
+  if (patch.loc) apply_patch<E>(patch, row, c, acc);
   store_chunk<TO, E>(y + (int64_t)row * ldy + c, acc);
 }
 
@@ -126,7 +140,7 @@ __device__ __noinline__ void aggregate_rows_global(const TI* __restrict__ x, int
 #pragma unroll
       for (int k = 0; k < E; ++k) acc[k] *= inv;
     }
-    if (patch.arg) apply_patch<E>(patch, row, c, acc);
+    if (patch.loc) apply_patch<E>(patch, row, c, acc);
     store_chunk<TO, E>(y + (int64_t)row * ldy + c, acc);
   }
 }
@@ -231,7 +245,7 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
 #pragma unroll
       for (int k = 0; k < E; ++k) acc[k] *= inv;
     }
-    if (patch.arg) apply_patch<E>(patch, r0 + lr, (int)threadIdx.x * E, acc);
+    if (patch.loc) apply_patch<E>(patch, r0 + lr, (int)threadIdx.x * E, acc);
     store_chunk<TO, E>(yrow, acc);
   }
 }
@@ -293,15 +307,16 @@ using namespace edg;
 static int aggregate_entry(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
                            int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
                            const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
-                           const int32_t* patch_arg, const float* patch_val, edg_stream stream) {
+                           const int16_t* patch_loc, const float* patch_val, int32_t ldp, edg_stream stream) {
   if (N < 0 || D <= 0 || (mode != 0 && mode != 1)) return EDG_ERR_ARG;
   if (N == 0) return EDG_OK;
   if (!x || !y || !row_ptr || !col) return EDG_ERR_ARG;
-  if ((patch_arg != nullptr) != (patch_val != nullptr)) return EDG_ERR_ARG;
-  if (patch_arg && !row_sent) return EDG_ERR_ARG;
+  if ((patch_loc != nullptr) != (patch_val != nullptr)) return EDG_ERR_ARG;
+  if (patch_loc && (!row_sent || !sent_ptr || ldp < D || (ldp & 7) || !aligned16(patch_loc) || !aligned16(patch_val)))
+    return EDG_ERR_ARG;
   if (!aligned16(x) || !aligned16(y) || !row_pitch_ok(x_dtype, ldx) || !row_pitch_ok(y_dtype, ldy)) return EDG_ERR_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
-  AggPatch patch{patch_arg, patch_val, row_sent, D};
+  AggPatch patch{patch_loc, patch_val, row_sent, sent_ptr, D, ldp};
   if (x_dtype == EDG_BF16 && y_dtype == EDG_BF16) return launch_aggregate<__nv_bfloat16, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch, s);
   if (x_dtype == EDG_F32 && y_dtype == EDG_F32) return launch_aggregate<float, float>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch, s);
   if (x_dtype == EDG_F32 && y_dtype == EDG_BF16) return launch_aggregate<float, __nv_bfloat16>(x, ldx, y, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch, s);
@@ -314,13 +329,14 @@ extern "C" int edg_aggregate(const void* x, int x_dtype, int64_t ldx, void* y, i
                              const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
                              edg_stream stream) {
   return aggregate_entry(x, x_dtype, ldx, y, y_dtype, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, nullptr,
-                         nullptr, stream);
+                         nullptr, 0, stream);
 }
 
 extern "C" int edg_aggregate_patched(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
                                      int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
                                      const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
-                                     const int32_t* patch_arg, const float* patch_val, edg_stream stream) {
-  return aggregate_entry(x, x_dtype, ldx, y, y_dtype, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch_arg,
-                         patch_val, stream);
+                                     const int16_t* patch_loc, const float* patch_val, int32_t ldp,
+                                     edg_stream stream) {
+  return aggregate_entry(x, x_dtype, ldx, y, y_dtype, ldy, N, D, row_ptr, col, mode, sent_ptr, row_sent, B, max_len, patch_loc,
+                         patch_val, ldp, stream);
 }

@@ -44,7 +44,8 @@ __global__ void trigger_scatter_add_kernel(const float* __restrict__ da, int B, 
 template <typename T, int V>
 __global__ void __launch_bounds__(128)
 pool_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr, int B, int D, int chunks,
-                const float* __restrict__ gates, float* __restrict__ pooled, int32_t* __restrict__ arg) {
+                const float* __restrict__ gates, float* __restrict__ pooled, int32_t* __restrict__ arg,
+                float* __restrict__ hmax) {
   // same rule as pool_staged_kernel: gate-independent column maximum + first row, one multiply per view
   constexpr int E = Vec16<T>::kElems;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,6 +82,10 @@ pool_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict_
         pooled[o] = (beg < end) ? m[k] * g : 0.f;
         arg[o] = (beg < end) ? (g != 0.f ? where[k] : beg) : -1;
       }
+  if (hmax)
+#pragma unroll
+    for (int k = 0; k < E; ++k)
+      if (c + k < D) hmax[(int64_t)b * D + c + k] = (beg < end) ? m[k] : 0.f;
 }
 
 // ---- diversity term -----------------------------------------------------------
@@ -148,41 +153,45 @@ views_bwd_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ a
 }
 
 // The same gradients WITHOUT touching dh: what the views send to their arg-max rows is written as one
-// (row, value) pair per (sentence, column) for the aggregation kernel that produces dh to add on the fly
-// (edg_aggregate_patched).  The views share their arg-max row (the gated maximum is the gate times the plain
-// column maximum for positive gates); a view whose gate is exactly 0 points elsewhere but contributes 0.
-template <typename T>
+// (sentence-local row, value) pair per (sentence, column) for the aggregation kernel that produces dh to add on
+// the fly (edg_aggregate_patched).  Pure [B,D] streaming: h at the arg-max row is the column maximum `hmax`
+// that edg_pool_fwd returns.  Positive gates (sigmoid outputs) as in edg_pool_fwd: the views then share their
+// arg-max row; a view whose gate is exactly 0 contributes nothing to dh.
 __global__ void __launch_bounds__(256)
 views_patch_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ arg, const float* __restrict__ gates,
-                   const T* __restrict__ h, int64_t ldh, int V, int B, int D, const float* __restrict__ g_xy,
-                   const float* __restrict__ g_pooled, int32_t* __restrict__ patch_arg, float* __restrict__ patch_val,
-                   float* __restrict__ dgates, int acc_view) {
+                   const float* __restrict__ hmax, const int32_t* __restrict__ sent_ptr, int V, int B, int D, int ldp,
+                   const float* __restrict__ g_xy, const float* __restrict__ g_pooled, int16_t* __restrict__ patch_loc,
+                   float* __restrict__ patch_val, float* __restrict__ dgates, int acc_view) {
   const int64_t BD = (int64_t)B * D;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BD) return;
-  const int d = (int)(i % D);
+  if (i >= (int64_t)B * ldp) return;
+  const int b = (int)(i / ldp), d = (int)(i - (int64_t)b * ldp);
+  if (d >= D) { patch_loc[i] = -1; patch_val[i] = 0.f; return; }
+  const int64_t o = (int64_t)b * D + d;
   const float gxy = g_xy ? (__ldg(g_xy) / (float)B) : 0.f;
   float tot = 0.f;
-  for (int v = 0; v < V; ++v) tot += pooled[v * BD + i];
+  for (int v = 0; v < V; ++v) tot += pooled[v * BD + o];
+  const float hm = hmax[o];
   int prow = -1;
   float pval = 0.f;
   for (int v = 0; v < V; ++v) {
-    float dp = gxy * (tot - pooled[v * BD + i]);
-    if (g_pooled) dp += g_pooled[v * BD + i];
-    const int r = arg[v * BD + i];
+    float dp = gxy * (tot - pooled[v * BD + o]);
+    if (g_pooled) dp += g_pooled[v * BD + o];
+    const int r = arg[v * BD + o];
     float dgv = 0.f;
     if (r >= 0) {
-      dgv = dp * to_f32(h[(int64_t)r * ldh + d]);
-      const float contrib = dp * gates[v * BD + i];
+      dgv = dp * hm;
+      const float contrib = dp * gates[v * BD + o];
       if (contrib != 0.f) {
         if (prow < 0) prow = r;
         if (r == prow) pval += contrib;
       }
     }
-    dgates[v * BD + i] = (v == acc_view) ? dgates[v * BD + i] + dgv : dgv;
+    dgates[v * BD + o] = (v == acc_view) ? dgates[v * BD + o] + dgv : dgv;
   }
-  patch_arg[i] = prow;
-  patch_val[i] = pval;
+  const int loc = prow >= 0 ? prow - sent_ptr[b] : -1;
+  patch_loc[i] = (int16_t)((loc >= 0 && loc < 32767) ? loc : -1);
+  patch_val[i] = (loc >= 0 && loc < 32767) ? pval : 0.f;
 }
 
 // ---- importance scores + softmax product ("kl") ---------------------------------
@@ -473,7 +482,7 @@ __global__ void cast_batch_kernel(const __grid_constant__ CastBatch b, int dst_d
 namespace edg {
 template <typename T>
 int pool_fwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
-                    int max_len, const float* gates, int V, float* pooled, int32_t* arg, cudaStream_t s);
+                    int max_len, const float* gates, int V, float* pooled, int32_t* arg, float* hmax, cudaStream_t s);
 template <typename T>
 int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
                      int max_len, const float* gate, const float* v, const float* c, const void* dist, int dist_i64,
@@ -527,7 +536,7 @@ extern "C" int edg_trigger_scatter_add(const float* da, int32_t B, int32_t D, co
 
 template <typename T>
 static int pool_fwd_dispatch(const void* h, int64_t ldh, const int32_t* sent_ptr, int B, int D, const float* gates,
-                             int V, float* pooled, int32_t* arg, cudaStream_t s) {
+                             int V, float* pooled, int32_t* arg, float* hmax, cudaStream_t s) {
   constexpr int E = Vec16<T>::kElems;
   const int chunks = (D + E - 1) / E;
   const unsigned blocks = blocks_for((int64_t)B * chunks, 128);
@@ -538,10 +547,10 @@ static int pool_fwd_dispatch(const void* h, int64_t ldh, const int32_t* sent_ptr
     float* p = pooled + v0 * BD;
     int32_t* a = arg + v0 * BD;
     switch (nv) {
-      case 1: pool_fwd_kernel<T, 1><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, g, p, a); break;
-      case 2: pool_fwd_kernel<T, 2><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, g, p, a); break;
-      case 3: pool_fwd_kernel<T, 3><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, g, p, a); break;
-      default: pool_fwd_kernel<T, 4><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, g, p, a); break;
+      case 1: pool_fwd_kernel<T, 1><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, g, p, a, v0 == 0 ? hmax : nullptr); break;
+      case 2: pool_fwd_kernel<T, 2><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, g, p, a, v0 == 0 ? hmax : nullptr); break;
+      case 3: pool_fwd_kernel<T, 3><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, g, p, a, v0 == 0 ? hmax : nullptr); break;
+      default: pool_fwd_kernel<T, 4><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, g, p, a, v0 == 0 ? hmax : nullptr); break;
     }
   }
   return check_launch();
@@ -549,7 +558,7 @@ static int pool_fwd_dispatch(const void* h, int64_t ldh, const int32_t* sent_ptr
 
 extern "C" int edg_pool_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                             int32_t D, const float* gates, int32_t V, float* pooled, int32_t* arg,
-                            const int32_t* row_sent, int32_t N, int32_t max_len, edg_stream stream) {
+                            const int32_t* row_sent, int32_t N, int32_t max_len, float* hmax, edg_stream stream) {
   if (B < 0 || D <= 0 || V <= 0) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
   if (!h || !sent_ptr || !gates || !pooled || !arg) return EDG_ERR_ARG;
@@ -557,10 +566,10 @@ extern "C" int edg_pool_fwd(const void* h, int dtype, int64_t ldh, const int32_t
   cudaStream_t s = (cudaStream_t)stream;
   EDG_DISPATCH_T(dtype, {
     if (staged_enabled()) {
-      const int rc = pool_fwd_staged<T>(h, ldh, sent_ptr, row_sent, N, B, D, max_len, gates, V, pooled, arg, s);
+      const int rc = pool_fwd_staged<T>(h, ldh, sent_ptr, row_sent, N, B, D, max_len, gates, V, pooled, arg, hmax, s);
       if (rc <= 0) return rc;
     }
-    return pool_fwd_dispatch<T>(h, ldh, sent_ptr, B, D, gates, V, pooled, arg, s);
+    return pool_fwd_dispatch<T>(h, ldh, sent_ptr, B, D, gates, V, pooled, arg, hmax, s);
   })
 }
 
@@ -595,15 +604,16 @@ extern "C" int edg_views_bwd(const float* pooled, const int32_t* arg, const floa
   return check_launch();
 }
 
-extern "C" int edg_views_patch(const float* pooled, const int32_t* arg, const float* gates, const void* h, int dtype,
-                               int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy, const float* g_pooled,
-                               int32_t* patch_arg, float* patch_val, float* dgates, int acc_view, edg_stream stream) {
-  if (V <= 0 || B < 0 || D <= 0) return EDG_ERR_ARG;
+extern "C" int edg_views_patch(const float* pooled, const int32_t* arg, const float* gates, const float* hmax,
+                               const int32_t* sent_ptr, int32_t V, int32_t B, int32_t D, int32_t ldp, const float* g_xy,
+                               const float* g_pooled, int16_t* patch_loc, float* patch_val, float* dgates, int acc_view,
+                               edg_stream stream) {
+  if (V <= 0 || B < 0 || D <= 0 || ldp < D || (ldp & 7)) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
-  if (!pooled || !arg || !gates || !h || !patch_arg || !patch_val || !dgates) return EDG_ERR_ARG;
+  if (!pooled || !arg || !gates || !hmax || !sent_ptr || !patch_loc || !patch_val || !dgates) return EDG_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  EDG_DISPATCH_T(dtype, views_patch_kernel<T><<<blocks_for((int64_t)B * D, 256), 256, 0, s>>>(
-      pooled, arg, gates, (const T*)h, ldh, V, B, D, g_xy, g_pooled, patch_arg, patch_val, dgates, acc_view);)
+  views_patch_kernel<<<blocks_for((int64_t)B * ldp, 256), 256, 0, s>>>(pooled, arg, gates, hmax, sent_ptr, V, B, D, ldp, g_xy,
+                                                                      g_pooled, patch_loc, patch_val, dgates, acc_view);
   return check_launch();
 }
 

@@ -22,7 +22,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr,
                    const int32_t* __restrict__ row_sent, int N, int B, int D, int tile_rows, int cap_rows,
-                   const float* __restrict__ gates, float* __restrict__ pooled, int32_t* __restrict__ arg) {
+                   const float* __restrict__ gates, float* __restrict__ pooled, int32_t* __restrict__ arg,
+                   float* __restrict__ hmax) {
   constexpr int E = Vec16<T>::kElems;
   extern __shared__ __align__(128) uint8_t win[];
   __shared__ __align__(8) uint64_t bar;
@@ -64,6 +65,10 @@ pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restri
           pooled[o] = (beg < end) ? m[k] * g[v][k] : 0.f;
           arg[o] = (beg < end) ? (g[v][k] != 0.f ? where[k] : beg) : -1;
         }
+    if (hmax)
+#pragma unroll
+      for (int k = 0; k < E; ++k)
+        if (c + k < D) hmax[(int64_t)s * D + c + k] = (beg < end) ? m[k] : 0.f;
   }
   if (!waited) wait_window(&bar);        // never leave a bulk copy in flight into a dead block
 }
@@ -336,7 +341,7 @@ static inline dim3 chunk_block(int chunks) {
 // returns 1 when the staged path does not apply (caller falls back to the per-sentence kernels)
 template <typename T>
 int pool_fwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
-                    int max_len, const float* gates, int V, float* pooled, int32_t* arg, cudaStream_t s) {
+                    int max_len, const float* gates, int V, float* pooled, int32_t* arg, float* hmax, cudaStream_t s) {
   constexpr int E = Vec16<T>::kElems;
   const int chunks = (D + E - 1) / E;
   if (!row_sent || max_len <= 0 || chunks > 256) return 1;
@@ -357,7 +362,7 @@ int pool_fwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const i
     rc = opt_in_smem(pool_staged_kernel<T, NV>, smem, &seen[NV - 1]);                                       \
     if (rc) return rc;                                                                                      \
     pool_staged_kernel<T, NV><<<blocks, blk, smem, s>>>((const T*)h, ldh, sent_ptr, row_sent, N, B, D, p.tile_rows,    \
-                                                       p.cap_rows, g, pp, aa);
+                                                       p.cap_rows, g, pp, aa, v0 == 0 ? hmax : nullptr);
     switch (nv) {
       case 1: EDG_POOL_CASE(1) break;
       default: EDG_POOL_CASE(2) break;

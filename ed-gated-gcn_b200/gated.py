@@ -131,7 +131,7 @@ class _GatedStackFn(torch.autograd.Function):
             ms.append(m)
             hs.append(h)
         # ---- gated views of layer 1 and the diversity term (:627-638)
-        v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
+        v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
         xy = ops.diversity_fwd(v_pooled) if Lyr > 1 else torch.zeros((), dtype=torch.float32, device=x.device)
         # ---- output pooling (:639-640)
         gL = gates[Lyr - 1]
@@ -160,6 +160,7 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.n_params = len(params)
         ctx.x_dtype = x.dtype
         ctx.x_cols = x.shape[1]
+        ctx.v_hmax = v_hmax
         ctx.save_for_backward(xr, gates, v_pooled, v_arg, p_arg, scores, kl_b, *ms, *hs, *params)
         # arg-max rows (global row ids), like the indices torch.max returns at :635-636/:640
         ctx.mark_non_differentiable(p_arg, v_arg)
@@ -244,7 +245,7 @@ class _GatedStackFn(torch.autograd.Function):
             if l == 1 and views_active:
                 # gated views of h_1 feed xy (:627-638): what they send to their arg-max rows is added while the
                 # adjoint aggregation writes d h_1 (no separate scattered pass)
-                patch = ops.views_patch(v_pooled, v_arg, gates, hs[0], g_xy, None, dgates, acc_view=Lyr - 1)
+                patch = ops.views_patch(v_pooled, v_arg, gates, ctx.v_hmax, graph, g_xy, None, dgates, acc_view=Lyr - 1)
             dh = ops.aggregate(dm, graph, mode=1, patch=patch)
         dx = dh
         # ---- gate MLP backward (bert_amir5.py:562-571)

@@ -57,7 +57,7 @@ def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype
     if patch is not None:
         L.call("edg_aggregate_patched", L.ptr(x), L.dt(x), ld(x), L.ptr(out), L.dt(out), ld(out), N, D,
                L.ptr(graph.row_ptr), L.ptr(graph.col), mode, L.ptr(graph.sent_ptr), L.ptr(graph.row_sent),
-               graph.n_graphs, graph.max_len, L.ptr(patch[0]), L.ptr(patch[1]), L.stream())
+               graph.n_graphs, graph.max_len, L.ptr(patch[0]), L.ptr(patch[1]), patch[0].shape[1], L.stream())
         return out
     L.call("edg_aggregate", L.ptr(x), L.dt(x), ld(x), L.ptr(out), L.dt(out), ld(out), N, D,
            L.ptr(graph.row_ptr), L.ptr(graph.col), mode, L.ptr(graph.sent_ptr), L.ptr(graph.row_sent),
@@ -207,13 +207,16 @@ def trigger_scatter_add(da: torch.Tensor, graph, anchor: torch.Tensor, dx: torch
            ld(dx), L.stream())
 
 
-def pool_fwd(h: torch.Tensor, graph, gates: torch.Tensor):
-    """gates fp32 [V,B,D] -> pooled fp32 [V,B,D], arg int32 [V,B,D]."""
+def pool_fwd(h: torch.Tensor, graph, gates: torch.Tensor, want_hmax: bool = False):
+    """gates fp32 [V,B,D] -> pooled fp32 [V,B,D], arg int32 [V,B,D] (+ hmax fp32 [B,D], the plain column maximum)."""
     V, B, D = gates.shape
     pooled = torch.empty((V, B, D), dtype=torch.float32, device=h.device)
     arg = torch.empty((V, B, D), dtype=torch.int32, device=h.device)
+    hmax = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_hmax else None
     L.call("edg_pool_fwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gates), V, L.ptr(pooled),
-           L.ptr(arg), L.ptr(graph.row_sent), graph.n_rows, graph.max_len, L.stream())
+           L.ptr(arg), L.ptr(graph.row_sent), graph.n_rows, graph.max_len, L.ptr(hmax), L.stream())
+    if want_hmax:
+        return pooled, arg, hmax
     return pooled, arg
 
 
@@ -231,15 +234,16 @@ def views_bwd(pooled, arg, gates, h, g_xy, g_pooled, dh, dgates, acc_view: int =
            L.ptr(g_pooled), L.ptr(dh), ld(dh), L.ptr(dgates), int(acc_view), L.stream())
 
 
-def views_patch(pooled, arg, gates, h, g_xy, g_pooled, dgates, acc_view: int = -1):
+def views_patch(pooled, arg, gates, hmax, graph, g_xy, g_pooled, dgates, acc_view: int = -1):
     """Backward of the gated views + diversity term without touching dh: writes dgates and returns
-    (patch_arg, patch_val) for :func:`aggregate` (``patch=``)."""
+    (patch_loc int16 [B,ldp], patch_val fp32 [B,ldp]) for :func:`aggregate` (``patch=``)."""
     V, B, D = pooled.shape
-    patch_arg = torch.empty((B, D), dtype=torch.int32, device=pooled.device)
-    patch_val = torch.empty((B, D), dtype=torch.float32, device=pooled.device)
-    L.call("edg_views_patch", L.ptr(pooled), L.ptr(arg), L.ptr(gates), L.ptr(h), L.dt(h), ld(h), V, B, D, L.ptr(g_xy),
-           L.ptr(g_pooled), L.ptr(patch_arg), L.ptr(patch_val), L.ptr(dgates), int(acc_view), L.stream())
-    return patch_arg, patch_val
+    ldp = _round_up(D, 8)
+    patch_loc = torch.empty((B, ldp), dtype=torch.int16, device=pooled.device)
+    patch_val = torch.empty((B, ldp), dtype=torch.float32, device=pooled.device)
+    L.call("edg_views_patch", L.ptr(pooled), L.ptr(arg), L.ptr(gates), L.ptr(hmax), L.ptr(graph.sent_ptr), V, B, D, ldp,
+           L.ptr(g_xy), L.ptr(g_pooled), L.ptr(patch_loc), L.ptr(patch_val), L.ptr(dgates), int(acc_view), L.stream())
+    return patch_loc, patch_val
 
 
 def _dist_flag(dist: torch.Tensor) -> int:

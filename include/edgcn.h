@@ -115,14 +115,15 @@ int edg_aggregate(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype,
                   const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
                   edg_stream stream);
 
-/* edg_aggregate followed by y[patch_arg[b,d], d] += patch_val[b,d] for every sentence b and column d
- * (patch_arg int32 [B,D] global row ids, -1 = none; patch_val fp32 [B,D]; row_sent required): the gradient the
- * gated max-pool views send to their arg-max rows (edg_views_patch) is added while d h_1 is being produced by
- * the adjoint aggregation, before its single rounding -- no separate scattered pass over d h_1. */
+/* edg_aggregate followed by y[sent_ptr[b] + patch_loc[b,d], d] += patch_val[b,d] for every sentence b and column d
+ * (patch_loc int16 [B,ldp] sentence-local row, -1 = none; patch_val fp32 [B,ldp]; ldp = D rounded up to a multiple
+ * of 8; sent_ptr and row_sent required): the gradient the gated max-pool views send to their arg-max rows
+ * (edg_views_patch) is added while d h_1 is being produced by the adjoint aggregation, before its single
+ * rounding -- no separate scattered pass over d h_1. */
 int edg_aggregate_patched(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy,
                           int32_t N, int32_t D, const int32_t* row_ptr, const int32_t* col, int mode,
                           const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
-                          const int32_t* patch_arg, const float* patch_val, edg_stream stream);
+                          const int16_t* patch_loc, const float* patch_val, int32_t ldp, edg_stream stream);
 
 /* C[M,Nout] = act(A[M,K] * W^T + bias), W given as [Nout,K] with K contiguous
  * (nn.Linear layout).  Replaces torch.matmul(text, weight) of gcn.py:34 (with a
@@ -205,10 +206,12 @@ int edg_trigger_scatter_add(const float* da, int32_t B, int32_t D, const int32_t
  * sentence's rows, arg = global row of the maximum (first row wins ties).
  * row_sent[N] + max_len (may be NULL/0) enable the shared-memory staged kernel: the rows of the sentences
  * starting in a window are brought in by one bulk async copy instead of one dependent load per row;
- * the same holds for edg_scores_kl_fwd and edg_head_bwd. */
+ * the same holds for edg_scores_kl_fwd and edg_head_bwd.
+ * hmax (optional, fp32 [B,D]): the plain column maximum max_t h[t,:] of every sentence -- h at the arg-max row,
+ * which the backward of the views needs (edg_views_patch). */
 int edg_pool_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                  int32_t D, const float* gates, int32_t V, float* pooled, int32_t* arg,
-                 const int32_t* row_sent, int32_t N, int32_t max_len, edg_stream stream);
+                 const int32_t* row_sent, int32_t N, int32_t max_len, float* hmax, edg_stream stream);
 
 /* bert_amir5.py:638: xy = sum_{v<v'} mean_b sum_d pooled[v]*pooled[v'].
  * ws: 1024 floats. */
@@ -238,13 +241,15 @@ int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent
                       float* dv_unit, float* dc_unit, const int32_t* row_sent, int32_t N, int32_t max_len,
                       edg_stream stream);
 
-/* edg_views_bwd without the read-modify-write of dh: dgates as there, and what would be added to dh comes back as
- * patch_arg int32 [B,D] (global row, -1 = nothing) / patch_val fp32 [B,D] for edg_aggregate_patched.  Assumes what
- * edg_pool_fwd guarantees for positive gates: the views of a (sentence, column) share their arg-max row (a view
- * whose gate is exactly 0 may point elsewhere; it contributes 0). */
-int edg_views_patch(const float* pooled, const int32_t* arg, const float* gates, const void* h, int dtype,
-                    int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy, const float* g_pooled,
-                    int32_t* patch_arg, float* patch_val, float* dgates, int acc_view, edg_stream stream);
+/* edg_views_bwd without the read-modify-write of dh and without the gather of h at the arg-max rows (hmax fp32
+ * [B,D] = the column maximum edg_pool_fwd returns): dgates as there; what would be added to dh comes back as
+ * patch_loc int16 [B,ldp] (sentence-local row, -1 = nothing) / patch_val fp32 [B,ldp] for edg_aggregate_patched.
+ * Assumes what edg_pool_fwd guarantees for positive gates (sigmoid outputs): the views of a (sentence, column)
+ * share their arg-max row; a view whose gate is exactly 0 contributes nothing to dh. */
+int edg_views_patch(const float* pooled, const int32_t* arg, const float* gates, const float* hmax,
+                    const int32_t* sent_ptr, int32_t V, int32_t B, int32_t D, int32_t ldp, const float* g_xy,
+                    const float* g_pooled, int16_t* patch_loc, float* patch_val, float* dgates, int acc_view,
+                    edg_stream stream);
 
 /* bert_amir5.py:645-646 collapsed: the per-sentence operands of the importance scores,
  *   [v_b | va_b] = logits_b @ fc.weight   (fc.weight [C, 2D], nn.Linear layout; C <= 64),

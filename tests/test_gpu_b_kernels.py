@@ -274,24 +274,38 @@ def test_views_patch_folded_into_adjoint_aggregation(dtype, long_sentences):
     """edg_views_patch + edg_aggregate_patched == edg_aggregate followed by edg_views_bwd (same dh, same dgates)."""
     from ed_gated_gcn_b200 import ops
     batch, g = _batch_graph(6 if long_sentences else 45, 300 if long_sentences else 1, 700 if long_sentences else 40, seed=17)
-    D, V, B = 72, 2, batch.n_graphs
+    D, V, B = 76, 2, batch.n_graphs                             # 76: the int16 patch rows need their own pitch (80)
     gen = torch.Generator().manual_seed(3)
     h = ops.as_rows(torch.randn(batch.n_rows, D, generator=gen).to(DEV), dtype)
     dm = ops.as_rows(torch.randn(batch.n_rows, D, generator=gen).to(DEV), dtype)
     gates = (torch.rand(V, B, D, generator=gen) + 0.05).to(DEV)
     gates[1, 2, :7] = 0.0                                       # an exactly-zero gate: other arg row, zero contribution
-    pooled, arg = ops.pool_fwd(h, g, gates)
+    pooled, arg, hmax = ops.pool_fwd(h, g, gates, want_hmax=True)
+    hu = h.float()
+    for b in (0, 2, B - 1):
+        lo, hi = int(batch.sent_ptr[b]), int(batch.sent_ptr[b + 1])
+        assert torch.equal(hmax[b], hu[lo:hi].max(0)[0])
     g_xy = torch.tensor(0.7, device=DEV)
     base = torch.randn(V, B, D, generator=gen).to(DEV)
-    # reference order: aggregate, then the scattered read-modify-write
-    dh_a = ops.aggregate(dm, g, mode=1, out_dtype=torch.float32)
+    # reference order: aggregate, then the scattered read-modify-write (in the compute dtype: two roundings)
+    dh_a = ops.aggregate(dm, g, mode=1)
     dg_a = base.clone()
     ops.views_bwd(pooled, arg, gates, h, g_xy, None, dh_a, dg_a, acc_view=1)
     dg_b = base.clone()
-    patch = ops.views_patch(pooled, arg, gates, h, g_xy, None, dg_b, acc_view=1)
-    dh_b = ops.aggregate(dm, g, mode=1, out_dtype=torch.float32, patch=patch)
-    assert torch.equal(dg_a, dg_b)
-    assert rel(dh_b, dh_a) < 1e-6
-    # and in the compute dtype (one rounding instead of two)
-    dh_c = ops.aggregate(dm, g, mode=1, patch=patch)
-    assert rel(dh_c.float(), dh_a) < (1e-6 if dtype == torch.float32 else 6e-3)
+    patch = ops.views_patch(pooled, arg, gates, hmax, g, g_xy, None, dg_b, acc_view=1)
+    dh_b = ops.aggregate(dm, g, mode=1, patch=patch)
+    live = gates != 0                                           # h at the arg row == hmax wherever the gate is live
+    assert torch.equal(dg_a[live], dg_b[live])
+    assert rel(dh_b.float(), dh_a.float()) < (1e-6 if dtype == torch.float32 else 6e-3)
+    # exact check of the patched rows in fp32 accumulation
+    dh32 = ops.aggregate(dm, g, mode=1, out_dtype=torch.float32)
+    dh32p = ops.aggregate(dm, g, mode=1, out_dtype=torch.float32, patch=patch)
+    want = dh32.clone()
+    loc, val = patch
+    for b in range(B):
+        for d in range(D):
+            l = int(loc[b, d])
+            if l >= 0:
+                want[int(batch.sent_ptr[b]) + l, d] += val[b, d]
+    assert rel(dh32p, want) < 1e-6
+    assert (loc[:, D:] == -1).all()
