@@ -47,6 +47,12 @@ def _chain_ok(cd: torch.dtype, D: int, n_gates: int, pairs: int) -> bool:
             and pairs <= ops.MLP_CHAIN_MAX_STAGES and os.environ.get("EDG_MLP_CHAIN", "1") != "0")
 
 
+# Opt-in (EDG_VIEWS_PATCH=1): the views' backward folded into the adjoint aggregation (edg_views_patch +
+# edg_aggregate_patched).  Correct (GPU suite passes with it) but measured SLOWER at C2: the patched aggregation
+# costs +26 us (two dependent index loads and eight compares per thread-row in an instruction-bound loop) and the
+# [B,D] patch kernel 40 us (twelve 4.9 MB fp32 arrays), against 54 us for the scattered edg_views_bwd pass.
+_PATCH_VIEWS = os.environ.get("EDG_VIEWS_PATCH", "0") == "1"
+
 StackOutput = namedtuple("StackOutput", ["logits", "xy", "kl", "scores", "pooled", "x_out", "pooled_arg", "view_arg"])
 
 
@@ -131,7 +137,10 @@ class _GatedStackFn(torch.autograd.Function):
             ms.append(m)
             hs.append(h)
         # ---- gated views of layer 1 and the diversity term (:627-638)
-        v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
+        if _PATCH_VIEWS:
+            v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
+        else:
+            (v_pooled, v_arg), v_hmax = ops.pool_fwd(hs[0], graph, gates), None
         xy = ops.diversity_fwd(v_pooled) if Lyr > 1 else torch.zeros((), dtype=torch.float32, device=x.device)
         # ---- output pooling (:639-640)
         gL = gates[Lyr - 1]
@@ -234,6 +243,9 @@ class _GatedStackFn(torch.autograd.Function):
         # ---- GCN chain backward (gcn.py:33-45)
         grads_out: List[Optional[torch.Tensor]] = [None] * ctx.n_params
         for l in range(Lyr - 1, -1, -1):
+            if l == 0 and views_active and not _PATCH_VIEWS:
+                # gated views of h_1 feed xy (:627-638): add their gradient before leaving layer 1
+                ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
             w, b = params[2 * l], params[2 * l + 1]
             if cfg["relu"]:
                 dh = ops.as_rows(dh * (hs[l] > 0), cd)
@@ -242,9 +254,7 @@ class _GatedStackFn(torch.autograd.Function):
             wk = ctx.w_n[l]                                                     # [in,out] = B operand of dh W^T
             dm = ops.linear(dh, wk, None)
             patch = None
-            if l == 1 and views_active:
-                # gated views of h_1 feed xy (:627-638): what they send to their arg-max rows is added while the
-                # adjoint aggregation writes d h_1 (no separate scattered pass)
+            if l == 1 and views_active and _PATCH_VIEWS:
                 patch = ops.views_patch(v_pooled, v_arg, gates, ctx.v_hmax, graph, g_xy, None, dgates, acc_view=Lyr - 1)
             dh = ops.aggregate(dm, graph, mode=1, patch=patch)
         dx = dh
