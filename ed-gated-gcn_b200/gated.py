@@ -96,10 +96,16 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.w_t = [casted[i] for i in range(nW)]
         ctx.w_n = [casted[nW + i] for i in range(nW)]
         # ---- trigger vector and the gate MLPs (bert_amir5.py:615-622)
+        gated = cfg["gated"]
         a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
-        gates = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
         gate_saved = []
-        use_chain = _chain_ok(cd, D, Lyr, pairs)
+        if gated:
+            gates = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
+        else:
+            # ungated ablation (BertAmir55NoGate, bert_amir5.py:731-749): x = gc2(gc1(x)), out = max_t x, xy = 0.0;
+            # the same kernels run with a unit gate
+            gates = torch.ones((Lyr, B, D), dtype=torch.float32, device=x.device)
+        use_chain = gated and _chain_ok(cd, D, Lyr, pairs)
         ctx.use_chain = use_chain
         if use_chain:
             # every Linear+Sigmoid of every gate in ONE launch (activation tile resident in shared memory)
@@ -115,7 +121,7 @@ class _GatedStackFn(torch.autograd.Function):
                 stages.append(st)
                 gate_saved.append(acts)
             ops.mlp_chain(0, [s0] * Lyr, stages, B, D)
-        for g in range(Lyr if not use_chain else 0):
+        for g in range(Lyr if (gated and not use_chain) else 0):
             s = s0
             acts = [s0]
             for i, (w, b) in enumerate(gate_p[g]):
@@ -137,11 +143,15 @@ class _GatedStackFn(torch.autograd.Function):
             ms.append(m)
             hs.append(h)
         # ---- gated views of layer 1 and the diversity term (:627-638)
-        if _PATCH_VIEWS:
-            v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
+        v_pooled = v_arg = v_hmax = None
+        if not gated or Lyr < 2:
+            xy = torch.zeros((), dtype=torch.float32, device=x.device)
         else:
-            (v_pooled, v_arg), v_hmax = ops.pool_fwd(hs[0], graph, gates), None
-        xy = ops.diversity_fwd(v_pooled) if Lyr > 1 else torch.zeros((), dtype=torch.float32, device=x.device)
+            if _PATCH_VIEWS:
+                v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
+            else:
+                v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
+            xy = ops.diversity_fwd(v_pooled)
         # ---- output pooling (:639-640)
         gL = gates[Lyr - 1]
         pooled, p_arg = ops.pool_fwd(hs[-1], graph, gL.unsqueeze(0))
@@ -172,6 +182,8 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.v_hmax = v_hmax
         ctx.save_for_backward(xr, gates, v_pooled, v_arg, p_arg, scores, kl_b, *ms, *hs, *params)
         # arg-max rows (global row ids), like the indices torch.max returns at :635-636/:640
+        if v_arg is None:
+            v_arg = torch.empty((0,), dtype=torch.int32, device=x.device)
         ctx.mark_non_differentiable(p_arg, v_arg)
         return logits.detach(), xy, kl, scores, pooled, x_out, p_arg, v_arg
 
@@ -233,7 +245,7 @@ class _GatedStackFn(torch.autograd.Function):
             gp_total = gp_head.float() if gp_total is None else gp_total + gp_head.float()
         # ---- pass B over h_L: dh_L, dgate_L
         dgates = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
-        views_active = g_xy is not None and Lyr > 1
+        views_active = g_xy is not None and Lyr > 1 and cfg["gated"]
         if not views_active and Lyr > 1:
             dgates[:Lyr - 1].zero_()                                  # no diversity gradient: the other gates get none
         dh, _, _, _ = ops.head_bwd(hL, graph, gL, v if need_scores else None, dist,
@@ -260,7 +272,8 @@ class _GatedStackFn(torch.autograd.Function):
         dx = dh
         # ---- gate MLP backward (bert_amir5.py:562-571)
         # the last Sigmoid of every gate in one launch (gates / dgates are [V*B, D] row blocks)
-        dz_all = ops.sigmoid_bwd(gates.view(Lyr * B, D), dgates.view(Lyr * B, D), cd)
+        gated = cfg["gated"]
+        dz_all = ops.sigmoid_bwd(gates.view(Lyr * B, D), dgates.view(Lyr * B, D), cd) if gated else None
         da = ga_head.float().contiguous() if ga_head is not None else None
         if da is not None and not da.is_contiguous():
             da = da.contiguous()
@@ -295,7 +308,7 @@ class _GatedStackFn(torch.autograd.Function):
                     grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
             da_gate = da_parts.sum(0) if Lyr > 1 else da_parts[0]
             da = da_gate if da is None else da + da_gate
-        for g in range(Lyr if not ctx.use_chain else 0):
+        for g in range(Lyr if (gated and not ctx.use_chain) else 0):
             acts = ctx.gate_saved[g]
             dz = dz_all[g * B:(g + 1) * B]
             for i in range(pairs - 1, -1, -1):
@@ -316,7 +329,8 @@ class _GatedStackFn(torch.autograd.Function):
                 else:
                     dlast = ops.linear(dz, wt, None, out_dtype=torch.float32)
                     da = dlast if da is None else da + dlast
-        ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
+        if da is not None:
+            ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
         grads_out[-2], grads_out[-1] = d_fcw, d_fcb
         if ctx.x_padded:        # hand back the whole [N, pitch] allocation (padding columns are finite)
             dx = dx.as_strided((N, dx.stride(0)), (dx.stride(0), 1))
@@ -335,12 +349,13 @@ class GatedGCNStack(nn.Module):
     bert_amir5.py:559-572) and runs the whole block fused."""
 
     def __init__(self, hidden: int, n_layers: int = 2, n_classes: int = 2, gate_arch: str = "sig-2",
-                 relu: bool = False, dropout: float = 0.0, compute_dtype="f32"):
+                 relu: bool = False, dropout: float = 0.0, compute_dtype="f32", gated: bool = True):
         super().__init__()
         if hidden % 4:
             raise ValueError("hidden size must be a multiple of 4 (16-byte fp32 rows)")
         self.hidden, self.n_layers, self.n_classes = hidden, n_layers, n_classes
         self.gate_arch = gate_arch
+        self.gated = gated            # False = BertAmir55NoGate (gates constructed, as there, but unused: :672-681, :731-748)
         self.relu = relu
         self.dropout_p = dropout
         self.compute_dtype = _compute_dtype(compute_dtype)
@@ -387,7 +402,7 @@ class GatedGCNStack(nn.Module):
             raise L.EdgError(f"expected {self.hidden} feature columns (or the padded pitch), got {x.shape[-1]}")
         cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
-                   head_params=list(head_params), relu=self.relu, return_x_out=return_x_out)
+                   head_params=list(head_params), relu=self.relu, return_x_out=return_x_out, gated=self.gated)
         logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params())
         if shape3 is not None:
             scores = scores.reshape(shape3[0], shape3[1])

@@ -275,6 +275,26 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
             "x_out": x_out, "pooled": pooled, "logits": logits, "scores": scores, "kl": kl}
 
 
+def ungated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tensor, dist: torch.Tensor,
+                      gcn_params: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]],
+                      fc_w: torch.Tensor, fc_b: torch.Tensor, logits_fn) -> Dict[str, torch.Tensor]:
+    """The ungated ablation BertAmir55NoGate.forward, bert_amir5.py:728-758: ``x = gc2(gc1(x))`` (:736, :749),
+    ``out = max_t x`` (:750), logits (:753), scores / kl as in the gated block (:755-758), ``xy = 0.0`` (:760)."""
+    B, T, D = x.shape
+    aspect = x[torch.arange(B), anchor_index]                       # :728
+    h = x
+    for (w, b) in gcn_params:
+        h = gcn_layer_ref(h, adj, w, b)
+    pooled = torch.max(h, dim=1)[0]
+    logits = logits_fn(aspect, pooled)
+    cat = torch.cat([h, aspect[:, None, :].expand(B, T, D)], dim=2)
+    output_w = cat @ fc_w.t() + fc_b
+    scores = (logits[:, None, :] * output_w).sum(2)
+    kl = (torch.softmax(scores, 1) * torch.softmax(dist.to(x.dtype), 1)).sum(1).mean()
+    return {"aspect": aspect, "x_out": h, "pooled": pooled, "logits": logits, "scores": scores, "kl": kl,
+            "xy": x.new_zeros(())}
+
+
 def block_loss_ref(out: Dict[str, torch.Tensor], targets: torch.Tensor,
                    gate_w: float = 0.01, kl_w: float = 0.01) -> torch.Tensor:
     """train.py:115-118: cross entropy + gate_w * xy + kl_w * kl."""

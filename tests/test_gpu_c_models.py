@@ -286,6 +286,56 @@ def test_stack_packed_rows_vs_oracle(dtype, cfg):
     _compare(out, loss, x.grad, stack, dense, ora, ora_g, tol, Lyr)
 
 
+def test_ungated_ablation_matches_oracle():
+    """gated=False = BertAmir55NoGate (bert_amir5.py:654-760): same kernels with a unit gate, xy = 0.0, gate
+    parameters present in the state dict (the reference constructs them, :672-681) but untouched by backward."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import synth
+    torch.manual_seed(5)
+    batch = synth.make_batch(11, 1, 30, seed=41)
+    D, C, B = 48, 5, batch.n_graphs
+    stack = E.GatedGCNStack(D, n_layers=2, n_classes=C, gated=False).to(DEV)
+    gen = torch.Generator().manual_seed(6)
+    O.reference_init_([p for p in stack.parameters()], gen)
+    dense = torch.nn.Linear(2 * D, C).to(DEV)
+    assert "gate1.1.weight" in stack.state_dict()
+    graph = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=DEV)
+    anchor = torch.from_numpy(batch.anchor).to(DEV)
+    dist = E.tree_distance(graph, anchor)
+    xp = torch.randn(batch.n_rows, D, generator=gen)
+    targets = torch.arange(B) % C
+    x = xp.to(DEV).requires_grad_(True)
+    out = stack(x, graph, anchor, dist, lambda a, p: dense(torch.cat([a, p], 1)), head_params=list(dense.parameters()),
+                return_x_out=True)
+    loss = torch.nn.functional.cross_entropy(out.logits, targets.to(DEV)) + 0.01 * out.xy + 0.01 * out.kl
+    loss.backward()
+    assert float(out.xy) == 0.0
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in stack.state_dict().items()}
+    dw, db = (t.detach().cpu().clone().requires_grad_(True) for t in (dense.weight, dense.bias))
+    gcn_p = [(sd["gc1.weight"], sd["gc1.bias"]), (sd["gc2.weight"], sd["gc2.bias"])]
+    sp = batch.sent_ptr
+    xs, logits, kl, scores, xouts = [], [], 0.0, [], []
+    for b, h in enumerate(batch.heads_list()):
+        xb = xp[sp[b]:sp[b + 1]].clone().requires_grad_(True)
+        adj = torch.from_numpy(O.dense_adjacency_from_heads(h, len(h))).float()
+        d = torch.tensor(O.tree_distance_bfs(h, int(batch.anchor[b])))
+        o = O.ungated_block_ref(xb[None], adj[None], torch.tensor([int(batch.anchor[b])]), d[None], gcn_p,
+                                sd["fc.0.weight"], sd["fc.0.bias"], lambda a, p: torch.cat([a, p], 1) @ dw.t() + db)
+        xs.append(xb); logits.append(o["logits"]); scores.append(o["scores"][0]); xouts.append(o["x_out"][0])
+        kl = kl + o["kl"] / B
+    want_loss = torch.nn.functional.cross_entropy(torch.cat(logits), targets) + 0.01 * kl
+    want_loss.backward()
+    assert rel(out.logits, torch.cat(logits)) < 1e-5 and rel(out.kl, kl) < 1e-5 and rel(loss, want_loss) < 1e-5
+    assert rel(out.scores, torch.cat(scores)) < 1e-5 and rel(out.x_out, torch.cat(xouts)) < 1e-5
+    assert rel(x.grad, torch.cat([t.grad for t in xs])) < 1e-5
+    for name in ("gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias", "fc.0.weight"):
+        assert rel(dict(stack.named_parameters())[name].grad, sd[name].grad) < 1e-5, name
+    assert rel(dense.weight.grad, dw.grad) < 1e-5
+    for name, p in stack.named_parameters():
+        if name.startswith("gate"):
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+
+
 def test_stack_rejects_cpu_and_training_dropout():
     import ed_gated_gcn_b200 as E
     from ed_gated_gcn_b200._lib import EdgError

@@ -132,3 +132,24 @@ def test_block_is_invariant_under_sentence_permutation(c2):
     for n in g1:
         if n != "fc.0.bias":
             assert rel(g2[n], g1[n]) < 2e-5, n
+
+
+def test_config5_shaped_aggregation_chunk_against_dense_reference():
+    """BASELINE config 5 shape: trees of 10..200 tokens (windows hold one or two sentences), D = 300 bf16,
+    aggregation only.  A 2,048-tree chunk against the reference's dense adj @ x / (rowsum + 1) per sentence."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import ops, synth
+    from oracle import ref_oracle as O
+    from gpu_util import DEV, rel
+    batch = synth.make_batch(2048, 10, 200, seed=synth.REFERENCE_SEED + 5)
+    g = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=DEV)
+    x = ops.as_rows(torch.randn(batch.n_rows, 300).to(DEV), torch.bfloat16)
+    y = ops.aggregate(x, g, mode=0).float().cpu()
+    xu = x.float().cpu()
+    worst = 0.0
+    for b in range(0, 2048, 37):
+        lo, hi = int(batch.sent_ptr[b]), int(batch.sent_ptr[b + 1])
+        adj = torch.from_numpy(O.dense_adjacency_from_heads(batch.heads[lo:hi], hi - lo)).float()
+        want = O.aggregation_only_ref(xu[lo:hi][None], adj[None])[0]
+        worst = max(worst, rel(y[lo:hi], want))
+    assert worst < 8e-3
