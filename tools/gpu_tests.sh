@@ -4,17 +4,15 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv | tee gpurun_out/gpu.txt
 run() {  # name, timeout, pytest args...
   local name=$1; shift; local to=$1; shift
+  local t0=$(date +%s)
   timeout $to python -m pytest "$@" -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/$name.log 2>&1
-  echo "== $name exit=$? : $(tail -1 gpurun_out/$name.log)"
+  echo "== $name exit=$? $(( $(date +%s) - t0 ))s : $(tail -1 gpurun_out/$name.log)"
 }
 run a_integer 600 tests/test_gpu_a_integer.py
-run b_aggregate 600 tests/test_gpu_b_kernels.py -k aggregate
-run b_linear_f32 600 tests/test_gpu_b_kernels.py -k "test_linear and f32"
-run b_wgrad_f32 600 tests/test_gpu_b_kernels.py -k "test_wgrad and f32"
-run b_pool_scores 600 tests/test_gpu_b_kernels.py -k "pool or scores"
-run c_models_f32 900 tests/test_gpu_c_models.py -k "f32 or share or relu or rejects"
-run b_linear_bf16 600 tests/test_gpu_b_kernels.py -k "test_linear and bf16"
-run b_wgrad_bf16 600 tests/test_gpu_b_kernels.py -k "test_wgrad and bf16"
-run b_tc_big 600 tests/test_gpu_b_kernels.py -k "tensor_core"
-run c_models_bf16 900 tests/test_gpu_c_models.py -k "bf16"
-for f in gpurun_out/*.log; do echo "---- $f"; grep -E "^(FAILED|ERROR)|Error|error|assert " $f | head -12; done
+run b_kernels_f32 900 tests/test_gpu_b_kernels.py -k "f32"
+run b_kernels_bf16 900 tests/test_gpu_b_kernels.py -k "bf16"
+run b_kernels_rest 900 tests/test_gpu_b_kernels.py -k "not f32 and not bf16"
+run c_models 900 tests/test_gpu_c_models.py
+run d_fullsize 900 tests/test_gpu_d_fullsize.py
+run e_neighbours 600 tests/test_gpu_e_neighbours.py
+for f in gpurun_out/[a-e]_*.log; do echo "---- $f"; grep -E "^(FAILED|ERROR)|Error|error|assert " $f | head -12; done
