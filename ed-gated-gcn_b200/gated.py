@@ -144,14 +144,14 @@ class _GatedStackFn(torch.autograd.Function):
             hs.append(h)
         # ---- gated views of layer 1 and the diversity term (:627-638)
         v_pooled = v_arg = v_hmax = None
-        if not gated or Lyr < 2:
-            xy = torch.zeros((), dtype=torch.float32, device=x.device)
-        else:
+        xy = torch.zeros((), dtype=torch.float32, device=x.device)
+        if gated:
             if _PATCH_VIEWS:
                 v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
             else:
                 v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
-            xy = ops.diversity_fwd(v_pooled)
+            if Lyr > 1:
+                xy = ops.diversity_fwd(v_pooled)
         # ---- output pooling (:639-640)
         gL = gates[Lyr - 1]
         pooled, p_arg = ops.pool_fwd(hs[-1], graph, gL.unsqueeze(0))
