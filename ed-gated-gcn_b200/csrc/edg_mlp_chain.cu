@@ -10,6 +10,8 @@
 //   direction / the weight-gradient GEMM needs, and write the bf16 result back into the SAME swizzled
 //   shared-memory tile as A_{s+1}  (generic-proxy stores + fence.proxy.async, then an mbarrier hands the tile
 //   to the MMA thread).  Only the [D x D] weights stream (3-stage TMA ring of [2*n_half x 64] K blocks).
+//   Warp 0 = TMA producer, warp 1 = MMA issuer, 16 epilogue warps (the epilogue is the critical path: a first
+//   version with 8 warps spent 12.8 cycles per issued instruction and left the tensor pipe waiting).
 //
 // D <= 320 (5 K blocks, two N halves of <= 160 TMEM columns); larger widths use the per-Linear kernels.
 // Unity build: included after edg_gemm_tc.cu (PTX wrappers, descriptors, tile constants).
@@ -22,6 +24,8 @@ constexpr int kChainMaxGroups = 4;
 constexpr int kChainWStages = 3;
 constexpr int kChainMaxKb = 5;
 constexpr int kChainBiasPitch = 64 * kChainMaxKb;   // 320
+constexpr int kChainEpiWarps = 16;                  // 4 per TMEM lane quarter: the epilogue is the critical path
+constexpr int kChainThreads = 64 + 32 * kChainEpiWarps;
 
 struct ChainStageDev {
   const float* bias;            // forward: [D] or null
@@ -45,7 +49,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kLinThreads, 1)
+__global__ void __launch_bounds__(kChainThreads, 1)
 mlp_chain_kernel(const __grid_constant__ ChainParams P, int M, int D, int n_stages, int mode, int n_half, int num_kb,
                  uint32_t idesc) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -64,7 +68,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams P, int M, int D, int n_stag
   auto Wst = [&](int s) { return w_base + (uint32_t)s * w_stage_bytes; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < n_stages * kChainBiasPitch; i += kLinThreads) {
+  for (int i = threadIdx.x; i < n_stages * kChainBiasPitch; i += kChainThreads) {
     const int s = i / kChainBiasPitch, col = i - s * kChainBiasPitch;
     const float* b = P.st[g][s].bias;
     bias_s[i] = (b && col < D) ? b[col] : 0.f;
@@ -72,7 +76,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams P, int M, int D, int n_stag
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.map_a[g]);
     for (int s = 0; s < n_stages; ++s) tma_prefetch_desc(&P.map_w[g][s]);
-    mbar_init(afull, 1); mbar_init(tfull, 1); mbar_init(aready, 8);
+    mbar_init(afull, 1); mbar_init(tfull, 1); mbar_init(aready, kChainEpiWarps);
     for (int s = 0; s < kChainWStages; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
     fence_barrier_init();
   }
@@ -127,8 +131,11 @@ mlp_chain_kernel(const __grid_constant__ ChainParams P, int M, int D, int n_stag
       }
     }
   } else {
+    // 16 epilogue warps: warp w reads TMEM lane quarter (w & 3); the four warps of a quarter take every fourth
+    // 32-column chunk.  The saved activation y of the next chunk (backward) is requested before the wait on the
+    // accumulator, so its DRAM/L2 latency overlaps the MMAs.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;
     const int r_tile = q * 32 + lane;
     const int row = m0 + r_tile;
     const bool row_ok = row < M;
@@ -137,10 +144,22 @@ mlp_chain_kernel(const __grid_constant__ ChainParams P, int M, int D, int n_stag
     for (int s = 0; s < n_stages; ++s) {
       const ChainStageDev& S = P.st[g][s];
       const bool last = s == n_stages - 1;
+      const bool has_y = mode == 1 && S.y != nullptr;
+      const __nv_bfloat16* yrow = has_y ? S.y + (int64_t)(row_ok ? row : 0) * S.ldy : nullptr;
+      uint4 yq[4];
+      auto load_y = [&](int c0) {
+#pragma unroll
+        for (int v8 = 0; v8 < 4; ++v8) {
+          const int col = c0 + v8 * 8;
+          yq[v8] = (row_ok && col + 8 <= S.ldy) ? __ldg(reinterpret_cast<const uint4*>(yrow + col)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if (has_y && sub < n_chunks) load_y(sub * 32);
       mbar_wait(tfull, (uint32_t)(s & 1));
       tc_fence_after();
-      for (int ci = half; ci < n_chunks; ci += 2) {
+      for (int ci = sub; ci < n_chunks; ci += 4) {
         const int c0 = ci * 32;
+        const bool full = c0 + 32 <= D;                      // chunk-uniform: only the last chunk masks columns
         uint32_t r[32];
         tmem_ld_32x32_nowait(tbase + c0, r);
         tmem_wait_ld();
@@ -148,25 +167,27 @@ mlp_chain_kernel(const __grid_constant__ ChainParams P, int M, int D, int n_stag
         if (mode == 0) {
           const float* bs = bias_s + s * kChainBiasPitch + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            val[j] = (c0 + j < D) ? __fdividef(1.0f, 1.0f + __expf(-(__uint_as_float(r[j]) + bs[j]))) : 0.f;
-        } else if (S.y != nullptr) {
+          for (int j = 0; j < 32; ++j) {
+            const float sg = __fdividef(1.0f, 1.0f + __expf(-(__uint_as_float(r[j]) + bs[j])));
+            val[j] = (full || c0 + j < D) ? sg : 0.f;
+          }
+        } else if (has_y) {
 #pragma unroll
           for (int v8 = 0; v8 < 4; ++v8) {
-            const int col = c0 + v8 * 8;
-            float yv[8];
-            if (row_ok && col + 8 <= S.ldy) Vec16<__nv_bfloat16>::load(S.y + (int64_t)row * S.ldy + col, yv);
-            else {
+            const uint32_t w[4] = {yq[v8].x, yq[v8].y, yq[v8].z, yq[v8].w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) yv[j] = 0.f;
+            for (int i = 0; i < 4; ++i) {                    // bf16 -> fp32 is a 16-bit shift; padding columns of y are 0
+              const float y0 = __uint_as_float(w[i] << 16), y1 = __uint_as_float(w[i] & 0xffff0000u);
+              const int j = v8 * 8 + 2 * i;
+              const float a0 = __uint_as_float(r[j]) * y0 * (1.f - y0), a1 = __uint_as_float(r[j + 1]) * y1 * (1.f - y1);
+              val[j] = (full || c0 + j < D) ? a0 : 0.f;
+              val[j + 1] = (full || c0 + j + 1 < D) ? a1 : 0.f;
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              val[v8 * 8 + j] = (col + j < D) ? __uint_as_float(r[v8 * 8 + j]) * yv[j] * (1.f - yv[j]) : 0.f;
           }
+          if (ci + 4 < n_chunks) load_y((ci + 4) * 32);      // next chunk's y while this one is stored
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = (c0 + j < D) ? __uint_as_float(r[j]) : 0.f;
+          for (int j = 0; j < 32; ++j) val[j] = (full || c0 + j < D) ? __uint_as_float(r[j]) : 0.f;
         }
         // global copy (saved activation / gate / gradient)
         if (row_ok && S.out != nullptr) {
@@ -174,12 +195,12 @@ mlp_chain_kernel(const __grid_constant__ ChainParams P, int M, int D, int n_stag
             float* o = reinterpret_cast<float*>(S.out) + (int64_t)row * S.ldo;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              if (c0 + j + 4 <= D) *reinterpret_cast<float4*>(o + c0 + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
+              if (full || c0 + j + 4 <= D) *reinterpret_cast<float4*>(o + c0 + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(S.out) + (int64_t)row * S.ldo;
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
-              if (c0 + j + 8 <= S.ldo)
+              if (full || c0 + j + 8 <= S.ldo)
                 *reinterpret_cast<uint4*>(o + c0 + j) =
                     make_uint4(pack_bf16x2(val[j], val[j + 1]), pack_bf16x2(val[j + 2], val[j + 3]),
                                pack_bf16x2(val[j + 4], val[j + 5]), pack_bf16x2(val[j + 6], val[j + 7]));
@@ -262,7 +283,7 @@ extern "C" int edg_mlp_chain(int mode, int32_t n_groups, int32_t n_stages, const
   }
   const int m_tiles = (M + kBlockM - 1) / kBlockM;
   const uint32_t idesc = make_idesc_bf16(kBlockM, n_half, 0, 0);
-  mlp_chain_kernel<<<dim3(m_tiles, n_groups), kLinThreads, smem, (cudaStream_t)stream>>>(P, M, D, n_stages, mode, n_half,
+  mlp_chain_kernel<<<dim3(m_tiles, n_groups), kChainThreads, smem, (cudaStream_t)stream>>>(P, M, D, n_stages, mode, n_half,
                                                                                          num_kb, idesc);
   return check_launch();
 }
