@@ -146,7 +146,7 @@ __device__ __noinline__ void aggregate_rows_global(const TI* __restrict__ x, int
 }
 
 template <typename TI, typename TO, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int N, int B,
                         int tile_rows, int cap_rows, const int32_t* __restrict__ sent_ptr,
                         const int32_t* __restrict__ row_sent, const int32_t* __restrict__ row_ptr,
@@ -270,9 +270,13 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
   // sentence cannot fit next to a useful window
   int cap_rows = (int)((72 * 1024) / (pitch + 24));
   int tile_rows = cap_rows - max_len + 1;
+  int max_threads = 256;
   if (tile_rows < 16) {
+    // long sentences (config 5: up to 200 tokens): one ~200 KB window per SM, so the block itself must bring
+    // the warps that hide the shared-memory latency (256 threads alone reached 34 % of the HBM peak)
     cap_rows = (int)((200 * 1024) / (pitch + 24));
     tile_rows = cap_rows - max_len + 1;
+    max_threads = 1024;
   }
   const bool staged = agg_variant() >= 3 && sent_ptr && row_sent && B > 0 && max_len > 0 && tile_rows >= 8;
   if (!staged) {
@@ -282,7 +286,7 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
     else aggregate_flat_kernel<TI, TO, 1><<<blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col, patch);
     return check_launch();
   }
-  int rpb = 256 / chunks;
+  int rpb = max_threads / chunks;
   if (rpb > 32) rpb = 32;
   dim3 block(chunks, rpb);
   const size_t smem = (size_t)cap_rows * pitch + (size_t)(6 * cap_rows + 8) * sizeof(int32_t);

@@ -53,6 +53,50 @@ def _chain_ok(cd: torch.dtype, D: int, n_gates: int, pairs: int) -> bool:
 # [B,D] patch kernel 40 us (twelve 4.9 MB fp32 arrays), against 54 us for the scattered edg_views_bwd pass.
 _PATCH_VIEWS = os.environ.get("EDG_VIEWS_PATCH", "0") == "1"
 
+# Two-stream overlap inside the autograd node (EDG_OVERLAP=0 disables it).  The gate MLPs (64 CTAs, latency-bound)
+# and the view pooling are independent of the aggregate -> projection chain until their results meet, so they are
+# enqueued on a side stream forked from / joined into the caller's stream with events; under CUDA-graph capture
+# the fork/join become parallel branches of the graph.  Discipline that keeps the caching allocator safe without
+# record_stream: the side stream always waits for the caller's current position before it starts, and the caller's
+# stream always joins the side stream before the node returns.
+_OVERLAP = os.environ.get("EDG_OVERLAP", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=key)
+        _SIDE_STREAMS[key] = st
+    return st
+
+
+class _Side:
+    """``with side.region():`` runs the body on the side stream after everything enqueued so far on the caller's
+    stream; ``side.join()`` makes the caller's stream wait for all side work.  Disabled = plain in-order code."""
+
+    def __init__(self, enabled: bool, device):
+        self.enabled = enabled
+        if enabled:
+            self.main = torch.cuda.current_stream(device)
+            self.side = _side_stream(device)
+        self.dirty = False
+
+    def region(self):
+        import contextlib
+        if not self.enabled:
+            return contextlib.nullcontext()
+        self.side.wait_stream(self.main)
+        self.dirty = True
+        return torch.cuda.stream(self.side)
+
+    def join(self):
+        if self.enabled and self.dirty:
+            self.main.wait_stream(self.side)
+            self.dirty = False
+
+
 StackOutput = namedtuple("StackOutput", ["logits", "xy", "kl", "scores", "pooled", "x_out", "pooled_arg", "view_arg"])
 
 
@@ -107,51 +151,55 @@ class _GatedStackFn(torch.autograd.Function):
             gates = torch.ones((Lyr, B, D), dtype=torch.float32, device=x.device)
         use_chain = gated and _chain_ok(cd, D, Lyr, pairs)
         ctx.use_chain = use_chain
-        if use_chain:
-            # every Linear+Sigmoid of every gate in ONE launch (activation tile resident in shared memory)
-            stages = []
-            for g in range(Lyr):
-                acts, st = [s0], []
+        side = _Side(_OVERLAP and gated, x.device)
+        with side.region():                       # overlaps the first aggregate -> projection below
+            if use_chain:
+                # every Linear+Sigmoid of every gate in ONE launch (activation tile resident in shared memory)
+                stages = []
+                for g in range(Lyr):
+                    acts, st = [s0], []
+                    for i, (w, b) in enumerate(gate_p[g]):
+                        last = i == pairs - 1
+                        out = gates[g] if last else ops.alloc_rows(B, D, cd, x.device)
+                        st.append(dict(w=w_n[id(w)], bias=b.detach().float().contiguous(), out=out))
+                        if not last:
+                            acts.append(out)
+                    stages.append(st)
+                    gate_saved.append(acts)
+                ops.mlp_chain(0, [s0] * Lyr, stages, B, D)
+            for g in range(Lyr if (gated and not use_chain) else 0):
+                s = s0
+                acts = [s0]
                 for i, (w, b) in enumerate(gate_p[g]):
+                    wk = w_n[id(w)]                                                 # nn.Linear [out,in] is K-major
                     last = i == pairs - 1
-                    out = gates[g] if last else ops.alloc_rows(B, D, cd, x.device)
-                    st.append(dict(w=w_n[id(w)], bias=b.detach().float().contiguous(), out=out))
+                    s = ops.linear(s, wk, b.detach().float().contiguous(), act=L.ACT_SIGMOID,
+                                   out_dtype=torch.float32 if last else cd, out=gates[g] if last else None)
                     if not last:
-                        acts.append(out)
-                stages.append(st)
+                        acts.append(s)
                 gate_saved.append(acts)
-            ops.mlp_chain(0, [s0] * Lyr, stages, B, D)
-        for g in range(Lyr if (gated and not use_chain) else 0):
-            s = s0
-            acts = [s0]
-            for i, (w, b) in enumerate(gate_p[g]):
-                wk = w_n[id(w)]                                                 # nn.Linear [out,in] is K-major
-                last = i == pairs - 1
-                s = ops.linear(s, wk, b.detach().float().contiguous(), act=L.ACT_SIGMOID,
-                               out_dtype=torch.float32 if last else cd, out=gates[g] if last else None)
-                if not last:
-                    acts.append(s)
-            gate_saved.append(acts)
-        # ---- ungated GCN chain (bert_amir5.py:626, :639; gcn.py:33-45)
+        # ---- ungated GCN chain (bert_amir5.py:626, :639; gcn.py:33-45); after layer 1 the gated views of h_1 and
+        # the diversity term (:627-638) go to the side stream (behind the gate MLPs) while layers 2.. run here
         h = xr
         ms, hs = [], []
-        for (w, b) in gcn_p:
+        v_pooled = v_arg = v_hmax = None
+        xy = torch.zeros((), dtype=torch.float32, device=x.device)
+        for l, (w, b) in enumerate(gcn_p):
             m = ops.aggregate(h, graph, mode=0)
             wt = w_t[id(w)]                                                     # [out,in]: K-major B operand
             h = ops.linear(m, wt, b.detach().float().contiguous() if b is not None else None,
                            act=L.ACT_RELU if cfg["relu"] else L.ACT_NONE)
             ms.append(m)
             hs.append(h)
-        # ---- gated views of layer 1 and the diversity term (:627-638)
-        v_pooled = v_arg = v_hmax = None
-        xy = torch.zeros((), dtype=torch.float32, device=x.device)
-        if gated:
-            if _PATCH_VIEWS:
-                v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
-            else:
-                v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
-            if Lyr > 1:
-                xy = ops.diversity_fwd(v_pooled)
+            if l == 0 and gated:
+                with side.region():
+                    if _PATCH_VIEWS:
+                        v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
+                    else:
+                        v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
+                    if Lyr > 1:
+                        xy = ops.diversity_fwd(v_pooled)
+        side.join()                                # gates (and the views) are complete from here on
         # ---- output pooling (:639-640)
         gL = gates[Lyr - 1]
         pooled, p_arg = ops.pool_fwd(hs[-1], graph, gL.unsqueeze(0))
@@ -252,12 +300,78 @@ class _GatedStackFn(torch.autograd.Function):
                                    scores if need_scores else None, kl_b, g_kl, g_scores,
                                    gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
                                    want_dh=True, want_dv=False, dgate_out=dgates[Lyr - 1])
-        # ---- GCN chain backward (gcn.py:33-45)
         grads_out: List[Optional[torch.Tensor]] = [None] * ctx.n_params
+        gated = cfg["gated"]
+        o = 2 * Lyr
+
+        # ---- gate MLP backward (bert_amir5.py:562-571): needs the complete dgates, nothing else of the GCN chain
+        def gate_backward():
+            # the last Sigmoid of every gate in one launch (gates / dgates are [V*B, D] row blocks)
+            dz_all = ops.sigmoid_bwd(gates.view(Lyr * B, D), dgates.view(Lyr * B, D), cd)
+            da_g = None
+            if ctx.use_chain:
+                # d z chain of every gate in ONE launch, then every weight gradient in one batched launch
+                da_parts = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
+                dz_in = [[None] * pairs for _ in range(Lyr)]      # gradient at the pre-activation output of Linear i
+                stages = []
+                for g in range(Lyr):
+                    acts = ctx.gate_saved[g]
+                    dz_in[g][pairs - 1] = dz_all[g * B:(g + 1) * B]
+                    st = []
+                    for i in range(pairs - 1, -1, -1):
+                        wt = ctx.w_t[Lyr + g * pairs + i]                       # [in,out]: row n = input column n
+                        if i > 0:
+                            out = ops.alloc_rows(B, D, cd, dev)
+                            dz_in[g][i - 1] = out
+                            st.append(dict(w=wt, y=acts[i], out=out))
+                        else:
+                            st.append(dict(w=wt, y=acts[0] if lead else None, out=da_parts[g]))
+                    stages.append(st)
+                ops.mlp_chain(1, [dz_in[g][pairs - 1] for g in range(Lyr)], stages, B, D)
+                idx = [(g, i) for g in range(Lyr) for i in range(pairs)]
+                for c0 in range(0, len(idx), 8):
+                    part = idx[c0:c0 + 8]
+                    dWs, dbs = ops.wgrad_batch([dz_in[g][i] for g, i in part], [ctx.gate_saved[g][i] for g, i in part],
+                                               bias_of=1)
+                    for (g, i), dW, db in zip(part, dWs, dbs):
+                        w, b = params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]
+                        grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
+                        grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
+                return da_parts.sum(0) if Lyr > 1 else da_parts[0]
+            for g in range(Lyr):
+                acts = ctx.gate_saved[g]
+                dz = dz_all[g * B:(g + 1) * B]
+                for i in range(pairs - 1, -1, -1):
+                    w, b = params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]
+                    dW, db = ops.wgrad(dz, acts[i], bias_of=1)                  # [out,in], [out]
+                    grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
+                    grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
+                    wt = ctx.w_t[Lyr + g * pairs + i]                           # [in,out]
+                    if i > 0:
+                        ds = ops.linear(dz, wt, None)
+                        dz = ops.sigmoid_bwd(acts[i], ds, cd)
+                    elif lead:
+                        ds = ops.linear(dz, wt, None)
+                        if da_g is None:
+                            da_g = ops.sigmoid_bwd(acts[0], ds, torch.float32,
+                                                   out=torch.empty((B, D), dtype=torch.float32, device=dev))
+                        else:
+                            ops.sigmoid_bwd(acts[0], ds, torch.float32, out=da_g, accumulate=True)
+                    else:
+                        dlast = ops.linear(dz, wt, None, out_dtype=torch.float32)
+                        da_g = dlast if da_g is None else da_g + dlast
+            return da_g
+
+        # ---- GCN chain backward (gcn.py:33-45); the gate MLPs' backward runs on the side stream next to layer 1's
+        side = _Side(_OVERLAP and gated, dev)
+        da_gate = None
         for l in range(Lyr - 1, -1, -1):
             if l == 0 and views_active and not _PATCH_VIEWS:
                 # gated views of h_1 feed xy (:627-638): add their gradient before leaving layer 1
                 ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
+            if l == 0 and gated and not _PATCH_VIEWS:
+                with side.region():               # dgates are complete from here on
+                    da_gate = gate_backward()
             w, b = params[2 * l], params[2 * l + 1]
             if cfg["relu"]:
                 dh = ops.as_rows(dh * (hs[l] > 0), cd)
@@ -270,65 +384,12 @@ class _GatedStackFn(torch.autograd.Function):
                 patch = ops.views_patch(v_pooled, v_arg, gates, ctx.v_hmax, graph, g_xy, None, dgates, acc_view=Lyr - 1)
             dh = ops.aggregate(dm, graph, mode=1, patch=patch)
         dx = dh
-        # ---- gate MLP backward (bert_amir5.py:562-571)
-        # the last Sigmoid of every gate in one launch (gates / dgates are [V*B, D] row blocks)
-        gated = cfg["gated"]
-        dz_all = ops.sigmoid_bwd(gates.view(Lyr * B, D), dgates.view(Lyr * B, D), cd) if gated else None
-        da = ga_head.float().contiguous() if ga_head is not None else None
-        if da is not None and not da.is_contiguous():
-            da = da.contiguous()
-        o = 2 * Lyr
-        if ctx.use_chain:
-            # d z chain of every gate in ONE launch, then every weight gradient in one batched launch
-            da_parts = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
-            dz_in = [[None] * pairs for _ in range(Lyr)]      # gradient at the pre-activation output of Linear i
-            stages = []
-            for g in range(Lyr):
-                acts = ctx.gate_saved[g]
-                dz_in[g][pairs - 1] = dz_all[g * B:(g + 1) * B]
-                st = []
-                for i in range(pairs - 1, -1, -1):
-                    wt = ctx.w_t[Lyr + g * pairs + i]                           # [in,out]: row n = input column n
-                    if i > 0:
-                        out = ops.alloc_rows(B, D, cd, dev)
-                        dz_in[g][i - 1] = out
-                        st.append(dict(w=wt, y=acts[i], out=out))
-                    else:
-                        st.append(dict(w=wt, y=acts[0] if lead else None, out=da_parts[g]))
-                stages.append(st)
-            ops.mlp_chain(1, [dz_in[g][pairs - 1] for g in range(Lyr)], stages, B, D)
-            idx = [(g, i) for g in range(Lyr) for i in range(pairs)]
-            for c0 in range(0, len(idx), 8):
-                part = idx[c0:c0 + 8]
-                dWs, dbs = ops.wgrad_batch([dz_in[g][i] for g, i in part], [ctx.gate_saved[g][i] for g, i in part],
-                                           bias_of=1)
-                for (g, i), dW, db in zip(part, dWs, dbs):
-                    w, b = params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]
-                    grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
-                    grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
-            da_gate = da_parts.sum(0) if Lyr > 1 else da_parts[0]
+        if gated and _PATCH_VIEWS:
+            da_gate = gate_backward()
+        side.join()
+        da = ga_head.float() if ga_head is not None else None
+        if da_gate is not None:
             da = da_gate if da is None else da + da_gate
-        for g in range(Lyr if (gated and not ctx.use_chain) else 0):
-            acts = ctx.gate_saved[g]
-            dz = dz_all[g * B:(g + 1) * B]
-            for i in range(pairs - 1, -1, -1):
-                w, b = params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]
-                dW, db = ops.wgrad(dz, acts[i], bias_of=1)                      # [out,in], [out]
-                grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
-                grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
-                wt = ctx.w_t[Lyr + g * pairs + i]                               # [in,out]
-                if i > 0:
-                    ds = ops.linear(dz, wt, None)
-                    dz = ops.sigmoid_bwd(acts[i], ds, cd)
-                elif lead:
-                    ds = ops.linear(dz, wt, None)
-                    if da is None:
-                        da = ops.sigmoid_bwd(acts[0], ds, torch.float32, out=torch.empty((B, D), dtype=torch.float32, device=dev))
-                    else:
-                        ops.sigmoid_bwd(acts[0], ds, torch.float32, out=da, accumulate=True)
-                else:
-                    dlast = ops.linear(dz, wt, None, out_dtype=torch.float32)
-                    da = dlast if da is None else da + dlast
         if da is not None:
             ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
         grads_out[-2], grads_out[-1] = d_fcw, d_fcb

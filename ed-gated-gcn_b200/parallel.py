@@ -80,11 +80,8 @@ class GradientAllReducer:
         for work, flat, bucket in self._pending:
             work.wait()
             flat.mul_(1.0 / world)
-            off = 0
-            for p in bucket:
-                n = p.grad.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+            views = [v.view_as(p.grad) for v, p in zip(flat.split([p.grad.numel() for p in bucket]), bucket)]
+            torch._foreach_copy_([p.grad for p in bucket], views)        # one multi-tensor launch, not one per parameter
         self._pending = []
 
     def __call__(self) -> None:
