@@ -37,10 +37,7 @@ struct AggPatch { const int16_t* loc; const float* val; const int32_t* row_sent;
 // loc = sentence-local row index per (sentence, column) or -1, pitch ldp (multiple of 8): one 8- or 16-byte load
 // covers the thread's E columns
 template <int E>
-__device__ __forceinline__ void apply_patch(const AggPatch& p, int row, int c, float (&acc)[E]) {
-  const int b = __ldg(p.row_sent + row);
-  const int lr = row - __ldg(p.sent_ptr + b);
-  const int64_t o = (int64_t)b * p.ldp + c;
+__device__ __forceinline__ void apply_patch_at(const AggPatch& p, int64_t o, int lr, float (&acc)[E]) {
   uint32_t w[E / 2];
   if (E == 8) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.loc + o));
@@ -54,6 +51,11 @@ __device__ __forceinline__ void apply_patch(const AggPatch& p, int row, int c, f
     const int l = (int)(int16_t)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu));
     if (l == lr) acc[k] += __ldg(p.val + o + k);
   }
+}
+template <int E>
+__device__ __forceinline__ void apply_patch(const AggPatch& p, int row, int c, float (&acc)[E]) {
+  const int b = __ldg(p.row_sent + row);
+  apply_patch_at<E>(p, (int64_t)b * p.ldp + c, row - __ldg(p.sent_ptr + b), acc);
 }
 
 template <typename TI, typename TO, int MODE>
@@ -161,6 +163,8 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
   int32_t* rp_s = reinterpret_cast<int32_t*>(agg_smem + (size_t)cap_rows * pitch);   // [cap_rows + 1] (+3 pad)
   int32_t* col_s = rp_s + cap_rows + 4;                                             // [4 * cap_rows] tile-local ids
   float* inv_s = reinterpret_cast<float*>(col_s + 4 * cap_rows);                    // [cap_rows] 1/(deg+1)
+  int32_t* poff_s = reinterpret_cast<int32_t*>(inv_s + cap_rows);                   // [cap_rows] sentence * ldp   (patch)
+  int32_t* plr_s = poff_s + cap_rows;                                               // [cap_rows] row - sentence start
   const int cap_nnz = 4 * cap_rows;
   const uint32_t b32 = agg_smem_u32(&bar);
   if (tid == 0) {
@@ -196,6 +200,12 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
   if (fits)
     for (int i = tid; i < nnz; i += nthreads) col_s[i] = __ldg(col + e0 + i) - r0;
   for (int i = tid; i < n; i += nthreads) inv_s[i] = __frcp_rn((float)(rp_s[i + 1] - rp_s[i] + 1));
+  if (patch.loc)                                    // per staged row: where its sentence's patch entries start, and
+    for (int i = tid; i < n; i += nthreads) {       // its sentence-local index (two dependent loads, once per row)
+      const int b = __ldg(patch.row_sent + r0 + i);
+      poff_s[i] = b * patch.ldp;
+      plr_s[i] = r0 + i - __ldg(patch.sent_ptr + b);
+    }
   __syncthreads();
   {
     uint32_t ok = 0;
@@ -245,7 +255,7 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
 #pragma unroll
       for (int k = 0; k < E; ++k) acc[k] *= inv;
     }
-    if (patch.loc) apply_patch<E>(patch, r0 + lr, (int)threadIdx.x * E, acc);
+    if (patch.loc) apply_patch_at<E>(patch, (int64_t)poff_s[lr] + threadIdx.x * E, plr_s[lr], acc);
     store_chunk<TO, E>(yrow, acc);
   }
 }
@@ -268,13 +278,13 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
   const size_t pitch = (size_t)ldx * sizeof(TI);
   // staged variant: ~72 KB windows (3 blocks per SM); falls back to the flat kernel when a
   // sentence cannot fit next to a useful window
-  int cap_rows = (int)((72 * 1024) / (pitch + 24));
+  int cap_rows = (int)((72 * 1024) / (pitch + 32));
   int tile_rows = cap_rows - max_len + 1;
   int max_threads = 256;
   if (tile_rows < 16) {
     // long sentences (config 5: up to 200 tokens): one ~200 KB window per SM, so the block itself must bring
     // the warps that hide the shared-memory latency (256 threads alone reached 34 % of the HBM peak)
-    cap_rows = (int)((200 * 1024) / (pitch + 24));
+    cap_rows = (int)((200 * 1024) / (pitch + 32));
     tile_rows = cap_rows - max_len + 1;
     max_threads = 1024;
   }
@@ -289,7 +299,7 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
   int rpb = max_threads / chunks;
   if (rpb > 32) rpb = 32;
   dim3 block(chunks, rpb);
-  const size_t smem = (size_t)cap_rows * pitch + (size_t)(6 * cap_rows + 8) * sizeof(int32_t);
+  const size_t smem = (size_t)cap_rows * pitch + (size_t)(8 * cap_rows + 8) * sizeof(int32_t);
   const unsigned blocks = (unsigned)((N + tile_rows - 1) / tile_rows);
   auto k0 = aggregate_staged_kernel<TI, TO, 0>;
   auto k1 = aggregate_staged_kernel<TI, TO, 1>;

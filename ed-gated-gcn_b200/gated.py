@@ -265,6 +265,19 @@ class _GatedStackFn(torch.autograd.Function):
         if g_xout is not None:
             g_xout = ops.as_rows(g_xout, cd)
         need_scores = g_kl is not None or g_scores is not None
+        gated = cfg["gated"]
+        views_active = g_xy is not None and Lyr > 1 and gated
+        dgates = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
+        side = _Side(_OVERLAP and gated, dev)
+        patch = patch_ev = None
+        if views_active and _PATCH_VIEWS:
+            # the views' backward needs only forward tensors and d xy: it runs on the side stream from the very start
+            # (all of dgates; what goes to d h_1 comes back as patch arrays for the adjoint aggregation of layer 2)
+            with side.region():
+                patch = ops.views_patch(v_pooled, v_arg, gates, ctx.v_hmax, graph, g_xy, None, dgates, acc_view=-1)
+                if side.enabled:
+                    patch_ev = torch.cuda.Event()
+                    patch_ev.record(side.side)
         # ---- d v, d c: the per-unit gradients of the forward sweep times d kl, or (when scores itself carries
         # gradient) pass A over h_L
         fc_w, fc_b = params[-2], params[-1]
@@ -297,16 +310,15 @@ class _GatedStackFn(torch.autograd.Function):
         if gp_head is not None:
             gp_total = gp_head.float() if gp_total is None else gp_total + gp_head.float()
         # ---- pass B over h_L: dh_L, dgate_L
-        dgates = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
-        views_active = g_xy is not None and Lyr > 1 and cfg["gated"]
         if not views_active and Lyr > 1:
             dgates[:Lyr - 1].zero_()                                  # no diversity gradient: the other gates get none
+        early_gate = patch is not None        # dgates[L-1] already holds the views' share: head_bwd writes elsewhere
+        dgL = torch.empty((B, D), dtype=torch.float32, device=dev) if early_gate else dgates[Lyr - 1]
         dh, _, _, _ = ops.head_bwd(hL, graph, gL, v if need_scores else None, dist,
                                    scores if need_scores else None, kl_b, g_kl, g_scores,
                                    gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
-                                   want_dh=True, want_dv=False, dgate_out=dgates[Lyr - 1])
+                                   want_dh=True, want_dv=False, dgate_out=dgL)
         grads_out: List[Optional[torch.Tensor]] = [None] * ctx.n_params
-        gated = cfg["gated"]
         o = 2 * Lyr
 
         # ---- gate MLP backward (bert_amir5.py:562-571): needs the complete dgates, nothing else of the GCN chain
@@ -367,16 +379,19 @@ class _GatedStackFn(torch.autograd.Function):
                         da_g = dlast if da_g is None else da_g + dlast
             return da_g
 
-        # ---- GCN chain backward (gcn.py:33-45); the gate MLPs' backward runs on the side stream next to layer 1's
-        side = _Side(_OVERLAP and gated, dev)
+        # ---- GCN chain backward (gcn.py:33-45); the gate MLPs' backward runs on the side stream next to it
         # (opt-in) the weight gradient of a layer next to its input gradient: both start from dh
         side_w = _Side(_OVERLAP_WGRAD, dev, which=1)
         da_gate = None
+        if early_gate:
+            with side.region():                   # after head_bwd: dgates are complete
+                dgates[Lyr - 1].add_(dgL)
+                da_gate = gate_backward()
         for l in range(Lyr - 1, -1, -1):
             if l == 0 and views_active and not _PATCH_VIEWS:
                 # gated views of h_1 feed xy (:627-638): add their gradient before leaving layer 1
                 ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
-            if l == 0 and gated and not _PATCH_VIEWS:
+            if l == 0 and gated and not early_gate:
                 with side.region():               # dgates are complete from here on
                     da_gate = gate_backward()
             w, b = params[2 * l], params[2 * l + 1]
@@ -387,13 +402,10 @@ class _GatedStackFn(torch.autograd.Function):
                 grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db.to(b.dtype)
             wk = ctx.w_n[l]                                                     # [in,out] = B operand of dh W^T
             dm = ops.linear(dh, wk, None)
-            patch = None
-            if l == 1 and views_active and _PATCH_VIEWS:
-                patch = ops.views_patch(v_pooled, v_arg, gates, ctx.v_hmax, graph, g_xy, None, dgates, acc_view=Lyr - 1)
-            dh = ops.aggregate(dm, graph, mode=1, patch=patch)
+            if l == 1 and patch is not None and patch_ev is not None:
+                torch.cuda.current_stream(dev).wait_event(patch_ev)       # the patch arrays come from the side stream
+            dh = ops.aggregate(dm, graph, mode=1, patch=patch if l == 1 else None)
         dx = dh
-        if gated and _PATCH_VIEWS:
-            da_gate = gate_backward()
         side.join()
         side_w.join()
         da = ga_head.float() if ga_head is not None else None
