@@ -362,8 +362,14 @@ def run_b200(args):
         if top["bytes"]:
             achieved = top["bytes"] / (top["us_per_launch"] * 1e-6) / 1e9
         share = top["ms_per_step"] / sum(e["ms_per_step"] for e in ktable.values())
+        traffic = None                  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath)).get(top_key)
+            if t:
+                traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
         roof = {"bound": "hbm", "kernel": top_key, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": (achieved / peaks["hbm"]) if achieved else None, "traffic": None,
+                "frac": (achieved / peaks["hbm"]) if achieved else None, "traffic": traffic,
                 "peak_source": peaks["src"], "us_per_launch": top["us_per_launch"],
                 "launches_per_step": top["launches_per_step"], "share_of_kernel_time": share,
                 "algorithmic_bytes_per_launch": top["bytes"]}

@@ -57,6 +57,7 @@ SIGNATURES = {
     "edg_segment_mean_bwd": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _P, _L, _I, _P]),
     "edg_lr_pool_fwd": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _I, _P, _P, _P]),
     "edg_lr_pool_bwd": (c_int, [_P, _P, _I, _I, _P, c_int, _L, _P]),
+    "edg_dropout_rows": (c_int, [_P, c_int, _L, _P, _L, _I, _I, _P, _I, _F, c_int, _P]),
     "edg_gate_rows": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, c_int, _L, _P]),
     "edg_sigmoid_bwd": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, c_int, _L, c_int, _P]),
     "edg_sum_scaled": (c_int, [_P, _L, _F, _P, _P]),

@@ -228,3 +228,72 @@ extern "C" int edg_lr_pool_bwd(const float* g, const int32_t* arg, int32_t B, in
   else return EDG_ERR_DTYPE;
   return check_launch();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gate dropout (bert_amir5.py:624-625: `gate = self.dropout(gate)` on the gate BROADCAST to [B,T,D], i.e. an
+// independent keep/drop decision per (token, column), shared by every use of that gate).  Since
+// h * (gate * m * s) == (h * m * s) * gate, the per-token mask is applied to the ROWS once,
+//     y[t,d] (+)= x[t,d] * keep(t,d) / (1 - p),
+// and every kernel of the gated block then runs unchanged on the masked rows; the backward pass multiplies the row
+// gradient by the same mask, regenerated from the seed (nothing is stored).
+// keep(t,d) is a counter-based hash of (seed, stream, row, column) -- restated in tests with numpy, bit for bit.
+namespace edg {
+
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool dropout_keep(uint32_t key_lo, uint32_t key_hi, uint32_t row, uint32_t col, uint32_t thr) {
+  const uint32_t u = mix32(mix32(row * 0x9E3779B1U + key_lo) ^ (col * 0x85EBCA77U + key_hi));
+  return u >= thr;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_rows_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, int N, int D, int chunks,
+                    const int64_t* __restrict__ seed, uint32_t stream_id, uint32_t thr, float scale, int accumulate) {
+  constexpr int E = Vec16<T>::kElems;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = (int)(idx / chunks);
+  if (row >= N) return;
+  const int c = (int)(idx - (int64_t)row * chunks) * E;
+  const uint64_t sd = (uint64_t)__ldg(seed);
+  const uint32_t key_lo = (uint32_t)sd ^ (stream_id * 0xC2B2AE3DU), key_hi = (uint32_t)(sd >> 32);
+  float f[E], o[E];
+  Vec16<T>::load(x + (int64_t)row * ldx + c, f);
+  if (accumulate) Vec16<T>::load(y + (int64_t)row * ldy + c, o);
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    const float v = (c + k < D && dropout_keep(key_lo, key_hi, (uint32_t)row, (uint32_t)(c + k), thr)) ? f[k] * scale : 0.f;
+    o[k] = accumulate ? o[k] + v : v;
+  }
+  Vec16<T>::store(y + (int64_t)row * ldy + c, o);
+}
+
+}  // namespace edg
+
+extern "C" int edg_dropout_rows(const void* x, int dtype, int64_t ldx, void* y, int64_t ldy, int32_t N, int32_t D,
+                                const int64_t* seed, int32_t stream_id, float p, int accumulate, edg_stream stream) {
+  if (N < 0 || D <= 0 || !(p >= 0.f) || !(p < 1.f)) return EDG_ERR_ARG;
+  if (N == 0) return EDG_OK;
+  if (!x || !y || !seed || ldx < D || ldy < D) return EDG_ERR_ARG;
+  if (!edg::aligned16(x) || !edg::aligned16(y) || !edg::row_pitch_ok(dtype, ldx) || !edg::row_pitch_ok(dtype, ldy)) return EDG_ERR_ALIGN;
+  const int E = dtype == EDG_BF16 ? 8 : 4;
+  const int chunks = (D + E - 1) / E;
+  if ((int64_t)chunks * E > ldx || (int64_t)chunks * E > ldy) return EDG_ERR_ALIGN;
+  double t = (double)p * 4294967296.0;
+  const uint32_t thr = t >= 4294967295.0 ? 4294967295U : (uint32_t)t;
+  const float scale = 1.0f / (1.0f - p);
+  const int64_t total = (int64_t)N * chunks;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == EDG_F32)
+    edg::dropout_rows_kernel<float><<<grid, 256, 0, s>>>((const float*)x, ldx, (float*)y, ldy, N, D, chunks, seed, (uint32_t)stream_id,
+                                                         thr, scale, accumulate);
+  else if (dtype == EDG_BF16)
+    edg::dropout_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, N, D, chunks,
+                                                                 seed, (uint32_t)stream_id, thr, scale, accumulate);
+  else
+    return EDG_ERR_DTYPE;
+  return edg::check_launch();
+}

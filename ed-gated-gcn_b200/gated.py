@@ -146,6 +146,8 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.w_n = [casted[nW + i] for i in range(nW)]
         # ---- trigger vector and the gate MLPs (bert_amir5.py:615-622)
         gated = cfg["gated"]
+        drop_p, seed = (cfg["drop_p"], cfg["seed"]) if gated else (0.0, None)
+        h1m = None
         a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
         gate_saved = []
         if gated:
@@ -198,16 +200,25 @@ class _GatedStackFn(torch.autograd.Function):
             hs.append(h)
             if l == 0 and gated:
                 with side.region():
-                    if _PATCH_VIEWS:
+                    if drop_p > 0:
+                        # gate dropout (:624-625): view v sees h_1 under the per-token mask of gate v
+                        h1m = [ops.dropout_rows(hs[0], seed, v, drop_p) for v in range(Lyr)]
+                        v_pooled = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
+                        v_arg = torch.empty((Lyr, B, D), dtype=torch.int32, device=x.device)
+                        for v in range(Lyr):
+                            pv, av = ops.pool_fwd(h1m[v], graph, gates[v:v + 1])
+                            v_pooled[v], v_arg[v] = pv[0], av[0]
+                    elif _PATCH_VIEWS:
                         v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
                     else:
                         v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
                     if Lyr > 1:
                         xy = ops.diversity_fwd(v_pooled)
         side.join()                                # gates (and the views) are complete from here on
-        # ---- output pooling (:639-640)
+        # ---- output pooling (:639-640); under gate dropout x_out = gate_L * (h_L * mask_L / (1-p))
         gL = gates[Lyr - 1]
-        pooled, p_arg = ops.pool_fwd(hs[-1], graph, gL.unsqueeze(0))
+        hL = ops.dropout_rows(hs[-1], seed, Lyr - 1, drop_p) if drop_p > 0 else hs[-1]
+        pooled, p_arg = ops.pool_fwd(hL, graph, gL.unsqueeze(0))
         pooled, p_arg = pooled[0], p_arg[0]
         # ---- classifier head: logits_fn is the model's own dense head (host torch, :643); the per-sentence
         # operands of the collapsed scores, [v_b | va_b] = logits_b @ fc.weight and
@@ -221,9 +232,10 @@ class _GatedStackFn(torch.autograd.Function):
         v, c = ops.fc_head_fwd(lg, fcw32, fcb32, a_raw)
         # ---- importance scores and the softmax product (:645-648)
         # (also d kl/d v, d kl/d c per unit gradient: saves the backward pass one sweep over h_L)
-        scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hs[-1], graph, gL, v, c, dist, want_units=True)
+        scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hL, graph, gL, v, c, dist, want_units=True)
         ctx.kl_units = (dvu, dcu)
-        x_out = ops.gate_rows(hs[-1], graph, gL, cd) if cfg["return_x_out"] else None
+        x_out = ops.gate_rows(hL, graph, gL, cd) if cfg["return_x_out"] else None
+        ctx.drop = (drop_p, seed, h1m, hL) if drop_p > 0 else None
 
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not zero tensors
         ctx.cfg = cfg
@@ -256,7 +268,8 @@ class _GatedStackFn(torch.autograd.Function):
         dev = xr.device
         a_leaf, p_leaf, logits, lg, a_raw, v = ctx.head
         gL = gates[Lyr - 1]
-        hL = hs[-1]
+        drop = ctx.drop
+        hL = drop[3] if drop else hs[-1]          # under gate dropout the block ran on the masked rows of h_L
 
         def f32(t):
             return None if t is None else t.detach().float().contiguous()
@@ -270,7 +283,7 @@ class _GatedStackFn(torch.autograd.Function):
         dgates = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
         side = _Side(_OVERLAP and gated, dev)
         patch = patch_ev = None
-        if views_active and _PATCH_VIEWS:
+        if views_active and _PATCH_VIEWS and not drop:
             # the views' backward needs only forward tensors and d xy: it runs on the side stream from the very start
             # (all of dgates; what goes to d h_1 comes back as patch arrays for the adjoint aggregation of layer 2)
             with side.region():
@@ -318,6 +331,8 @@ class _GatedStackFn(torch.autograd.Function):
                                    scores if need_scores else None, kl_b, g_kl, g_scores,
                                    gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
                                    want_dh=True, want_dv=False, dgate_out=dgL)
+        if drop:
+            dh = ops.dropout_rows(dh, drop[1], Lyr - 1, drop[0])      # d h_L = d (h_L * mask / (1-p)) * mask / (1-p)
         grads_out: List[Optional[torch.Tensor]] = [None] * ctx.n_params
         o = 2 * Lyr
 
@@ -388,7 +403,15 @@ class _GatedStackFn(torch.autograd.Function):
                 dgates[Lyr - 1].add_(dgL)
                 da_gate = gate_backward()
         for l in range(Lyr - 1, -1, -1):
-            if l == 0 and views_active and not _PATCH_VIEWS:
+            if l == 0 and views_active and drop:
+                # every view pooled its own masked copy of h_1: route per view, then mask the row gradient again
+                dp = (g_xy / B) * (v_pooled.sum(0, keepdim=True) - v_pooled)              # d xy / d pooled_v  (:638)
+                for vi in range(Lyr):
+                    tmp = ops.alloc_rows(N, D, cd, dev, zero=True)
+                    ops.views_bwd(v_pooled[vi:vi + 1], v_arg[vi:vi + 1], gates[vi:vi + 1], drop[2][vi], None,
+                                  dp[vi:vi + 1].contiguous(), tmp, dgates[vi:vi + 1], acc_view=0 if vi == Lyr - 1 else -1)
+                    ops.dropout_rows(tmp, drop[1], vi, drop[0], out=dh, accumulate=True)
+            elif l == 0 and views_active and not _PATCH_VIEWS:
                 # gated views of h_1 feed xy (:627-638): add their gradient before leaving layer 1
                 ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
             if l == 0 and gated and not early_gate:
@@ -467,10 +490,13 @@ class GatedGCNStack(nn.Module):
         parameters ``logits_fn`` closes over (so their gradients are delivered)."""
         if not x.is_cuda:
             raise L.EdgError("GatedGCNStack runs on CUDA tensors only (there is no CPU path)")
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError(
-                "gate dropout p>0 in training mode is not implemented yet (bert_amir5.py:624-625 applies it to "
-                "the broadcast gate, per token); use dropout=0 or eval()")
+        drop_p, seed = 0.0, None
+        if self.training and self.dropout_p > 0 and self.gated:
+            # nn.Dropout on the broadcast gates (bert_amir5.py:624-625).  The seed is a DEVICE scalar drawn from
+            # torch's CUDA generator, so a captured CUDA graph draws a fresh mask on every replay.
+            drop_p = float(self.dropout_p)
+            seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=x.device)
+            self.last_dropout_seed = seed
         shape3 = None
         if x.dim() == 3:
             shape3 = x.shape
@@ -484,7 +510,8 @@ class GatedGCNStack(nn.Module):
             raise L.EdgError(f"expected {self.hidden} feature columns (or the padded pitch), got {x.shape[-1]}")
         cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
-                   head_params=list(head_params), relu=self.relu, return_x_out=return_x_out, gated=self.gated)
+                   head_params=list(head_params), relu=self.relu, return_x_out=return_x_out, gated=self.gated,
+                   drop_p=drop_p, seed=seed)
         logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params())
         if shape3 is not None:
             scores = scores.reshape(shape3[0], shape3[1])

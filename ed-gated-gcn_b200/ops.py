@@ -333,3 +333,15 @@ def sigmoid_bwd(y: torch.Tensor, dy: torch.Tensor, out_dtype: torch.dtype, out: 
     L.call("edg_sigmoid_bwd", L.ptr(y), L.dt(y), ld(y), L.ptr(dy), L.dt(dy), ld(dy), R, C, L.ptr(dz), L.dt(dz),
            ld(dz), int(accumulate), L.stream())
     return dz
+
+
+def dropout_rows(x: torch.Tensor, seed: torch.Tensor, stream_id: int, p: float, out: Optional[torch.Tensor] = None,
+                 accumulate: bool = False) -> torch.Tensor:
+    """``out (+)= x * keep / (1 - p)`` with the counter-based per-(row, column) mask of ``edg_dropout_rows``
+    (``seed`` = device int64 scalar)."""
+    N, D = x.shape
+    if out is None:
+        out = alloc_rows(N, D, x.dtype, x.device)
+    L.call("edg_dropout_rows", L.ptr(x), L.dt(x), ld(x), L.ptr(out), ld(out), N, D, L.ptr(seed), int(stream_id), float(p),
+           int(accumulate), L.stream())
+    return out

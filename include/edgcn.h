@@ -334,6 +334,16 @@ int edg_lr_pool_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_p
 int edg_lr_pool_bwd(const float* g, const int32_t* arg, int32_t B, int32_t D, void* dh, int dtype, int64_t lddh,
                     edg_stream stream);
 
+/* Gate dropout (bert_amir5.py:624-625: nn.Dropout on the gate broadcast to [B,T,D], so one keep/drop decision per
+ * (token, column), shared by every use of that gate).  h * (gate * m / (1-p)) == (h * m / (1-p)) * gate, so the mask
+ * is applied to the rows:  y[t,d] (+)= x[t,d] * keep(t,d) / (1-p)  and the kernels of the block run unchanged on y;
+ * the backward pass applies the same call to the row gradient.  keep(t,d) = mix32(mix32(t*0x9E3779B1 + klo) ^
+ * (d*0x85EBCA77 + khi)) >= floor(p * 2^32) with klo = lo32(seed) ^ (stream_id * 0xC2B2AE3D), khi = hi32(seed),
+ * mix32 = the lowbias32 finaliser (x ^= x>>16; x *= 0x7feb352d; x ^= x>>15; x *= 0x846ca68b; x ^= x>>16).
+ * seed: DEVICE int64 scalar (so a captured CUDA graph sees a new seed every replay).  x, y: same dtype. */
+int edg_dropout_rows(const void* x, int dtype, int64_t ldx, void* y, int64_t ldy, int32_t N, int32_t D,
+                     const int64_t* seed, int32_t stream_id, float p, int accumulate, edg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

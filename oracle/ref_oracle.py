@@ -222,7 +222,8 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
                     gate_params: Sequence[Sequence[Tuple[torch.Tensor, torch.Tensor]]],
                     fc_w: torch.Tensor, fc_b: torch.Tensor, logits_fn,
                     lead_sigmoid: bool = True, forced_view_arg: Optional[torch.Tensor] = None,
-                    forced_final_arg: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                    forced_final_arg: Optional[torch.Tensor] = None,
+                    gate_masks: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """The canonical block, bert_amir5.py:615-648, for ``L = len(gcn_params)``
     layers (the reference has L = 2: gc1, gc2).
 
@@ -241,6 +242,9 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
     resolution, and the gradient then flows elsewhere.  The bf16 tests therefore compare
     gradients against this oracle with the CUDA path's own routing, and separately check
     that every re-routed position is such a near-tie.
+
+    ``gate_masks`` (one [B,T,D] tensor per gate, entries 0 or 1/(1-p)) stand for ``gate = self.dropout(gate)`` on
+    the broadcast gates (:624-625) with the random draw made explicit; ``None`` = dropout p = 0 / eval mode.
     """
     B, T, D = x.shape
     L = len(gcn_params)
@@ -258,13 +262,15 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
             return torch.max(t, dim=1)[0]
         return torch.gather(t, 1, forced.long()[:, None, :])[:, 0, :]
 
-    views = [pool(h1 * g[:, None, :], None if forced_view_arg is None else forced_view_arg[i])
-             for i, g in enumerate(gates)]                            # :627-636
+    # :621-625 -- gates broadcast over the tokens (`.repeat(1,T).view`), then dropped per (token, column)
+    gb = [g[:, None, :].expand(B, T, D) * (1.0 if gate_masks is None else gate_masks[i]) for i, g in enumerate(gates)]
+    views = [pool(h1 * gb[i], None if forced_view_arg is None else forced_view_arg[i])
+             for i in range(L)]                                       # :627-636
     xy = x.new_zeros(())
     for i in range(L):
         for j in range(i + 1, L):
             xy = xy + (views[i] * views[j]).sum(1).mean()             # :638
-    x_out = gates[-1][:, None, :] * hs[-1]                            # :639
+    x_out = gb[-1] * hs[-1]                                           # :639 (the SAME dropped gate as the last view)
     pooled = pool(x_out, forced_final_arg)                            # :640
     logits = logits_fn(aspect, pooled)                                # :643
     cat = torch.cat([x_out, aspect[:, None, :].expand(B, T, D)], dim=2)

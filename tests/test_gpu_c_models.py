@@ -336,7 +336,114 @@ def test_ungated_ablation_matches_oracle():
             assert p.grad is None or float(p.grad.abs().max()) == 0.0
 
 
-def test_stack_rejects_cpu_and_training_dropout():
+def _dropout_mask_numpy(seed: int, stream_id: int, p: float, n_rows: int, D: int) -> np.ndarray:
+    """keep(t,d) / (1-p) of edg_dropout_rows, restated with numpy uint32 arithmetic (include/edgcn.h)."""
+    M = np.uint64(0xFFFFFFFF)
+
+    def mix32(x):
+        x = x & M
+        x ^= x >> np.uint64(16); x = (x * np.uint64(0x7feb352d)) & M
+        x ^= x >> np.uint64(15); x = (x * np.uint64(0x846ca68b)) & M
+        x ^= x >> np.uint64(16)
+        return x
+
+    klo = np.uint64((seed & 0xFFFFFFFF) ^ ((stream_id * 0xC2B2AE3D) & 0xFFFFFFFF))
+    khi = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    rows = np.arange(n_rows, dtype=np.uint64)[:, None]
+    cols = np.arange(D, dtype=np.uint64)[None, :]
+    u = mix32(mix32((rows * np.uint64(0x9E3779B1) + klo) & M) ^ ((cols * np.uint64(0x85EBCA77) + khi) & M))
+    thr = np.uint64(min(int(p * 4294967296.0), 4294967295))
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return np.where(u >= thr, scale, np.float32(0.0)).astype(np.float32)
+
+
+def test_dropout_rows_kernel_matches_the_numpy_restatement():
+    from ed_gated_gcn_b200 import ops
+    for dtype in DTYPES:
+        x = ops.as_rows(torch.randn(97, 44).to(DEV), dtype)
+        seed = torch.tensor([0x1234_5678_9ABC_DEF1 >> 1], dtype=torch.int64, device=DEV)
+        y = ops.dropout_rows(x, seed, 3, 0.25)
+        m = torch.from_numpy(_dropout_mask_numpy(int(seed), 3, 0.25, 97, 44))
+        want = (x.float().cpu() * m)
+        assert torch.equal(y.float().cpu(), want.to(dtype).float())
+        assert 0.68 < float((m > 0).float().mean()) < 0.82
+        base = y.as_strided((97, y.stride(0)), (y.stride(0), 1))
+        assert (base[:, 44:] == 0).all()
+        z = ops.dropout_rows(x, seed, 3, 0.25, out=y.clone(), accumulate=True)
+        assert rel(z.float().cpu(), 2 * want) < (1e-6 if dtype == torch.float32 else 8e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+@pytest.mark.parametrize("Lyr", [2, 3])
+def test_stack_training_mode_gate_dropout_vs_oracle(dtype, Lyr):
+    """Training mode with dropout p = 0.25 (the reference default, train.py:294): nn.Dropout on the broadcast
+    gates (bert_amir5.py:624-625).  The oracle gets the SAME masks, rebuilt with numpy from the seed the stack drew."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import synth
+    tol = tol_for(dtype)
+    torch.manual_seed(77 + Lyr)
+    batch = synth.make_batch(10, 2, 24, seed=50 + Lyr)
+    D, C, B, p = 40, 4, batch.n_graphs, 0.25
+    stack = E.GatedGCNStack(D, n_layers=Lyr, n_classes=C, compute_dtype=dtype, dropout=p).to(DEV).train()
+    gen = torch.Generator().manual_seed(8)
+    O.reference_init_([q for q in stack.parameters()], gen)
+    dense = torch.nn.Linear(2 * D, C).to(DEV)
+    graph = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=DEV)
+    anchor = torch.from_numpy(batch.anchor).to(DEV)
+    dist = E.tree_distance(graph, anchor)
+    xp = torch.randn(batch.n_rows, D, generator=gen)
+    targets = torch.arange(B) % C
+    x = xp.to(DEV).requires_grad_(True)
+    out = stack(x, graph, anchor, dist, lambda a, q: dense(torch.cat([a, q], 1)), head_params=list(dense.parameters()),
+                return_x_out=True)
+    loss = torch.nn.functional.cross_entropy(out.logits, targets.to(DEV)) + 0.01 * out.xy + 0.01 * out.kl
+    loss.backward()
+    seed = int(stack.last_dropout_seed)
+    masks = [torch.from_numpy(_dropout_mask_numpy(seed, v, p, batch.n_rows, D)) for v in range(Lyr)]
+    assert float((out.x_out == 0).float().mean()) > 0.15                  # dropped positions are really zero
+
+    def run_oracle(forced=None):
+        sd, dw, db, gcn_p, gate_p, lead = _oracle_params(stack, dense)
+        sp = batch.sent_ptr
+        xs, logits, scores, xouts, vv, fv = [], [], [], [], [], []
+        xy = kl = 0.0
+        for b, h in enumerate(batch.heads_list()):
+            lo, hi = int(sp[b]), int(sp[b + 1])
+            xb = xp[lo:hi].clone().requires_grad_(True)
+            adj = torch.from_numpy(O.dense_adjacency_from_heads(h, len(h))).float()
+            d = torch.tensor(O.tree_distance_bfs(h, int(batch.anchor[b])))
+            o = O.gated_block_ref(xb[None], adj[None], torch.tensor([int(batch.anchor[b])]), d[None], gcn_p, gate_p,
+                                  sd["fc.0.weight"], sd["fc.0.bias"], lambda a, q: torch.cat([a, q], 1) @ dw.t() + db,
+                                  lead_sigmoid=lead, gate_masks=[m[lo:hi][None] for m in masks],
+                                  forced_view_arg=None if forced is None else forced[1][:, b:b + 1],
+                                  forced_final_arg=None if forced is None else forced[0][b:b + 1])
+            xs.append(xb); logits.append(o["logits"]); scores.append(o["scores"][0]); xouts.append(o["x_out"][0])
+            vv.append([(o["hs"][0][0] * g[0][None, :] * masks[i][lo:hi]).detach() for i, g in enumerate(o["gates"])])
+            fv.append(o["x_out"][0].detach())
+            xy = xy + o["xy"] / B
+            kl = kl + o["kl"] / B
+        lg = torch.cat(logits)
+        ls = torch.nn.functional.cross_entropy(lg, targets) + 0.01 * xy + 0.01 * kl
+        ls.backward()
+        grads = {k: v.grad for k, v in sd.items()}
+        grads["dense.weight"], grads["dense.bias"] = dw.grad, db.grad
+        return dict(logits=lg, scores=scores, x_out=xouts, xy=xy, kl=kl, loss=ls, dx=[t.grad for t in xs], grads=grads,
+                    views_vals=vv, final_vals=fv)
+
+    ora = run_oracle()
+    assert rel(out.x_out, torch.cat(ora["x_out"])) < tol
+    ora_g = ora
+    if dtype == torch.bfloat16:
+        forced = _check_routing(out, ora, batch.sent_ptr[:-1], max_frac=0.2)   # many exact ties at the dropped zeros
+        ora_g = run_oracle(forced)
+    _compare(out, loss, x.grad, stack, dense, ora, ora_g, tol, Lyr)
+    # eval mode = no dropout
+    stack.eval()
+    out_e = stack(xp.to(DEV), graph, anchor, dist, lambda a, q: dense(torch.cat([a, q], 1)), return_x_out=True)
+    assert float((out_e.x_out == 0).float().mean()) < 0.01
+
+
+def test_stack_rejects_cpu_tensors():
     import ed_gated_gcn_b200 as E
     from ed_gated_gcn_b200._lib import EdgError
     stack = E.GatedGCNStack(8, 2, 2, dropout=0.25)
