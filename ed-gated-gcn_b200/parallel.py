@@ -70,16 +70,19 @@ class GradientAllReducer:
             return
         for bucket in self._buckets():
             flat = torch.cat([p.grad.reshape(-1).float() for p in bucket])
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._pending.append((work, flat, bucket))
+            # NCCL averages inside the collective; gloo (the CPU tests) only sums
+            avg = dist.get_backend(self.group) == "nccl"
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append((work, flat, bucket, avg))
 
     def wait(self) -> None:
         if not self._pending:
             return
         world = dist.get_world_size(self.group)
-        for work, flat, bucket in self._pending:
+        for work, flat, bucket, avg in self._pending:
             work.wait()
-            flat.mul_(1.0 / world)
+            if not avg:
+                flat.mul_(1.0 / world)
             views = [v.view_as(p.grad) for v, p in zip(flat.split([p.grad.numel() for p in bucket]), bucket)]
             torch._foreach_copy_([p.grad for p in bucket], views)        # one multi-tensor launch, not one per parameter
         self._pending = []
