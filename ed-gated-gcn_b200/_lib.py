@@ -59,6 +59,7 @@ SIGNATURES = {
     "edg_lr_pool_bwd": (c_int, [_P, _P, _I, _I, _P, c_int, _L, _P]),
     "edg_dropout_rows": (c_int, [_P, c_int, _L, _P, _L, _I, _I, _P, _I, _F, c_int, _P]),
     "edg_gate_rows": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, c_int, _L, _P]),
+    "edg_gate_rows_act": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, c_int, _L, c_int, _P]),
     "edg_sigmoid_bwd": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, c_int, _L, c_int, _P]),
     "edg_sum_scaled": (c_int, [_P, _L, _F, _P, _P]),
     "edg_colsum_workspace": (_Z, [_I, _I]),

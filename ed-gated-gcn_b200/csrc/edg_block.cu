@@ -408,7 +408,7 @@ head_bwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict_
 template <typename T, typename TO>
 __global__ void __launch_bounds__(128)
 gate_rows_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr, int B, int D, int chunks,
-                 const float* __restrict__ gate, TO* __restrict__ out, int64_t ldo) {
+                 const float* __restrict__ gate, TO* __restrict__ out, int64_t ldo, int act) {
   constexpr int E = Vec16<T>::kElems;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = (int)(idx / chunks);
@@ -422,7 +422,10 @@ gate_rows_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict
     Vec16<T>::load(h + (int64_t)t * ldh + c, f);
 #pragma unroll
     for (int k = 0; k < E; ++k)
-      if (c + k < D) out[(int64_t)t * ldo + c + k] = from_f32<TO>(f[k] * g[k]);
+      if (c + k < D) {
+        const float v = f[k] * g[k];
+        out[(int64_t)t * ldo + c + k] = from_f32<TO>(act == EDG_ACT_SIGMOID ? sigmoidf_(v) : v);
+      }
   }
 }
 
@@ -679,10 +682,10 @@ extern "C" int edg_head_bwd(const void* h, int dtype, int64_t ldh, const int32_t
   return check_launch();
 }
 
-extern "C" int edg_gate_rows(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
-                             int32_t D, const float* gate, void* out, int out_dtype, int64_t ldo,
-                             edg_stream stream) {
-  if (B < 0 || D <= 0) return EDG_ERR_ARG;
+static int gate_rows_entry(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
+                           int32_t D, const float* gate, void* out, int out_dtype, int64_t ldo, int act,
+                           edg_stream stream) {
+  if (B < 0 || D <= 0 || (act != EDG_ACT_NONE && act != EDG_ACT_SIGMOID)) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
   if (!h || !sent_ptr || !gate || !out) return EDG_ERR_ARG;
   if (!aligned16(h) || !row_pitch_ok(dtype, ldh)) return EDG_ERR_ALIGN;
@@ -691,11 +694,23 @@ extern "C" int edg_gate_rows(const void* h, int dtype, int64_t ldh, const int32_
     constexpr int E = Vec16<T>::kElems;
     const int chunks = (D + E - 1) / E;
     const unsigned blocks = blocks_for((int64_t)B * chunks, 128);
-    if (out_dtype == EDG_F32) gate_rows_kernel<T, float><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, (float*)out, ldo);
-    else if (out_dtype == EDG_BF16) gate_rows_kernel<T, __nv_bfloat16><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, (__nv_bfloat16*)out, ldo);
+    if (out_dtype == EDG_F32) gate_rows_kernel<T, float><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, (float*)out, ldo, act);
+    else if (out_dtype == EDG_BF16) gate_rows_kernel<T, __nv_bfloat16><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, (__nv_bfloat16*)out, ldo, act);
     else return EDG_ERR_DTYPE;
   })
   return check_launch();
+}
+
+extern "C" int edg_gate_rows(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
+                             int32_t D, const float* gate, void* out, int out_dtype, int64_t ldo,
+                             edg_stream stream) {
+  return gate_rows_entry(h, dtype, ldh, sent_ptr, B, D, gate, out, out_dtype, ldo, EDG_ACT_NONE, stream);
+}
+
+extern "C" int edg_gate_rows_act(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
+                                 int32_t D, const float* gate, void* out, int out_dtype, int64_t ldo, int act,
+                                 edg_stream stream) {
+  return gate_rows_entry(h, dtype, ldh, sent_ptr, B, D, gate, out, out_dtype, ldo, act, stream);
 }
 
 extern "C" int edg_sigmoid_bwd(const void* y, int y_dtype, int64_t ldy, const void* dy, int dy_dtype,

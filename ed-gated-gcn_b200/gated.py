@@ -229,10 +229,21 @@ class _GatedStackFn(torch.autograd.Function):
             logits = logits_fn(a_leaf, p_leaf)
         lg = logits.detach().float().contiguous()
         fcw32, fcb32 = fc_w.detach().float().contiguous(), fc_b.detach().float().contiguous()
-        v, c = ops.fc_head_fwd(lg, fcw32, fcb32, a_raw)
+        fc_sig = cfg["fc_sigmoid"]
+        # BertAmir54: fc = Sequential(Sigmoid, Linear) (:464-465): the scores read z = sigmoid(x_out) (materialised
+        # rows, unit gate) and sigmoid(a); everything downstream is the same kernels
+        a_fc = torch.sigmoid(a_raw) if fc_sig else a_raw
+        v, c = ops.fc_head_fwd(lg, fcw32, fcb32, a_fc)
         # ---- importance scores and the softmax product (:645-648)
         # (also d kl/d v, d kl/d c per unit gradient: saves the backward pass one sweep over h_L)
-        scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hL, graph, gL, v, c, dist, want_units=True)
+        if fc_sig:
+            z = ops.gate_rows(hL, graph, gL, cd, act=L.ACT_SIGMOID)
+            ones = torch.ones((B, D), dtype=torch.float32, device=x.device)
+            scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(z, graph, ones, v, c, dist, want_units=True)
+            ctx.fc_sig = (z, ones, a_fc)
+        else:
+            scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hL, graph, gL, v, c, dist, want_units=True)
+            ctx.fc_sig = None
         ctx.kl_units = (dvu, dcu)
         x_out = ops.gate_rows(hL, graph, gL, cd) if cfg["return_x_out"] else None
         ctx.drop = (drop_p, seed, h1m, hL) if drop_p > 0 else None
@@ -300,12 +311,16 @@ class _GatedStackFn(torch.autograd.Function):
             if g_scores is None:
                 dv_in, dc_in, scale = ctx.kl_units[0], ctx.kl_units[1], g_kl
             else:
-                _, _, dv_in, dc_in = ops.head_bwd(hL, graph, gL, v, dist, scores, kl_b, g_kl, g_scores,
+                rows_s, gate_s = (ctx.fc_sig[0], ctx.fc_sig[1]) if ctx.fc_sig else (hL, gL)
+                _, _, dv_in, dc_in = ops.head_bwd(rows_s, graph, gate_s, v, dist, scores, kl_b, g_kl, g_scores,
                                                   None, None, None, want_dh=False, want_dv=True)
                 scale = None
             # backward of [v | va] = logits @ fc.weight, c = a . va + logits . fc.bias  (one kernel + a reduction)
+            a_fc = ctx.fc_sig[2] if ctx.fc_sig else a_raw
             d_lg, da_fc, d_fcw, d_fcb = ops.fc_head_bwd(lg, fc_w.detach().float().contiguous(),
-                                                        fc_b.detach().float().contiguous(), a_raw, dv_in, dc_in, scale)
+                                                        fc_b.detach().float().contiguous(), a_fc, dv_in, dc_in, scale)
+            if ctx.fc_sig:
+                da_fc = da_fc * a_fc * (1.0 - a_fc)                   # through sigmoid(a)
             d_fcw, d_fcb = d_fcw.to(fc_w.dtype), d_fcb.to(fc_b.dtype)
             g_lg = d_lg if g_lg is None else g_lg + d_lg
         # ---- host head backward through logits_fn: d a, d pooled, and .grad of the parameters it closes over
@@ -327,10 +342,22 @@ class _GatedStackFn(torch.autograd.Function):
             dgates[:Lyr - 1].zero_()                                  # no diversity gradient: the other gates get none
         early_gate = patch is not None        # dgates[L-1] already holds the views' share: head_bwd writes elsewhere
         dgL = torch.empty((B, D), dtype=torch.float32, device=dev) if early_gate else dgates[Lyr - 1]
-        dh, _, _, _ = ops.head_bwd(hL, graph, gL, v if need_scores else None, dist,
-                                   scores if need_scores else None, kl_b, g_kl, g_scores,
-                                   gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
-                                   want_dh=True, want_dv=False, dgate_out=dgL)
+        if ctx.fc_sig and need_scores:
+            # scores branch on z = sigmoid(x_out): d z (unit gate), through the sigmoid, then into the x_out path
+            z, ones, _ = ctx.fc_sig
+            dz, _, _, _ = ops.head_bwd(z, graph, ones, v, dist, scores, kl_b, g_kl, g_scores, None, None, None,
+                                       want_dh=True, want_dv=False)
+            dxo = ops.sigmoid_bwd(z, dz, cd)
+            if g_xout is not None:
+                dxo = ops.as_rows(dxo + g_xout, cd)
+            dh, _, _, _ = ops.head_bwd(hL, graph, gL, None, dist, None, kl_b, None, None,
+                                       gp_total.contiguous() if gp_total is not None else None, p_arg, dxo,
+                                       want_dh=True, want_dv=False, dgate_out=dgL)
+        else:
+            dh, _, _, _ = ops.head_bwd(hL, graph, gL, v if need_scores else None, dist,
+                                       scores if need_scores else None, kl_b, g_kl, g_scores,
+                                       gp_total.contiguous() if gp_total is not None else None, p_arg, g_xout,
+                                       want_dh=True, want_dv=False, dgate_out=dgL)
         if drop:
             dh = ops.dropout_rows(dh, drop[1], Lyr - 1, drop[0])      # d h_L = d (h_L * mask / (1-p)) * mask / (1-p)
         grads_out: List[Optional[torch.Tensor]] = [None] * ctx.n_params
@@ -454,7 +481,8 @@ class GatedGCNStack(nn.Module):
     bert_amir5.py:559-572) and runs the whole block fused."""
 
     def __init__(self, hidden: int, n_layers: int = 2, n_classes: int = 2, gate_arch: str = "sig-2",
-                 relu: bool = False, dropout: float = 0.0, compute_dtype="f32", gated: bool = True):
+                 relu: bool = False, dropout: float = 0.0, compute_dtype="f32", gated: bool = True,
+                 fc_sigmoid: bool = False):
         super().__init__()
         if hidden % 4:
             raise ValueError("hidden size must be a multiple of 4 (16-byte fp32 rows)")
@@ -467,7 +495,11 @@ class GatedGCNStack(nn.Module):
         for l in range(1, n_layers + 1):
             setattr(self, f"gc{l}", GraphConvolution(hidden, hidden, None, compute_dtype=self.compute_dtype))
             setattr(self, f"gate{l}", make_gate(hidden, gate_arch))
-        self.fc = nn.Sequential(nn.Linear(2 * hidden, n_classes))        # bert_amir5.py:572
+        self.fc_sigmoid = fc_sigmoid
+        if fc_sigmoid:                                                   # BertAmir54, bert_amir5.py:464-465 (keys fc.1.*)
+            self.fc = nn.Sequential(nn.Sigmoid(), nn.Linear(2 * hidden, n_classes))
+        else:
+            self.fc = nn.Sequential(nn.Linear(2 * hidden, n_classes))    # bert_amir5.py:572
 
     def _flat_params(self) -> List[torch.Tensor]:
         ps: List[torch.Tensor] = []
@@ -478,7 +510,7 @@ class GatedGCNStack(nn.Module):
             for m in getattr(self, f"gate{l}"):
                 if isinstance(m, nn.Linear):
                     ps += [m.weight, m.bias]
-        ps += [self.fc[0].weight, self.fc[0].bias]
+        ps += [self.fc[-1].weight, self.fc[-1].bias]
         return ps
 
     def forward(self, x: torch.Tensor, graph: DepGraph, anchor_index: torch.Tensor, dist_to_target: torch.Tensor,
@@ -511,7 +543,7 @@ class GatedGCNStack(nn.Module):
         cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
                    head_params=list(head_params), relu=self.relu, return_x_out=return_x_out, gated=self.gated,
-                   drop_p=drop_p, seed=seed)
+                   drop_p=drop_p, seed=seed, fc_sigmoid=self.fc_sigmoid)
         logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params())
         if shape3 is not None:
             scores = scores.reshape(shape3[0], shape3[1])

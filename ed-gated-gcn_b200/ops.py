@@ -317,11 +317,12 @@ def head_bwd(h, graph, gate, v, dist, scores, kl_b, g_kl, g_scores, g_pooled, ar
     return dh, dgate, dv, dc
 
 
-def gate_rows(h, graph, gate, out_dtype):
+def gate_rows(h, graph, gate, out_dtype, act: int = L.ACT_NONE):
+    """``act(gate[b] * h[t])`` per row (act = none or sigmoid); padding columns zero."""
     B, D = gate.shape
-    out = alloc_rows(h.shape[0], D, out_dtype, h.device)
-    L.call("edg_gate_rows", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(out),
-           L.dt(out), ld(out), L.stream())
+    out = alloc_rows(h.shape[0], D, out_dtype, h.device, zero=True)
+    L.call("edg_gate_rows_act", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(out),
+           L.dt(out), ld(out), int(act), L.stream())
     return out
 
 

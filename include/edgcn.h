@@ -294,6 +294,13 @@ int edg_gate_rows(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr
                   int32_t D, const float* gate, void* out, int out_dtype, int64_t ldo,
                   edg_stream stream);
 
+/* out[i,:] = act(gate[b(i),:]*h[i,:]), act = EDG_ACT_NONE or EDG_ACT_SIGMOID: the rows BertAmir54's
+ * `fc = Sequential(Sigmoid, Linear)` (bert_amir5.py:464-465) scores, z = sigmoid(x_out).  Padding columns of `out`
+ * are not written (allocate them zeroed). */
+int edg_gate_rows_act(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
+                      int32_t D, const float* gate, void* out, int out_dtype, int64_t ldo, int act,
+                      edg_stream stream);
+
 /* elementwise helper of the gate MLP backward: dz (+)= dy*y*(1-y) (nn.Sigmoid); writes the whole
  * [R, lddz] allocation (padding columns = 0). */
 int edg_sigmoid_bwd(const void* y, int y_dtype, int64_t ldy, const void* dy, int dy_dtype,

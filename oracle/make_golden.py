@@ -139,10 +139,13 @@ def golden_tree_dist(get_dist_to_target) -> None:
     print("tree_dist_cycle.npz", d)
 
 
-def golden_block55(BertAmir55) -> None:
+def golden_block55(BertAmir55, fname: str = "block55.npz", seed: int = 55) -> None:
+    """Also used for BertAmir54 (``block54.npz``): same inputs / hooks, the class differs in ``fc`` (a Sigmoid in
+    front of the Linear, bert_amir5.py:464-465) and in the ``dense`` head (two Linears over cat[aspect, out,
+    pooled_output], :443-446, :536)."""
     from ed_gated_gcn_b200 import synth
     from oracle import ref_oracle as O
-    torch.manual_seed(55)
+    torch.manual_seed(seed)
     B, ORI_ML, BERT_ML, C = 6, 20, 24, 5
     batch = synth.make_batch(B, 4, 14, seed=55)
     T = int(batch.lengths.max())
@@ -216,6 +219,7 @@ def golden_block55(BertAmir55) -> None:
         "x": cap["x"].detach().numpy(), "dx": cap["x"].grad.numpy(),
         "adj": adj[:, :T, :T], "dist": np.asarray(dist, dtype=np.int64)[:, :T],
         "anchor_rep": cap["dense_in"].detach().numpy()[:, :768 * 12],
+        "dense_in": cap["dense_in"].detach().numpy(),
         "h1": cap["h1"].detach().numpy(), "h2": cap["h2"].detach().numpy(),
         "g1": cap["g1"].detach().numpy(), "g2": cap["g2"].detach().numpy(),
         "logits": logits.detach().numpy(), "xy": xy.detach().numpy(), "kl": kl.detach().numpy(),
@@ -225,9 +229,14 @@ def golden_block55(BertAmir55) -> None:
     for n, p in model.named_parameters():
         if n.startswith(keep):
             out["p_" + n] = p.detach().numpy()
-            out["g_" + n] = p.grad.numpy()
-    np.savez_compressed(os.path.join(GOLD, "block55.npz"), **out)
-    print("block55.npz", {k: v.shape for k, v in out.items() if k[:2] not in ("p_", "g_")})
+            if p.numel() < 500_000:                                    # BertAmir54's dense.0.weight is 768 x 1280: keep the
+                out["g_" + n] = p.grad.numpy()                         # fixture small, its bias gradient pins that layer
+    if fname != "block55.npz":
+        out.pop("anchor_rep")
+    else:
+        out.pop("dense_in")                                            # block55.npz keeps its committed layout
+    np.savez_compressed(os.path.join(GOLD, fname), **out)
+    print(fname, {k: v.shape for k, v in out.items() if k[:2] not in ("p_", "g_")})
 
 
 def golden_bertdm(BertDM) -> None:
@@ -279,6 +288,8 @@ def main() -> None:
     golden_gcn_layer(GraphConvolution)
     golden_tree_dist(data_utils.get_dist_to_target)
     golden_block55(BertAmir55)
+    from models.bert_amir5 import BertAmir54           # reference, unmodified
+    golden_block55(BertAmir54, "block54.npz", seed=54)
     from models.bertdm import BertDM                   # reference, unmodified
     golden_bertdm(BertDM)
 

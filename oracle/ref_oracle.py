@@ -223,7 +223,8 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
                     fc_w: torch.Tensor, fc_b: torch.Tensor, logits_fn,
                     lead_sigmoid: bool = True, forced_view_arg: Optional[torch.Tensor] = None,
                     forced_final_arg: Optional[torch.Tensor] = None,
-                    gate_masks: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                    gate_masks: Optional[Sequence[torch.Tensor]] = None,
+                    fc_sigmoid: bool = False) -> Dict[str, torch.Tensor]:
     """The canonical block, bert_amir5.py:615-648, for ``L = len(gcn_params)``
     layers (the reference has L = 2: gc1, gc2).
 
@@ -245,6 +246,8 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
 
     ``gate_masks`` (one [B,T,D] tensor per gate, entries 0 or 1/(1-p)) stand for ``gate = self.dropout(gate)`` on
     the broadcast gates (:624-625) with the random draw made explicit; ``None`` = dropout p = 0 / eval mode.
+
+    ``fc_sigmoid`` = BertAmir54, whose ``fc`` is ``Sequential(Sigmoid, Linear)`` (:464-465, applied at :538).
     """
     B, T, D = x.shape
     L = len(gcn_params)
@@ -274,7 +277,7 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
     pooled = pool(x_out, forced_final_arg)                            # :640
     logits = logits_fn(aspect, pooled)                                # :643
     cat = torch.cat([x_out, aspect[:, None, :].expand(B, T, D)], dim=2)
-    output_w = cat @ fc_w.t() + fc_b                                  # :645
+    output_w = (torch.sigmoid(cat) if fc_sigmoid else cat) @ fc_w.t() + fc_b      # :645 (:538 for BertAmir54)
     scores = (logits[:, None, :] * output_w).sum(2)                   # :646
     kl = (torch.softmax(scores, 1) * torch.softmax(dist.to(x.dtype), 1)).sum(1).mean()   # :648
     return {"aspect": aspect, "gates": gates, "hs": hs, "views": views, "xy": xy,

@@ -286,6 +286,44 @@ def test_stack_packed_rows_vs_oracle(dtype, cfg):
     _compare(out, loss, x.grad, stack, dense, ora, ora_g, tol, Lyr)
 
 
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+def test_bert_amir54_variant_matches_full_reference_forward_backward(dtype):
+    """BertAmir54.forward + backward as run by the reference (golden block54): fc = Sequential(Sigmoid, Linear)
+    (bert_amir5.py:464-465), dense = two Linears over cat[aspect, out, pooled_output] (:443-446, :536)."""
+    import ed_gated_gcn_b200 as E
+    z = np.load(os.path.join(GOLDEN, "block54.npz"))
+    tol = tol_for(dtype)
+    C, D2 = z["p_fc.1.weight"].shape
+    D = D2 // 2
+    stack = E.GatedGCNStack(D, n_layers=2, n_classes=C, gate_arch="sig-2", compute_dtype=dtype, fc_sigmoid=True).to(DEV)
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p_") and not k.startswith("p_dense.")}
+    stack.load_state_dict(sd)                                         # keys of BertAmir54 incl. fc.1.*
+    dense = torch.nn.Sequential(torch.nn.Linear(2 * D + 768, 768), torch.nn.Linear(768, C)).to(DEV)
+    dense.load_state_dict({k[len("p_dense."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p_dense.")})
+    x = torch.from_numpy(z["x"]).to(DEV).requires_grad_(True)
+    adj = torch.from_numpy(z["adj"]).to(DEV)
+    anchor = torch.from_numpy(z["anchor"]).to(DEV)
+    dist = torch.from_numpy(z["dist"]).to(DEV)
+    pooled_output = torch.from_numpy(z["dense_in"][:, 2 * D:]).to(DEV)
+    targets = torch.from_numpy(z["targets"])
+    graph = E.graph_from_dense(adj)
+    out = stack(x, graph, anchor, dist, lambda a, p: dense(torch.cat([a, p, pooled_output], dim=1)),
+                head_params=list(dense.parameters()))
+    loss = torch.nn.functional.cross_entropy(out.logits, targets.to(DEV)) + 0.01 * out.xy + 0.01 * out.kl
+    loss.backward()
+    for k in ("logits", "scores", "xy", "kl"):
+        assert rel(getattr(out, k), z[k]) < tol, k
+    assert rel(loss, z["loss"]) < tol
+    if dtype == torch.float32:
+        assert rel(x.grad, z["dx"]) < tol
+        got = dict(stack.named_parameters())
+        got.update({"dense." + n: p for n, p in dense.named_parameters()})
+        for k in z.files:
+            if k.startswith("g_") and k != "g_fc.1.bias":
+                # fc.1.weight: a ~1e-6 gradient whose aspect half cancels inside the softmax (rounding noise)
+                assert rel(got[k[2:]].grad, z[k]) < (2e-3 if k == "g_fc.1.weight" else tol), k
+
+
 def test_ungated_ablation_matches_oracle():
     """gated=False = BertAmir55NoGate (bert_amir5.py:654-760): same kernels with a unit gate, xy = 0.0, gate
     parameters present in the state dict (the reference constructs them, :672-681) but untouched by backward."""

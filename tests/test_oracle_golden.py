@@ -129,3 +129,39 @@ def test_bertdm_block_matches_reference_fixture(golden_dir):
     for b in range(transform.shape[0]):
         nz = (transform[b] != 0)
         assert nz.sum(1)[: int(lengths[b])].min() >= 1 and nz[int(lengths[b]):].sum() == 0
+
+
+def test_block54_matches_full_reference_forward_backward():
+    """BertAmir54 (fc = Sequential(Sigmoid, Linear), bert_amir5.py:464-465; two-layer dense head over
+    cat[aspect, out, pooled_output], :443-446, :536) against the fixture produced by the reference's own forward."""
+    z = np.load(os.path.join(GOLDEN, "block54.npz"))
+    P = {k[2:]: torch.tensor(z[k], requires_grad=True) for k in z.files if k.startswith("p_")}
+    x = torch.tensor(z["x"], requires_grad=True)
+    D = x.shape[-1]
+    pooled_output = torch.tensor(z["dense_in"][:, 2 * D:])
+
+    def logits_fn(aspect, pooled):          # bert_amir5.py:536
+        h = torch.cat([aspect, pooled, pooled_output], dim=1) @ P["dense.0.weight"].t() + P["dense.0.bias"]
+        return h @ P["dense.1.weight"].t() + P["dense.1.bias"]
+
+    out = O.gated_block_ref(
+        x, torch.tensor(z["adj"]), torch.tensor(z["anchor"], dtype=torch.long), torch.tensor(z["dist"]),
+        [(P["gc1.weight"], P["gc1.bias"]), (P["gc2.weight"], P["gc2.bias"])],
+        [[(P["gate1.1.weight"], P["gate1.1.bias"]), (P["gate1.3.weight"], P["gate1.3.bias"])],
+         [(P["gate2.1.weight"], P["gate2.1.bias"]), (P["gate2.3.weight"], P["gate2.3.bias"])]],
+        P["fc.1.weight"], P["fc.1.bias"], logits_fn, lead_sigmoid=True, fc_sigmoid=True)
+    loss = O.block_loss_ref(out, torch.tensor(z["targets"]))
+    loss.backward()
+    for k in ("logits", "scores", "xy", "kl"):
+        assert rel_err(out[k], z[k]) < 2e-6, k
+    assert rel_err(loss, z["loss"]) < 2e-6
+    assert rel_err(x.grad, z["dx"]) < 1e-5
+    for name, p in P.items():
+        if "g_" + name not in z.files or name == "fc.1.bias":
+            continue
+        if name == "fc.1.weight":
+            # behind the Sigmoid the importance term's gradient is ~1e-6 in magnitude (its aspect half cancels inside
+            # the softmax like the bias): summation-order noise of ~1e-11 is 1e-5 of that
+            assert rel_err(p.grad, z["g_" + name]) < 1e-4, name
+            continue
+        assert rel_err(p.grad, z["g_" + name]) < 1e-5, name
