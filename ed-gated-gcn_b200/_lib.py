@@ -50,7 +50,7 @@ SIGNATURES = {
     "edg_scores_kl_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _I, _I, _P]),
     "edg_fc_head_fwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "edg_fc_head_bwd_workspace": (_Z, [_I, _I, _I]),
-    "edg_fc_head_bwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _P, _P, _P, _I, _I, _I, _P, _L, _P, _P, _L, _P, _P, _Z, _P]),
+    "edg_fc_head_bwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _P, _P, _P, _I, _I, _I, c_int, _P, _L, _P, _P, _L, _P, _P, _Z, _P]),
     "edg_head_bwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _L,
                              _P, _L, _P, _P, _P, _I, _P, _I, _P]),
     "edg_segment_mean": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _P, c_int, _L, _P]),

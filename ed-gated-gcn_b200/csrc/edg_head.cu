@@ -120,8 +120,10 @@ __global__ void __launch_bounds__(kHeadThreads, 2)
 fc_head_bwd_kernel(const float* __restrict__ lg, int64_t ldl, const float* __restrict__ W, int64_t ldw,
                    const float* __restrict__ fcb, const float* __restrict__ a, int64_t lda,
                    const float* __restrict__ dv, const float* __restrict__ dc, const float* __restrict__ scale,
-                   int B, int D, int C, int vec4, float* __restrict__ dlg_part, float* __restrict__ da,
+                   int B, int D, int C, int vec4, int parts, float* __restrict__ dlg_part, float* __restrict__ da,
                    float* __restrict__ partial) {
+  // parts: bit 0 = input gradients (d logits, d a), bit 1 = parameter-gradient partials (two launches on two
+  // streams keep the parameter gradients, which nothing downstream waits for, off the critical path)
   extern __shared__ __align__(16) float head_smem[];
   __shared__ __align__(16) float lg_t[CP][kHeadGraphs];                  // [class][sentence]
   __shared__ __align__(16) float lg_s[kHeadGraphs][CP];                  // [sentence][class]
@@ -148,7 +150,7 @@ fc_head_bwd_kernel(const float* __restrict__ lg, int64_t ldl, const float* __res
 
   for (int d0 = 0; d0 < D; d0 += kHeadPitch) {
     __syncthreads();                                                     // previous pass consumed, dc_s / lg_* written
-    stage_w_chunk<CP>(Ws, W, ldw, C, half * D + d0, (half + 1) * D, vec4 != 0);
+    if (parts & 1) stage_w_chunk<CP>(Ws, W, ldw, C, half * D + d0, (half + 1) * D, vec4 != 0);
     const int lim = min(kHeadPitch, D - d0);
     // u rows of the block for these columns: sc * dv (half 0) or dc * a (half 1); zero beyond `lim` / `nb`
     if (vec4) {
@@ -178,7 +180,7 @@ fc_head_bwd_kernel(const float* __restrict__ lg, int64_t ldl, const float* __res
       }
     }
     __syncthreads();
-    if (g0 < nb) {
+    if (g0 < nb && (parts & 1)) {
       // ---- d a (half 1): four sentences of the warp share every Wfc element
       if (half == 1) {
         for (int jj = lane; jj < lim; jj += 32) {
@@ -222,7 +224,7 @@ fc_head_bwd_kernel(const float* __restrict__ lg, int64_t ldl, const float* __res
       }
     }
     // ---- parameter-gradient partials of this block: thread = column of the pass
-    for (int jj = threadIdx.x; jj < lim; jj += kHeadThreads) {
+    for (int jj = threadIdx.x; (parts & 2) && jj < lim; jj += kHeadThreads) {
       float acc[CP];
 #pragma unroll
       for (int cc = 0; cc < CP; ++cc) acc[cc] = 0.f;
@@ -246,11 +248,11 @@ fc_head_bwd_kernel(const float* __restrict__ lg, int64_t ldl, const float* __res
   __syncthreads();
   // this half's part of d logits (+ the bias term once); bias-gradient partial (column 2D of the slab)
   float* dl = dlg_part + (int64_t)half * B * C;
-  for (int i = threadIdx.x; i < nb * C; i += kHeadThreads) {
+  for (int i = threadIdx.x; (parts & 1) && i < nb * C; i += kHeadThreads) {
     const int g = i / C, cc = i - g * C;
     dl[(int64_t)(b0 + g) * C + cc] = half == 0 ? fmaf(dc_s[g], __ldg(fcb + cc), dlg_s[g][cc]) : dlg_s[g][cc];
   }
-  if (half == 1 && threadIdx.x < C) {
+  if ((parts & 2) && half == 1 && threadIdx.x < C) {
     float t = 0.f;
     for (int g = 0; g < nb; ++g) t = fmaf(dc_s[g], lg_s[g][threadIdx.x], t);
     P[(int64_t)threadIdx.x * (W2 + 1) + W2] = t;
@@ -262,17 +264,18 @@ fc_head_bwd_kernel(const float* __restrict__ lg, int64_t ldl, const float* __res
 __global__ void __launch_bounds__(256)
 fc_head_reduce_kernel(const float* __restrict__ partial, int nblocks, int C, int W2, float* __restrict__ dW,
                       int64_t lddw, float* __restrict__ db, const float* __restrict__ dlg_part, int64_t BC,
-                      int B, float* __restrict__ dlg, int64_t lddl) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                      int B, float* __restrict__ dlg, int64_t lddl, int parts, unsigned first_block) {
+  const int64_t idx = (int64_t)(blockIdx.x + first_block) * blockDim.x + threadIdx.x;
   const int64_t per = (int64_t)C * (W2 + 1);
   if (idx < per) {
+    if (!(parts & 2)) return;
     const int cc = (int)(idx / (W2 + 1)), j = (int)(idx - (int64_t)cc * (W2 + 1));
     float s = 0.f;
 #pragma unroll 8
     for (int k = 0; k < nblocks; ++k) s += partial[k * per + idx];
     if (j < W2) dW[(int64_t)cc * lddw + j] = s;
     else db[cc] = s;
-  } else if (idx - per < BC) {
+  } else if (idx - per < BC && (parts & 1)) {
     const int64_t i = idx - per;
     const int64_t b = i / C;
     dlg[b * lddl + (i - b * C)] = dlg_part[i] + dlg_part[BC + i];
@@ -305,7 +308,9 @@ extern "C" int edg_fc_head_fwd(const float* logits, int64_t ldl, const float* fc
   return launch(fc_head_fwd_kernel<64>, 64);
 }
 
-// workspace: per-block parameter-gradient slabs + the two column-half parts of d logits
+// workspace: per-block parameter-gradient slabs + the two column-half parts of d logits (calls with parts = 1 and
+// parts = 2 may run concurrently on two streams: they touch disjoint regions, pass each its own workspace or the
+// same one)
 extern "C" size_t edg_fc_head_bwd_workspace(int32_t B, int32_t D, int32_t C) {
   if (B <= 0 || D <= 0 || C <= 0) return 16;
   const size_t blocks = (size_t)(B + kHeadGraphs - 1) / kHeadGraphs;
@@ -314,20 +319,24 @@ extern "C" size_t edg_fc_head_bwd_workspace(int32_t B, int32_t D, int32_t C) {
 
 extern "C" int edg_fc_head_bwd(const float* logits, int64_t ldl, const float* fc_w, int64_t ldw, const float* fc_b,
                                const float* a, int64_t lda, const float* dv, const float* dc, const float* scale,
-                               int32_t B, int32_t D, int32_t C, float* d_logits, int64_t lddl, float* d_a,
+                               int32_t B, int32_t D, int32_t C, int parts, float* d_logits, int64_t lddl, float* d_a,
                                float* d_fc_w, int64_t lddw, float* d_fc_b, void* ws, size_t ws_bytes,
                                edg_stream stream) {
-  if (B < 0 || D <= 0 || C <= 0) return EDG_ERR_ARG;
+  if (B < 0 || D <= 0 || C <= 0 || parts < 1 || parts > 3) return EDG_ERR_ARG;
   if (C > kHeadMaxC) return EDG_ERR_UNSUPPORTED;
-  if (!d_fc_w || !d_fc_b || lddw < 2 * D) return EDG_ERR_ARG;
+  const bool want_in = parts & 1, want_par = parts & 2;
+  if (want_par && (!d_fc_w || !d_fc_b || lddw < 2 * D)) return EDG_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (B == 0) {
-    cudaMemset2DAsync(d_fc_w, lddw * sizeof(float), 0, 2 * (size_t)D * sizeof(float), C, s);
-    cudaMemsetAsync(d_fc_b, 0, C * sizeof(float), s);
+    if (want_par) {
+      cudaMemset2DAsync(d_fc_w, lddw * sizeof(float), 0, 2 * (size_t)D * sizeof(float), C, s);
+      cudaMemsetAsync(d_fc_b, 0, C * sizeof(float), s);
+    }
     return check_launch();
   }
-  if (!logits || !fc_w || !fc_b || !a || !dv || !dc || !d_logits || !d_a || !ws) return EDG_ERR_ARG;
-  if (ldl < C || ldw < 2 * D || lda < D || lddl < C) return EDG_ERR_ARG;
+  if (!logits || !fc_w || !fc_b || !a || !dv || !dc || !ws) return EDG_ERR_ARG;
+  if (want_in && (!d_logits || !d_a || lddl < C)) return EDG_ERR_ARG;
+  if (ldl < C || ldw < 2 * D || lda < D) return EDG_ERR_ARG;
   if (ws_bytes < edg_fc_head_bwd_workspace(B, D, C)) return EDG_ERR_WORKSPACE;
   const int blocks = (B + kHeadGraphs - 1) / kHeadGraphs;
   float* partial = reinterpret_cast<float*>(ws);
@@ -336,7 +345,7 @@ extern "C" int edg_fc_head_bwd(const float* logits, int64_t ldl, const float* fc
   auto launch = [&](auto kern, int CP) -> int {
     const size_t smem = (size_t)(CP + kHeadGraphs) * kHeadPitch * sizeof(float);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
-    kern<<<dim3(blocks, 2), kHeadThreads, smem, s>>>(logits, ldl, fc_w, ldw, fc_b, a, lda, dv, dc, scale, B, D, C, vec4,
+    kern<<<dim3(blocks, 2), kHeadThreads, smem, s>>>(logits, ldl, fc_w, ldw, fc_b, a, lda, dv, dc, scale, B, D, C, vec4, parts,
                                                       dlg_part, d_a, partial);
     return check_launch();
   };
@@ -346,7 +355,10 @@ extern "C" int edg_fc_head_bwd(const float* logits, int64_t ldl, const float* fc
   else rc = launch(fc_head_bwd_kernel<64>, 64);
   if (rc) return rc;
   const int64_t per = (int64_t)C * (2 * D + 1), BC = (int64_t)B * C;
-  fc_head_reduce_kernel<<<(unsigned)((per + BC + 255) / 256), 256, 0, s>>>(partial, blocks, C, 2 * D, d_fc_w, lddw, d_fc_b,
-                                                                           dlg_part, BC, B, d_logits, lddl);
+  // parameter-gradient slabs first, the d logits halves after them: launch only the part of the grid that has work
+  const int64_t lo = want_par ? 0 : per, hi = want_in ? per + BC : per;
+  const unsigned first = (unsigned)(lo / 256), nblk = (unsigned)((hi + 255) / 256) - first;
+  fc_head_reduce_kernel<<<nblk, 256, 0, s>>>(partial, blocks, C, 2 * D, d_fc_w, lddw, d_fc_b, dlg_part, BC, B, d_logits, lddl,
+                                             parts, first);
   return check_launch();
 }

@@ -317,8 +317,10 @@ class _GatedStackFn(torch.autograd.Function):
                 scale = None
             # backward of [v | va] = logits @ fc.weight, c = a . va + logits . fc.bias  (one kernel + a reduction)
             a_fc = ctx.fc_sig[2] if ctx.fc_sig else a_raw
-            d_lg, da_fc, d_fcw, d_fcb = ops.fc_head_bwd(lg, fc_w.detach().float().contiguous(),
-                                                        fc_b.detach().float().contiguous(), a_fc, dv_in, dc_in, scale)
+            fcw32, fcb32 = fc_w.detach().float().contiguous(), fc_b.detach().float().contiguous()
+            d_lg, da_fc, _, _ = ops.fc_head_bwd(lg, fcw32, fcb32, a_fc, dv_in, dc_in, scale, parts=1)
+            with side.region():       # nothing downstream waits for the fc parameter gradients: side stream
+                _, _, d_fcw, d_fcb = ops.fc_head_bwd(lg, fcw32, fcb32, a_fc, dv_in, dc_in, scale, parts=2)
             if ctx.fc_sig:
                 da_fc = da_fc * a_fc * (1.0 - a_fc)                   # through sigmoid(a)
             d_fcw, d_fcb = d_fcw.to(fc_w.dtype), d_fcb.to(fc_b.dtype)

@@ -282,20 +282,20 @@ def fc_head_fwd(logits: torch.Tensor, fc_w: torch.Tensor, fc_b: torch.Tensor, a:
     return v, c
 
 
-def fc_head_bwd(logits, fc_w, fc_b, a, dv, dc, scale: Optional[torch.Tensor] = None):
-    """Backward of :func:`fc_head_fwd` -> d_logits [B,C], d_a [B,D], d_fc_w [C,2D], d_fc_b [C]
-    (``dv``/``dc`` are multiplied by the device scalar ``scale`` when given)."""
+def fc_head_bwd(logits, fc_w, fc_b, a, dv, dc, scale: Optional[torch.Tensor] = None, parts: int = 3):
+    """Backward of :func:`fc_head_fwd` -> d_logits [B,C], d_a [B,D] (``parts & 1``), d_fc_w [C,2D], d_fc_b [C]
+    (``parts & 2``); ``dv``/``dc`` are multiplied by the device scalar ``scale`` when given."""
     B, C = logits.shape
     D = a.shape[1]
     dev = a.device
-    d_lg = torch.empty((B, C), dtype=torch.float32, device=dev)
-    d_a = torch.empty((B, D), dtype=torch.float32, device=dev)
-    d_w = torch.empty((C, 2 * D), dtype=torch.float32, device=dev)
-    d_b = torch.empty((C,), dtype=torch.float32, device=dev)
+    d_lg = torch.empty((B, C), dtype=torch.float32, device=dev) if parts & 1 else None
+    d_a = torch.empty((B, D), dtype=torch.float32, device=dev) if parts & 1 else None
+    d_w = torch.empty((C, 2 * D), dtype=torch.float32, device=dev) if parts & 2 else None
+    d_b = torch.empty((C,), dtype=torch.float32, device=dev) if parts & 2 else None
     nbytes = L.load().edg_fc_head_bwd_workspace(B, D, C)
     ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
     L.call("edg_fc_head_bwd", L.ptr(logits), ld(logits), L.ptr(fc_w), ld(fc_w), L.ptr(fc_b), L.ptr(a), ld(a),
-           L.ptr(dv), L.ptr(dc), L.ptr(scale), B, D, C, L.ptr(d_lg), ld(d_lg), L.ptr(d_a), L.ptr(d_w), ld(d_w),
+           L.ptr(dv), L.ptr(dc), L.ptr(scale), B, D, C, int(parts), L.ptr(d_lg), C, L.ptr(d_a), L.ptr(d_w), 2 * D,
            L.ptr(d_b), L.ptr(ws), ws.numel() * 4, L.stream())
     return d_lg, d_a, d_w, d_b
 

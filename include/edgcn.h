@@ -261,14 +261,15 @@ int edg_fc_head_fwd(const float* logits, int64_t ldl, const float* fc_w, int64_t
 
 /* backward of edg_fc_head_fwd.  dv [B,D], dc [B] (both multiplied by the device scalar *scale when scale != NULL:
  * the per-unit gradients of edg_scores_kl_fwd times the upstream d kl):
- *   d_logits[b,:] = [dv_b | dc_b a_b] @ fc.weight^T + dc_b fc.bias        (overwritten, [B, lddl])
- *   d_a[b,:]      = dc_b va_b                                             (overwritten, [B, D])
- *   d_fc_w        = logits^T @ [dv | dc a],  d_fc_b = logits^T dc         (overwritten; fixed summation order)
- * ws: edg_fc_head_bwd_workspace() bytes. */
+ *   parts & 1:  d_logits[b,:] = [dv_b | dc_b a_b] @ fc.weight^T + dc_b fc.bias        (overwritten, [B, lddl])
+ *               d_a[b,:]      = dc_b va_b                                             (overwritten, [B, D])
+ *   parts & 2:  d_fc_w        = logits^T @ [dv | dc a],  d_fc_b = logits^T dc         (overwritten; fixed summation order)
+ * The two parts may be issued as two calls on two streams (nothing downstream waits for the parameter gradients);
+ * outputs of a part that is not requested may be NULL.  ws: edg_fc_head_bwd_workspace() bytes. */
 size_t edg_fc_head_bwd_workspace(int32_t B, int32_t D, int32_t C);
 int edg_fc_head_bwd(const float* logits, int64_t ldl, const float* fc_w, int64_t ldw, const float* fc_b,
                     const float* a, int64_t lda, const float* dv, const float* dc, const float* scale,
-                    int32_t B, int32_t D, int32_t C, float* d_logits, int64_t lddl, float* d_a,
+                    int32_t B, int32_t D, int32_t C, int parts, float* d_logits, int64_t lddl, float* d_a,
                     float* d_fc_w, int64_t lddw, float* d_fc_b, void* ws, size_t ws_bytes, edg_stream stream);
 
 /* backward of x_out = gate*h_L through scores/kl, the final max-pool and an

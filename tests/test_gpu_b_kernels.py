@@ -180,6 +180,12 @@ def test_fc_head_forward_backward(shape):
         got = ops.fc_head_bwd(lg.to(DEV), W.to(DEV), bfc.to(DEV), a.to(DEV), dv.to(DEV), dc.to(DEV), sc)
         for name, x, y in zip(["d_logits", "d_a", "d_fc_w", "d_fc_b"], got, want):
             assert rel(x, y) < 2e-6, (name, shape, scale)
+        # the two halves of the work as separate calls (input gradients / parameter gradients) give the same bits
+        g1 = ops.fc_head_bwd(lg.to(DEV), W.to(DEV), bfc.to(DEV), a.to(DEV), dv.to(DEV), dc.to(DEV), sc, parts=1)
+        g2 = ops.fc_head_bwd(lg.to(DEV), W.to(DEV), bfc.to(DEV), a.to(DEV), dv.to(DEV), dc.to(DEV), sc, parts=2)
+        assert g1[2] is None and g2[0] is None
+        assert torch.equal(g1[0], got[0]) and torch.equal(g1[1], got[1])
+        assert torch.equal(g2[2], got[2]) and torch.equal(g2[3], got[3])
 
 
 @pytest.mark.parametrize("D", [300, 256, 200, 64, 320])
