@@ -46,6 +46,7 @@ SIGNATURES = {
     "edg_pool_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P]),
     "edg_diversity_fwd": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "edg_views_bwd": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _L, _P, c_int, _P]),
+    "edg_views_bwd_parts": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _L, _P, c_int, c_int, _P]),
     "edg_views_patch": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, c_int, _P]),
     "edg_scores_kl_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _I, _I, _P]),
     "edg_fc_head_fwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _P, _P, _P]),

@@ -125,12 +125,15 @@ sum_scaled_kernel(const float* __restrict__ in, int64_t n, float scale, float* _
 }
 
 // ---- backward of the views + diversity ------------------------------------------
+// parts: bit 0 = add the views' gradient into dh (scattered read-modify-write), bit 1 = dgates (gathers h at the
+// arg-max rows).  The two halves have different consumers (layer 1's backward / the gate MLPs' backward), so the
+// caller may issue them as two launches on two streams.
 template <typename T>
 __global__ void __launch_bounds__(256)
 views_bwd_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ arg, const float* __restrict__ gates,
                  const T* __restrict__ h, int64_t ldh, int V, int B, int D, const float* __restrict__ g_xy,
                  const float* __restrict__ g_pooled, T* __restrict__ dh, int64_t lddh, float* __restrict__ dgates,
-                 int acc_view) {
+                 int acc_view, int parts) {
   const int64_t BD = (int64_t)B * D;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= BD) return;
@@ -144,11 +147,13 @@ views_bwd_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ a
     const int r = arg[v * BD + i];
     float dgv = 0.f;
     if (r >= 0) {
-      dgv = dp * to_f32(h[(int64_t)r * ldh + d]);
-      T* p = dh + (int64_t)r * lddh + d;                 // this thread owns column d of sentence b
-      *p = from_f32<T>(to_f32(*p) + dp * gates[v * BD + i]);
+      if (parts & 2) dgv = dp * to_f32(h[(int64_t)r * ldh + d]);
+      if (parts & 1) {
+        T* p = dh + (int64_t)r * lddh + d;                 // this thread owns column d of sentence b
+        *p = from_f32<T>(to_f32(*p) + dp * gates[v * BD + i]);
+      }
     }
-    dgates[v * BD + i] = (v == acc_view) ? dgates[v * BD + i] + dgv : dgv;    // acc_view already holds d gate_L
+    if (parts & 2) dgates[v * BD + i] = (v == acc_view) ? dgates[v * BD + i] + dgv : dgv;    // acc_view already holds d gate_L
   }
 }
 
@@ -594,17 +599,34 @@ extern "C" int edg_diversity_fwd(const float* pooled, int32_t V, int32_t B, int3
   return check_launch();
 }
 
+static int views_bwd_entry(const float* pooled, const int32_t* arg, const float* gates, const void* h,
+                           int dtype, int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy,
+                           const float* g_pooled, void* dh, int64_t lddh, float* dgates, int acc_view, int parts,
+                           edg_stream stream) {
+  if (V <= 0 || B < 0 || D <= 0 || parts < 1 || parts > 3) return EDG_ERR_ARG;
+  if (B == 0) return EDG_OK;
+  if (!pooled || !arg || !gates) return EDG_ERR_ARG;
+  if ((parts & 1) && !dh) return EDG_ERR_ARG;
+  if ((parts & 2) && (!h || !dgates)) return EDG_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  EDG_DISPATCH_T(dtype, views_bwd_kernel<T><<<blocks_for((int64_t)B * D, 256), 256, 0, s>>>(
+      pooled, arg, gates, (const T*)h, ldh, V, B, D, g_xy, g_pooled, (T*)dh, lddh, dgates, acc_view, parts);)
+  return check_launch();
+}
+
 extern "C" int edg_views_bwd(const float* pooled, const int32_t* arg, const float* gates, const void* h,
                              int dtype, int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy,
                              const float* g_pooled, void* dh, int64_t lddh, float* dgates, int acc_view,
                              edg_stream stream) {
-  if (V <= 0 || B < 0 || D <= 0) return EDG_ERR_ARG;
-  if (B == 0) return EDG_OK;
-  if (!pooled || !arg || !gates || !h || !dh || !dgates) return EDG_ERR_ARG;
-  cudaStream_t s = (cudaStream_t)stream;
-  EDG_DISPATCH_T(dtype, views_bwd_kernel<T><<<blocks_for((int64_t)B * D, 256), 256, 0, s>>>(
-      pooled, arg, gates, (const T*)h, ldh, V, B, D, g_xy, g_pooled, (T*)dh, lddh, dgates, acc_view);)
-  return check_launch();
+  return views_bwd_entry(pooled, arg, gates, h, dtype, ldh, V, B, D, g_xy, g_pooled, dh, lddh, dgates, acc_view, 3, stream);
+}
+
+extern "C" int edg_views_bwd_parts(const float* pooled, const int32_t* arg, const float* gates, const void* h,
+                                   int dtype, int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy,
+                                   const float* g_pooled, void* dh, int64_t lddh, float* dgates, int acc_view,
+                                   int parts, edg_stream stream) {
+  return views_bwd_entry(pooled, arg, gates, h, dtype, ldh, V, B, D, g_xy, g_pooled, dh, lddh, dgates, acc_view, parts,
+                         stream);
 }
 
 extern "C" int edg_views_patch(const float* pooled, const int32_t* arg, const float* gates, const float* hmax,

@@ -294,14 +294,19 @@ class _GatedStackFn(torch.autograd.Function):
         dgates = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
         side = _Side(_OVERLAP and gated, dev)
         patch = patch_ev = None
-        if views_active and _PATCH_VIEWS and not drop:
-            # the views' backward needs only forward tensors and d xy: it runs on the side stream from the very start
-            # (all of dgates; what goes to d h_1 comes back as patch arrays for the adjoint aggregation of layer 2)
+        early_views = views_active and not drop
+        if early_views:
+            # the dgates half of the views' backward needs only forward tensors and d xy: it runs on the side stream
+            # from the very start, so the gate MLPs' backward can follow right after edg_head_bwd.  (With
+            # EDG_VIEWS_PATCH=1 what goes to d h_1 comes back as patch arrays for the adjoint aggregation of layer 2.)
             with side.region():
-                patch = ops.views_patch(v_pooled, v_arg, gates, ctx.v_hmax, graph, g_xy, None, dgates, acc_view=-1)
-                if side.enabled:
-                    patch_ev = torch.cuda.Event()
-                    patch_ev.record(side.side)
+                if _PATCH_VIEWS:
+                    patch = ops.views_patch(v_pooled, v_arg, gates, ctx.v_hmax, graph, g_xy, None, dgates, acc_view=-1)
+                    if side.enabled:
+                        patch_ev = torch.cuda.Event()
+                        patch_ev.record(side.side)
+                else:
+                    ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, None, dgates, acc_view=-1, parts=2)
         # ---- d v, d c: the per-unit gradients of the forward sweep times d kl, or (when scores itself carries
         # gradient) pass A over h_L
         fc_w, fc_b = params[-2], params[-1]
@@ -342,7 +347,7 @@ class _GatedStackFn(torch.autograd.Function):
         # ---- pass B over h_L: dh_L, dgate_L
         if not views_active and Lyr > 1:
             dgates[:Lyr - 1].zero_()                                  # no diversity gradient: the other gates get none
-        early_gate = patch is not None        # dgates[L-1] already holds the views' share: head_bwd writes elsewhere
+        early_gate = early_views              # dgates[L-1] already holds the views' share: head_bwd writes elsewhere
         dgL = torch.empty((B, D), dtype=torch.float32, device=dev) if early_gate else dgates[Lyr - 1]
         if ctx.fc_sig and need_scores:
             # scores branch on z = sigmoid(x_out): d z (unit gate), through the sigmoid, then into the x_out path
@@ -441,8 +446,8 @@ class _GatedStackFn(torch.autograd.Function):
                                   dp[vi:vi + 1].contiguous(), tmp, dgates[vi:vi + 1], acc_view=0 if vi == Lyr - 1 else -1)
                     ops.dropout_rows(tmp, drop[1], vi, drop[0], out=dh, accumulate=True)
             elif l == 0 and views_active and not _PATCH_VIEWS:
-                # gated views of h_1 feed xy (:627-638): add their gradient before leaving layer 1
-                ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
+                # gated views of h_1 feed xy (:627-638): add their gradient to d h_1 before leaving layer 1
+                ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, None, parts=1)
             if l == 0 and gated and not early_gate:
                 with side.region():               # dgates are complete from here on
                     da_gate = gate_backward()

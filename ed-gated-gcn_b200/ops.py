@@ -228,10 +228,11 @@ def diversity_fwd(pooled: torch.Tensor) -> torch.Tensor:
     return xy
 
 
-def views_bwd(pooled, arg, gates, h, g_xy, g_pooled, dh, dgates, acc_view: int = -1) -> None:
+def views_bwd(pooled, arg, gates, h, g_xy, g_pooled, dh, dgates, acc_view: int = -1, parts: int = 3) -> None:
+    """``parts & 1``: add the views' gradient into ``dh``; ``parts & 2``: write ``dgates``."""
     V, B, D = pooled.shape
-    L.call("edg_views_bwd", L.ptr(pooled), L.ptr(arg), L.ptr(gates), L.ptr(h), L.dt(h), ld(h), V, B, D, L.ptr(g_xy),
-           L.ptr(g_pooled), L.ptr(dh), ld(dh), L.ptr(dgates), int(acc_view), L.stream())
+    L.call("edg_views_bwd_parts", L.ptr(pooled), L.ptr(arg), L.ptr(gates), L.ptr(h), L.dt(h), ld(h), V, B, D, L.ptr(g_xy),
+           L.ptr(g_pooled), L.ptr(dh), ld(dh) if dh is not None else 0, L.ptr(dgates), int(acc_view), int(parts), L.stream())
 
 
 def views_patch(pooled, arg, gates, hmax, graph, g_xy, g_pooled, dgates, acc_view: int = -1):

@@ -241,6 +241,14 @@ int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent
                       float* dv_unit, float* dc_unit, const int32_t* row_sent, int32_t N, int32_t max_len,
                       edg_stream stream);
 
+/* edg_views_bwd in halves: parts & 1 = the additions into dh only (h, dgates may be NULL), parts & 2 = dgates only
+ * (dh may be NULL).  The halves have different consumers (layer 1's backward / the gate MLPs' backward): two launches
+ * on two streams take the dgates half off the critical path. */
+int edg_views_bwd_parts(const float* pooled, const int32_t* arg, const float* gates, const void* h,
+                        int dtype, int64_t ldh, int32_t V, int32_t B, int32_t D, const float* g_xy,
+                        const float* g_pooled, void* dh, int64_t lddh, float* dgates, int acc_view, int parts,
+                        edg_stream stream);
+
 /* edg_views_bwd without the read-modify-write of dh and without the gather of h at the arg-max rows (hmax fp32
  * [B,D] = the column maximum edg_pool_fwd returns): dgates as there; what would be added to dh comes back as
  * patch_loc int16 [B,ldp] (sentence-local row, -1 = nothing) / patch_val fp32 [B,ldp] for edg_aggregate_patched.
