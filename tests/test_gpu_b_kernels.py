@@ -315,3 +315,25 @@ def test_views_patch_folded_into_adjoint_aggregation(dtype, long_sentences):
                 want[int(batch.sent_ptr[b]) + l, d] += val[b, d]
     assert rel(dh32p, want) < 1e-6
     assert (loc[:, D:] == -1).all()
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+def test_views_bwd_in_halves_equals_one_call(dtype):
+    """edg_views_bwd_parts: the dh half and the dgates half issued separately give the bits of the single call."""
+    from ed_gated_gcn_b200 import ops
+    batch, g = _batch_graph(30, 1, 35, seed=23)
+    D, V, B = 48, 3, batch.n_graphs
+    gen = torch.Generator().manual_seed(5)
+    h = ops.as_rows(torch.randn(batch.n_rows, D, generator=gen).to(DEV), dtype)
+    gates = (torch.rand(V, B, D, generator=gen) + 0.05).to(DEV)
+    pooled, arg = ops.pool_fwd(h, g, gates)
+    g_xy = torch.tensor(1.3, device=DEV)
+    dh0 = ops.as_rows(torch.randn(batch.n_rows, D, generator=gen).to(DEV), dtype)
+    base = torch.randn(V, B, D, generator=gen).to(DEV)
+    dh_a, dg_a = dh0.clone(), base.clone()
+    ops.views_bwd(pooled, arg, gates, h, g_xy, None, dh_a, dg_a, acc_view=2)
+    dh_b, dg_b = dh0.clone(), base.clone()
+    ops.views_bwd(pooled, arg, gates, h, g_xy, None, None, dg_b, acc_view=2, parts=2)
+    ops.views_bwd(pooled, arg, gates, h, g_xy, None, dh_b, None, parts=1)
+    assert torch.equal(dh_a, dh_b) and torch.equal(dg_a, dg_b)
+    assert not torch.equal(dh_a, dh0)
