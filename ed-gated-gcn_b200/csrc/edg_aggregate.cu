@@ -147,8 +147,10 @@ __device__ __noinline__ void aggregate_rows_global(const TI* __restrict__ x, int
   }
 }
 
-template <typename TI, typename TO, int MODE>
-__global__ void __launch_bounds__(1024)
+// PATCH / MAXT are compile-time so that the default instantiation (no patch arrays, 256-thread blocks) carries
+// neither the patch code nor the 64-register cap of 1024-thread blocks (they cost ~2-4 us per launch at C2)
+template <typename TI, typename TO, int MODE, bool PATCH, int MAXT>
+__global__ void __launch_bounds__(MAXT)
 aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int N, int B,
                         int tile_rows, int cap_rows, const int32_t* __restrict__ sent_ptr,
                         const int32_t* __restrict__ row_sent, const int32_t* __restrict__ row_ptr,
@@ -200,7 +202,7 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
   if (fits)
     for (int i = tid; i < nnz; i += nthreads) col_s[i] = __ldg(col + e0 + i) - r0;
   for (int i = tid; i < n; i += nthreads) inv_s[i] = __frcp_rn((float)(rp_s[i + 1] - rp_s[i] + 1));
-  if (patch.loc)                                    // per staged row: where its sentence's patch entries start, and
+  if (PATCH && patch.loc)                           // per staged row: where its sentence's patch entries start, and
     for (int i = tid; i < n; i += nthreads) {       // its sentence-local index (two dependent loads, once per row)
       const int b = __ldg(patch.row_sent + r0 + i);
       poff_s[i] = b * patch.ldp;
@@ -255,7 +257,7 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
 #pragma unroll
       for (int k = 0; k < E; ++k) acc[k] *= inv;
     }
-    if (patch.loc) apply_patch_at<E>(patch, (int64_t)poff_s[lr] + threadIdx.x * E, plr_s[lr], acc);
+    if (PATCH && patch.loc) apply_patch_at<E>(patch, (int64_t)poff_s[lr] + threadIdx.x * E, plr_s[lr], acc);
     store_chunk<TO, E>(yrow, acc);
   }
 }
@@ -301,16 +303,21 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
   dim3 block(chunks, rpb);
   const size_t smem = (size_t)cap_rows * pitch + (size_t)(8 * cap_rows + 8) * sizeof(int32_t);
   const unsigned blocks = (unsigned)((N + tile_rows - 1) / tile_rows);
-  auto k0 = aggregate_staged_kernel<TI, TO, 0>;
-  auto k1 = aggregate_staged_kernel<TI, TO, 1>;
-  static size_t attr0 = 0, attr1 = 0;         // largest dynamic smem opted into so far (per instantiation)
-  if (mode == 0) {
-    if (smem > attr0) { if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch(); attr0 = smem; }
-    k0<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col, patch);
-  } else {
-    if (smem > attr1) { if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch(); attr1 = smem; }
-    k1<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col, patch);
+  // four instantiations per (mode): {patch, no patch} x {256-thread, 1024-thread blocks}
+  const bool pt = patch.loc != nullptr, big = max_threads > 256;
+  void (*kern)(const TI*, int64_t, TO*, int64_t, int, int, int, int, const int32_t*, const int32_t*, const int32_t*,
+               const int32_t*, AggPatch);
+  if (mode == 0) kern = pt ? (big ? aggregate_staged_kernel<TI, TO, 0, true, 1024> : aggregate_staged_kernel<TI, TO, 0, true, 256>)
+                           : (big ? aggregate_staged_kernel<TI, TO, 0, false, 1024> : aggregate_staged_kernel<TI, TO, 0, false, 256>);
+  else kern = pt ? (big ? aggregate_staged_kernel<TI, TO, 1, true, 1024> : aggregate_staged_kernel<TI, TO, 1, true, 256>)
+                 : (big ? aggregate_staged_kernel<TI, TO, 1, false, 1024> : aggregate_staged_kernel<TI, TO, 1, false, 256>);
+  static size_t attr[2][2][2] = {};               // largest dynamic smem opted into so far (per instantiation)
+  size_t& seen = attr[mode][pt][big];
+  if (smem > seen) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
+    seen = smem;
   }
+  kern<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col, patch);
   return check_launch();
 }
 
