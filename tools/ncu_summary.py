@@ -10,6 +10,8 @@ def launches(path):
     for row in csv.DictReader(lines):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
+        if "spin_kernel" in row["Kernel Name"]:       # bench.py's preload of the per-kernel pass, not part of a step
+            continue
         v = float(row["Metric Value"].replace(",", ""))
         v = v / 1000 if row["Metric Unit"] == "ns" else v * 1000 if row["Metric Unit"] == "ms" else v
         a = agg.setdefault(row["Kernel Name"][:90], [0, 0.0]); a[0] += 1; a[1] += v; n += 1
