@@ -147,7 +147,7 @@ __device__ __noinline__ void aggregate_rows_global(const TI* __restrict__ x, int
   }
 }
 
-// PATCH / MAXT are compile-time so that the default instantiation (no patch arrays, 256-thread blocks) carries
+// PATCH / MAXT are compile-time so that the default instantiation (no patch arrays, 384-thread blocks) carries
 // neither the patch code nor the 64-register cap of 1024-thread blocks (they cost ~2-4 us per launch at C2)
 template <typename TI, typename TO, int MODE, bool PATCH, int MAXT>
 __global__ void __launch_bounds__(MAXT)
@@ -282,7 +282,7 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
   // sentence cannot fit next to a useful window
   int cap_rows = (int)((72 * 1024) / (pitch + 32));
   int tile_rows = cap_rows - max_len + 1;
-  int max_threads = 256;
+  int max_threads = 384;        // 3 blocks x 380 threads per SM: 40.6 / 39.6 us at C2 (256 threads: 43.9 / 43.0, 512: 46.4 / 45.7)
   if (tile_rows < 16) {
     // long sentences (config 5: up to 200 tokens): one ~200 KB window per SM, so the block itself must bring
     // the warps that hide the shared-memory latency (256 threads alone reached 34 % of the HBM peak)
@@ -298,19 +298,25 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
     else aggregate_flat_kernel<TI, TO, 1><<<blocks, 256, 0, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, chunks, row_ptr, col, patch);
     return check_launch();
   }
+  {
+    static int forced = -1;                 // experiment switch (bring-up only): EDG_AGG_THREADS = threads per block
+    if (forced < 0) { const char* e = getenv("EDG_AGG_THREADS"); forced = e ? atoi(e) : 0; }
+    if (forced >= 64 && forced <= 1024) max_threads = forced;
+  }
   int rpb = max_threads / chunks;
   if (rpb > 32) rpb = 32;
+  if (rpb < 1) rpb = 1;
   dim3 block(chunks, rpb);
   const size_t smem = (size_t)cap_rows * pitch + (size_t)(8 * cap_rows + 8) * sizeof(int32_t);
   const unsigned blocks = (unsigned)((N + tile_rows - 1) / tile_rows);
-  // four instantiations per (mode): {patch, no patch} x {256-thread, 1024-thread blocks}
-  const bool pt = patch.loc != nullptr, big = max_threads > 256;
+  // four instantiations per (mode): {patch, no patch} x {<= 384-thread, <= 1024-thread blocks}
+  const bool pt = patch.loc != nullptr, big = max_threads > 384;
   void (*kern)(const TI*, int64_t, TO*, int64_t, int, int, int, int, const int32_t*, const int32_t*, const int32_t*,
                const int32_t*, AggPatch);
-  if (mode == 0) kern = pt ? (big ? aggregate_staged_kernel<TI, TO, 0, true, 1024> : aggregate_staged_kernel<TI, TO, 0, true, 256>)
-                           : (big ? aggregate_staged_kernel<TI, TO, 0, false, 1024> : aggregate_staged_kernel<TI, TO, 0, false, 256>);
-  else kern = pt ? (big ? aggregate_staged_kernel<TI, TO, 1, true, 1024> : aggregate_staged_kernel<TI, TO, 1, true, 256>)
-                 : (big ? aggregate_staged_kernel<TI, TO, 1, false, 1024> : aggregate_staged_kernel<TI, TO, 1, false, 256>);
+  if (mode == 0) kern = pt ? (big ? aggregate_staged_kernel<TI, TO, 0, true, 1024> : aggregate_staged_kernel<TI, TO, 0, true, 384>)
+                           : (big ? aggregate_staged_kernel<TI, TO, 0, false, 1024> : aggregate_staged_kernel<TI, TO, 0, false, 384>);
+  else kern = pt ? (big ? aggregate_staged_kernel<TI, TO, 1, true, 1024> : aggregate_staged_kernel<TI, TO, 1, true, 384>)
+                 : (big ? aggregate_staged_kernel<TI, TO, 1, false, 1024> : aggregate_staged_kernel<TI, TO, 1, false, 384>);
   static size_t attr[2][2][2] = {};               // largest dynamic smem opted into so far (per instantiation)
   size_t& seen = attr[mode][pt][big];
   if (smem > seen) {
