@@ -172,10 +172,11 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
   if (tid == 0) {
     // sentences that START in [w0, w1): first sentence starting at or after w0 / w1
     const int w0 = blockIdx.x * tile_rows, w1 = w0 + tile_rows;
-    int s0 = B, s1 = B;
-    if (w0 < N) { s0 = row_sent[w0]; if (sent_ptr[s0] < w0) ++s0; }
-    if (w1 < N) { s1 = row_sent[w1]; if (sent_ptr[s1] < w1) ++s1; }
-    const int r0 = sent_ptr[s0], r1 = sent_ptr[s1];
+    // two levels of dependent loads only (see stage_window in edg_staged.cuh)
+    const int a0 = w0 < N ? __ldg(row_sent + w0) : B, a1 = w1 < N ? __ldg(row_sent + w1) : B;
+    const int p0 = __ldg(sent_ptr + a0), q0 = a0 < B ? __ldg(sent_ptr + a0 + 1) : p0;
+    const int p1 = __ldg(sent_ptr + a1), q1 = a1 < B ? __ldg(sent_ptr + a1 + 1) : p1;
+    const int r0 = (w0 < N && p0 < w0) ? q0 : p0, r1 = (w1 < N && p1 < w1) ? q1 : p1;
     range[0] = r0; range[1] = r1;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

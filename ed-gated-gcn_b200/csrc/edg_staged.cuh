@@ -22,10 +22,14 @@ __device__ __forceinline__ RowWindow stage_window(const T* __restrict__ x, int64
                                                   uint8_t* smem_rows, uint64_t* bar, int* sh) {
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const int w0 = blockIdx.x * tile_rows, w1 = w0 + tile_rows;
-    int s0 = B, s1 = B;                       // first sentence starting at or after w0 / w1
-    if (w0 < N) { s0 = row_sent[w0]; if (sent_ptr[s0] < w0) ++s0; }
-    if (w1 < N) { s1 = row_sent[w1]; if (sent_ptr[s1] < w1) ++s1; }
-    const int r0 = sent_ptr[s0], r1 = sent_ptr[s1];
+    // first sentence starting at or after w0 / w1.  Two levels of dependent loads only (the copy cannot start before
+    // them): both row_sent lookups together, then sent_ptr[s] and sent_ptr[s + 1] of both speculatively.
+    const int a0 = w0 < N ? __ldg(row_sent + w0) : B, a1 = w1 < N ? __ldg(row_sent + w1) : B;
+    const int p0 = __ldg(sent_ptr + a0), q0 = a0 < B ? __ldg(sent_ptr + a0 + 1) : p0;
+    const int p1 = __ldg(sent_ptr + a1), q1 = a1 < B ? __ldg(sent_ptr + a1 + 1) : p1;
+    const bool up0 = w0 < N && p0 < w0, up1 = w1 < N && p1 < w1;
+    const int s0 = a0 + up0, s1 = a1 + up1;
+    const int r0 = up0 ? q0 : p0, r1 = up1 ? q1 : p1;
     sh[0] = r0; sh[1] = r1; sh[2] = s0; sh[3] = s1;
     const uint32_t b32 = stg_smem_u32(bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
