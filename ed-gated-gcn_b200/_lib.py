@@ -12,7 +12,8 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libedgcn.so")
+# EDG_LIB = another build of the same ABI (A/B timing of kernel changes on one box); default: the in-tree library
+LIB_PATH = os.environ.get("EDG_LIB") or os.path.join(_HERE, "csrc", "libedgcn.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SIGMOID, ACT_RELU = 0, 1, 2
