@@ -81,10 +81,15 @@ pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restri
 //   P2 softmax statistics, kl_b and u_t = P_t (Q_t - kl_b) / B: warp per SENTENCE
 //   P3 dv_unit = gate * sum_t u_t h_t: thread = (chunk, sentence lane)
 constexpr int kSMaxQ = 4;
+#ifndef EDG_SCORES_WARPS
+#define EDG_SCORES_WARPS 8
+#endif
+constexpr int kScoresWarps = EDG_SCORES_WARPS;     // warps per block (P1: one row per warp iteration); 12 / 16 measured
+                                                   // slower than 8 at C2 (51.4 / 53.2 vs 50.5 us)
 constexpr int kWCache = 8;      // sentences per window whose gate*v vector is cached in shared memory
 
 template <typename T, int I64, int Q>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kScoresWarps)
 scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr,
                      const int32_t* __restrict__ row_sent, int N, int B, int D, int chunks, int tile_rows, int cap_rows,
                      const float* __restrict__ gate, const float* __restrict__ vvec, const float* __restrict__ cvec,
@@ -106,10 +111,10 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
   const int width = chunks * E;
   const uint32_t xs = stg_smem_u32(win);
   // P0 (overlaps the bulk copy): small per-row / per-sentence data -> shared memory, coalesced
-  for (int i = tid; i < n; i += 256) { dq_s[i] = sdist_at<I64>(dist, w.r0 + i); rs_s[i] = __ldg(row_sent + w.r0 + i); }
+  for (int i = tid; i < n; i += 32 * kScoresWarps) { dq_s[i] = sdist_at<I64>(dist, w.r0 + i); rs_s[i] = __ldg(row_sent + w.r0 + i); }
   {
     const int ns = min(w.s1 - w.s0, kWCache);
-    for (int i = tid; i < ns * width; i += 256) {
+    for (int i = tid; i < ns * width; i += 32 * kScoresWarps) {
       const int si = i / width, d = i - si * width;
       w_s[i] = d < D ? __ldg(gate + (int64_t)(w.s0 + si) * D + d) * __ldg(vvec + (int64_t)(w.s0 + si) * D + d) : 0.f;
     }
@@ -121,7 +126,7 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
     int cur = -1;
     float wq[Q][E];
     float cb = 0.f;
-    for (int lr = warp; lr < n; lr += 8) {
+    for (int lr = warp; lr < n; lr += kScoresWarps) {
       const int s = rs_s[lr];
       if (s != cur) {
         cur = s;
@@ -154,7 +159,7 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
   __syncthreads();
   // P2
   const float invB = 1.0f / (float)B;
-  for (int s = w.s0 + warp; s < w.s1; s += 8) {
+  for (int s = w.s0 + warp; s < w.s1; s += kScoresWarps) {
     const int beg = __ldg(sent_ptr + s) - w.r0, end = __ldg(sent_ptr + s + 1) - w.r0;
     float ms = -INFINITY, mq = -INFINITY;
     for (int t = beg + lane; t < end; t += 32) { ms = fmaxf(ms, sc_s[t]); mq = fmaxf(mq, dq_s[t]); }
@@ -180,7 +185,7 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
   if (dv_unit == nullptr) return;
   __syncthreads();
   // P3
-  const int ylanes = 256 / chunks;
+  const int ylanes = (32 * kScoresWarps) / chunks;
   const int x = tid % chunks, y = tid / chunks;
   if (y < ylanes) {
     const int c = x * E;
@@ -380,7 +385,7 @@ static int launch_scores_q(const void* h, int64_t ldh, const int32_t* sent_ptr, 
   int rc = opt_in_smem(scores_staged_kernel<T, I64, Q>, smem, &seen);
   if (rc) return rc;
   const unsigned blocks = (unsigned)((N + p.tile_rows - 1) / p.tile_rows);
-  scores_staged_kernel<T, I64, Q><<<blocks, dim3(32, 8), smem, s>>>((const T*)h, ldh, sent_ptr, row_sent, N, B, D, chunks,
+  scores_staged_kernel<T, I64, Q><<<blocks, dim3(32, kScoresWarps), smem, s>>>((const T*)h, ldh, sent_ptr, row_sent, N, B, D, chunks,
                                                                    p.tile_rows, p.cap_rows, gate, v, c, dist, scores, kl_b,
                                                                    dv_unit, dc_unit);
   return check_launch();
