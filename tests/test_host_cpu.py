@@ -224,3 +224,24 @@ def test_segments_from_dense_transform_host_logic():
     bad = t.clone(); bad[0, 0, 5] = 0.5                       # not a contiguous run of 1/len
     with pytest.raises(EdgError):
         segment.segments_from_transform(bad)
+
+
+def test_heads_from_adjacency_forest_and_singletons():
+    """A forest (several components, as CoreNLP emits for fragments) and one-token sentences orient cleanly;
+    the packed batch tolerates missing optional fields."""
+    import ed_gated_gcn_b200 as E
+    from oracle import ref_oracle as O
+    heads = np.array([-1, 0, 0, -1, 3, -1], dtype=np.int32)            # three components: {0,1,2}, {3,4}, {5}
+    adj = O.dense_adjacency_from_heads(heads, 9)                        # padded to 9 like the [100,100] matrices
+    got = E.heads_from_adjacency(adj, 6)
+    assert (got == -1).sum() == 3
+    assert np.array_equal(O.dense_adjacency_from_heads(got, 6), adj[:6, :6])
+    assert E.heads_from_adjacency(np.eye(4, dtype=np.int64), 1).tolist() == [-1]
+    items = [{"dependency_graph": adj.tolist(), "anchor_index": 4, "sentence_length": 6},
+             {"dependency_graph": np.eye(9, dtype=np.int64).tolist(), "anchor_index": 0, "sentence_length": 1}]
+    pb = E.collate_packed(items)
+    assert pb.dist is None and pb.seg_start is None and pb.polarity is None
+    assert pb.sent_ptr.tolist() == [0, 6, 7] and pb.max_len == 6 and pb.n_rows == 7
+    with pytest.raises(ValueError):
+        asym = adj.copy(); asym[0, 5] = 1
+        E.heads_from_adjacency(asym, 6)
