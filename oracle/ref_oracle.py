@@ -13,9 +13,12 @@ follows (paths relative to the upstream repository root).
 Pinning status: the reference holds no golden vectors / known-answer tests for
 this path, so the oracle is pinned against OUTPUTS OF THE
 REFERENCE ITSELF, generated in the build container by ``oracle/make_golden.py``
-(which imports the reference's own ``GraphConvolution``, ``get_dist_to_target``
-and the full ``BertAmir55.forward`` with a stub BERT) and committed under
-``tests/golden/``.  ``tests/test_oracle_golden.py`` replays them.
+(which imports the reference's own ``GraphConvolution``, ``get_dist_to_target``,
+the full ``BertAmir55.forward`` / ``BertAmir54.forward`` and ``BertDM.forward`` with a
+stub BERT) and committed under ``tests/golden/``.  ``tests/test_oracle_golden.py``
+replays them.  Not pinned by a reference run (the reference cannot produce them):
+``gate_masks`` (the dropout draw made explicit -- the reference's own Philox stream is
+not reproducible) and the L > 2 generalisation of the block.
 """
 from __future__ import annotations
 
