@@ -245,3 +245,38 @@ def test_heads_from_adjacency_forest_and_singletons():
     with pytest.raises(ValueError):
         asym = adj.copy(); asym[0, 5] = 1
         E.heads_from_adjacency(asym, 6)
+
+
+def test_built_library_contains_tcgen05_and_tma_instructions():
+    """No GPU needed: the SASS of the in-tree library must hold what the design claims -- tcgen05.mma (UTCHMMA),
+    tcgen05.ld (LDTM), TMA tensor loads (UTMALDG) and bulk copies (UBLKCP) -- per kernel family."""
+    import shutil
+    from ed_gated_gcn_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    per_fn = {}
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_fn[cur] = set()
+        elif cur:
+            for op in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP"):
+                if op in line:
+                    per_fn[cur].add(op)
+    def ops_of(substr):
+        out = set()
+        for fn, ops in per_fn.items():
+            if substr in fn:
+                out |= ops
+        return out
+    for kern in ("linear_ws_kernel", "linear_tc_kernel", "wgrad_tc_kernel", "wgrad_tall_kernel", "wgrad_tc_batch_kernel",
+                 "mlp_chain_kernel"):
+        assert {"UTCHMMA", "UTMALDG"} <= ops_of(kern), kern          # tensor cores fed by TMA
+    for kern in ("linear_ws_kernel", "mlp_chain_kernel", "wgrad_tall_kernel"):
+        assert "LDTM" in ops_of(kern), kern                          # accumulators read back from TMEM
+    for kern in ("aggregate_staged_kernel", "pool_staged_kernel", "scores_staged_kernel", "head_bwd_staged_kernel"):
+        assert "UBLKCP" in ops_of(kern), kern                        # windows staged by bulk async copies
