@@ -209,8 +209,13 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
 }
 
 // ---- head backward (scores/kl, final max-pool, optional direct x_out gradient) -----------------------
+// three ~72 KB windows fit an SM; without the cap the bf16 instantiation takes 106 registers and only two blocks
+// are resident (65.5 vs 70.5 us at C2 with the cap; 60 bytes of spills)
+#ifndef EDG_HEAD_MINBLOCKS
+#define EDG_HEAD_MINBLOCKS 3
+#endif
 template <typename T, int I64>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, EDG_HEAD_MINBLOCKS)
 head_bwd_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr,
                        const int32_t* __restrict__ row_sent, int N, int B, int D, int tile_rows, int cap_rows,
                        const float* __restrict__ gate, const float* __restrict__ vvec, const void* __restrict__ dist,
