@@ -128,8 +128,14 @@ sum_scaled_kernel(const float* __restrict__ in, int64_t n, float scale, float* _
 // parts: bit 0 = add the views' gradient into dh (scattered read-modify-write), bit 1 = dgates (gathers h at the
 // arg-max rows).  The two halves have different consumers (layer 1's backward / the gate MLPs' backward), so the
 // caller may issue them as two launches on two streams.
+// latency-bound scattered gathers / read-modify-writes: occupancy is what helps.  Uncapped the kernel takes 80 registers
+// (3 blocks per SM, 68 us at C2); capped to 32 registers for 8 resident blocks it runs in 48 us (104 bytes of spills),
+// same-box A/B of the whole step 0.915 vs 0.953 ms
+#ifndef EDG_VIEWS_MINBLOCKS
+#define EDG_VIEWS_MINBLOCKS 8
+#endif
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, EDG_VIEWS_MINBLOCKS)
 views_bwd_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ arg, const float* __restrict__ gates,
                  const T* __restrict__ h, int64_t ldh, int V, int B, int D, const float* __restrict__ g_xy,
                  const float* __restrict__ g_pooled, T* __restrict__ dh, int64_t lddh, float* __restrict__ dgates,
