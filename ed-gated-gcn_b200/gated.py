@@ -67,6 +67,22 @@ _OVERLAP = os.environ.get("EDG_OVERLAP", "1") != "0"
 _OVERLAP_WGRAD = _OVERLAP and os.environ.get("EDG_OVERLAP_WGRAD", "0") == "1"
 _SIDE_STREAMS = {}
 
+# The fused layer kernel (edg_gcn_layer: projection + tree aggregation + max-pool in one launch, both directions).
+# EDG_FUSED=0 keeps the unfused aggregate -> linear -> pool kernels (bring-up / A-B timing).
+_FUSED = os.environ.get("EDG_FUSED", "1") != "0"
+
+
+def _fused_plan(cfg, cd, D, graph, drop_p):
+    """(tile_rows, plan) when the whole GCN chain can run on ``edg_gcn_layer``: bf16, no ReLU, no gate dropout, no
+    BertAmir54 head, every sentence fits a tile.  Otherwise None (the unfused kernels cover everything)."""
+    if not _FUSED or cd != torch.bfloat16 or cfg["relu"] or drop_p > 0 or cfg["fc_sigmoid"]:
+        return None
+    rows = ops.fused_tile_rows(D, D)
+    if rows <= 0:
+        return None
+    plan = graph.tile_plan(rows)
+    return None if plan is None else (rows, plan)
+
 
 def _side_stream(device: torch.device, which: int = 0) -> "torch.cuda.Stream":
     idx = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
@@ -191,36 +207,63 @@ class _GatedStackFn(torch.autograd.Function):
         h = xr
         ms, hs = [], []
         v_pooled = v_arg = v_hmax = None
+        hmaxL = None
         xy = torch.zeros((), dtype=torch.float32, device=x.device)
-        for l, (w, b) in enumerate(gcn_p):
-            m = ops.aggregate(h, graph, mode=0)
-            wt = w_t[id(w)]                                                     # [out,in]: K-major B operand
-            h = ops.linear(m, wt, b.detach().float().contiguous() if b is not None else None,
-                           act=L.ACT_RELU if cfg["relu"] else L.ACT_NONE)
-            ms.append(m)
-            hs.append(h)
-            if l == 0 and gated:
-                with side.region():
-                    if drop_p > 0:
-                        # gate dropout (:624-625): view v sees h_1 under the per-token mask of gate v
-                        h1m = [ops.dropout_rows(hs[0], seed, v, drop_p) for v in range(Lyr)]
-                        v_pooled = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
-                        v_arg = torch.empty((Lyr, B, D), dtype=torch.int32, device=x.device)
-                        for v in range(Lyr):
-                            pv, av = ops.pool_fwd(h1m[v], graph, gates[v:v + 1])
-                            v_pooled[v], v_arg[v] = pv[0], av[0]
-                    elif _PATCH_VIEWS:
-                        v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
-                    else:
-                        v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
+        fused = _fused_plan(cfg, cd, D, graph, drop_p)
+        ctx.fused = fused
+        if fused is not None:
+            # one launch per layer: h_l = A^ (h_{l-1} W_l) + b_l with the column maxima of every sentence (and their
+            # first rows) from the epilogue -- the aggregated rows and the pooling passes never touch HBM
+            rows, plan = fused
+            for l, (w, b) in enumerate(gcn_p):
+                views_here = l == 0 and gated
+                want_pool = views_here or l == Lyr - 1
+                h, hm, ha, _ = ops.gcn_layer(h, w_t[id(w)], b.detach().float().contiguous() if b is not None else None,
+                                             graph, 0, plan, rows, want_pool=want_pool)
+                hs.append(h)
+                if views_here:
+                    v_hmax = hm
+                    v_arg = ha.unsqueeze(0).expand(Lyr, B, D)     # positive gates: the views share their arg-max row
                     if Lyr > 1:
-                        xy = ops.diversity_fwd(v_pooled)
+                        with side.region():
+                            v_pooled = gates * hm.unsqueeze(0)    # max_t (h_t g) = g max_t h_t for g > 0
+                            xy = ops.diversity_fwd(v_pooled)
+                if l == Lyr - 1:
+                    hmaxL, p_arg = hm, ha
+        else:
+            for l, (w, b) in enumerate(gcn_p):
+                m = ops.aggregate(h, graph, mode=0)
+                wt = w_t[id(w)]                                                     # [out,in]: K-major B operand
+                h = ops.linear(m, wt, b.detach().float().contiguous() if b is not None else None,
+                               act=L.ACT_RELU if cfg["relu"] else L.ACT_NONE)
+                ms.append(m)
+                hs.append(h)
+                if l == 0 and gated:
+                    with side.region():
+                        if drop_p > 0:
+                            # gate dropout (:624-625): view v sees h_1 under the per-token mask of gate v
+                            h1m = [ops.dropout_rows(hs[0], seed, v, drop_p) for v in range(Lyr)]
+                            v_pooled = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
+                            v_arg = torch.empty((Lyr, B, D), dtype=torch.int32, device=x.device)
+                            for v in range(Lyr):
+                                pv, av = ops.pool_fwd(h1m[v], graph, gates[v:v + 1])
+                                v_pooled[v], v_arg[v] = pv[0], av[0]
+                        elif _PATCH_VIEWS:
+                            v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
+                        else:
+                            v_pooled, v_arg = ops.pool_fwd(hs[0], graph, gates)
+                        if Lyr > 1:
+                            xy = ops.diversity_fwd(v_pooled)
         side.join()                                # gates (and the views) are complete from here on
         # ---- output pooling (:639-640); under gate dropout x_out = gate_L * (h_L * mask_L / (1-p))
         gL = gates[Lyr - 1]
-        hL = ops.dropout_rows(hs[-1], seed, Lyr - 1, drop_p) if drop_p > 0 else hs[-1]
-        pooled, p_arg = ops.pool_fwd(hL, graph, gL.unsqueeze(0))
-        pooled, p_arg = pooled[0], p_arg[0]
+        if fused is not None:
+            hL = hs[-1]
+            pooled = gL * hmaxL                        # the arg-max rows came with the maxima (p_arg)
+        else:
+            hL = ops.dropout_rows(hs[-1], seed, Lyr - 1, drop_p) if drop_p > 0 else hs[-1]
+            pooled, p_arg = ops.pool_fwd(hL, graph, gL.unsqueeze(0))
+            pooled, p_arg = pooled[0], p_arg[0]
         # ---- classifier head: logits_fn is the model's own dense head (host torch, :643); the per-sentence
         # operands of the collapsed scores, [v_b | va_b] = logits_b @ fc.weight and
         # c_b = a_b . va_b + logits_b . fc.bias  (= logits_b . (Wfc[:, D:] a_b + bfc)), are one kernel
@@ -257,6 +300,10 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.x_dtype = x.dtype
         ctx.x_cols = x.shape[1]
         ctx.v_hmax = v_hmax
+        ctx.hmaxL = hmaxL
+        if fused is not None:
+            ms = [None] * Lyr                     # never materialised
+            v_arg = v_arg.contiguous() if v_arg is not None else None
         ctx.save_for_backward(xr, gates, v_pooled, v_arg, p_arg, scores, kl_b, *ms, *hs, *params)
         # arg-max rows (global row ids), like the indices torch.max returns at :635-636/:640
         if v_arg is None:
@@ -297,7 +344,8 @@ class _GatedStackFn(torch.autograd.Function):
         patch = patch_ev = None
         # (the unpatched default keeps ONE edg_views_bwd launch at layer 1: issuing its dgates half early on the side
         # stream was measured slower, 0.989 vs 0.965 ms/step -- the two halves re-read the same [B,D] arrays)
-        early_views = views_active and not drop and _PATCH_VIEWS
+        fused = ctx.fused
+        early_views = views_active and not drop and _PATCH_VIEWS and fused is None
         if early_views:
             # the dgates half of the views' backward needs only forward tensors and d xy: it runs on the side stream
             # from the very start, so the gate MLPs' backward can follow right after edg_head_bwd.  (With
@@ -439,32 +487,56 @@ class _GatedStackFn(torch.autograd.Function):
             with side.region():                   # after head_bwd: dgates are complete
                 dgates[Lyr - 1].add_(dgL)
                 da_gate = gate_backward()
-        for l in range(Lyr - 1, -1, -1):
-            if l == 0 and views_active and drop:
-                # every view pooled its own masked copy of h_1: route per view, then mask the row gradient again
-                dp = (g_xy / B) * (v_pooled.sum(0, keepdim=True) - v_pooled)              # d xy / d pooled_v  (:638)
-                for vi in range(Lyr):
-                    tmp = ops.alloc_rows(N, D, cd, dev, zero=True)
-                    ops.views_bwd(v_pooled[vi:vi + 1], v_arg[vi:vi + 1], gates[vi:vi + 1], drop[2][vi], None,
-                                  dp[vi:vi + 1].contiguous(), tmp, dgates[vi:vi + 1], acc_view=0 if vi == Lyr - 1 else -1)
-                    ops.dropout_rows(tmp, drop[1], vi, drop[0], out=dh, accumulate=True)
-            elif l == 0 and views_active and not _PATCH_VIEWS:
-                # gated views of h_1 feed xy (:627-638): add their gradient to d h_1 before leaving layer 1
-                ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
-            if l == 0 and gated and not early_gate:
+        if fused is not None:
+            # with u_l = h_{l-1} W_l and h_l = A^ u_l + b_l:  db_l = colsum(dh_l), du_l = A^T dh_l, dW_l = h_{l-1}^T du_l,
+            # dh_{l-1} = du_l W_l^T.  One fused launch per layer produces du_{l-1} = A^T (du_l W_l^T + views patch) and the
+            # column sums of its argument (= db_{l-1}); neither dh_{l-1} nor the aggregated rows exist in HBM.
+            rows, plan = fused
+            db_next = ops.colsum(dh)
+            du = ops.aggregate(dh, graph, mode=1)
+            patch = None
+            if views_active:
+                patch = (ops.views_bwd_hmax(ctx.v_hmax, gates, g_xy, dgates, acc_view=Lyr - 1), v_arg[0])
+            if gated:
                 with side.region():               # dgates are complete from here on
                     da_gate = gate_backward()
-            w, b = params[2 * l], params[2 * l + 1]
-            if cfg["relu"]:
-                dh = ops.as_rows(dh * (hs[l] > 0), cd)
-            with side_w.region():
-                dW, db = ops.wgrad(ms[l], dh, bias_of=2)
-                grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db.to(b.dtype)
-            wk = ctx.w_n[l]                                                     # [in,out] = B operand of dh W^T
-            dm = ops.linear(dh, wk, None)
-            if l == 1 and patch is not None and patch_ev is not None:
-                torch.cuda.current_stream(dev).wait_event(patch_ev)       # the patch arrays come from the side stream
-            dh = ops.aggregate(dm, graph, mode=1, patch=patch if l == 1 else None)
+            for l in range(Lyr - 1, -1, -1):
+                w, b = params[2 * l], params[2 * l + 1]
+                dW, _ = ops.wgrad(hs[l - 1] if l > 0 else xr, du, bias_of=0)
+                grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db_next.to(b.dtype)
+                wk = ctx.w_n[l]                                                 # [in,out] = B operand of du W^T
+                if l > 0:
+                    du, _, _, db_next = ops.gcn_layer(du, wk, None, graph, 1, plan, rows,
+                                                      patch=patch if l == 1 else None, want_colsum=True)
+                else:
+                    dh = ops.linear(du, wk, None)
+        else:
+            for l in range(Lyr - 1, -1, -1):
+                if l == 0 and views_active and drop:
+                    # every view pooled its own masked copy of h_1: route per view, then mask the row gradient again
+                    dp = (g_xy / B) * (v_pooled.sum(0, keepdim=True) - v_pooled)              # d xy / d pooled_v  (:638)
+                    for vi in range(Lyr):
+                        tmp = ops.alloc_rows(N, D, cd, dev, zero=True)
+                        ops.views_bwd(v_pooled[vi:vi + 1], v_arg[vi:vi + 1], gates[vi:vi + 1], drop[2][vi], None,
+                                      dp[vi:vi + 1].contiguous(), tmp, dgates[vi:vi + 1], acc_view=0 if vi == Lyr - 1 else -1)
+                        ops.dropout_rows(tmp, drop[1], vi, drop[0], out=dh, accumulate=True)
+                elif l == 0 and views_active and not _PATCH_VIEWS:
+                    # gated views of h_1 feed xy (:627-638): add their gradient to d h_1 before leaving layer 1
+                    ops.views_bwd(v_pooled, v_arg, gates, hs[0], g_xy, None, dh, dgates, acc_view=Lyr - 1)
+                if l == 0 and gated and not early_gate:
+                    with side.region():               # dgates are complete from here on
+                        da_gate = gate_backward()
+                w, b = params[2 * l], params[2 * l + 1]
+                if cfg["relu"]:
+                    dh = ops.as_rows(dh * (hs[l] > 0), cd)
+                with side_w.region():
+                    dW, db = ops.wgrad(ms[l], dh, bias_of=2)
+                    grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db.to(b.dtype)
+                wk = ctx.w_n[l]                                                     # [in,out] = B operand of dh W^T
+                dm = ops.linear(dh, wk, None)
+                if l == 1 and patch is not None and patch_ev is not None:
+                    torch.cuda.current_stream(dev).wait_event(patch_ev)       # the patch arrays come from the side stream
+                dh = ops.aggregate(dm, graph, mode=1, patch=patch if l == 1 else None)
         dx = dh
         side.join()
         side_w.join()

@@ -28,10 +28,31 @@ class DepGraph:
     n_rows: int
     max_len: int
     padded_T: Optional[int] = None     # set when built from a dense [B,T,T] batch
+    max_sent_nnz: Optional[int] = None  # largest CSR entry count of one sentence (None: a tree, 3n - 2)
 
     @property
     def device(self):
         return self.row_ptr.device
+
+    def tile_plan(self, max_rows: int):
+        """Sentence-aligned row tiles for the fused layer kernel (``edg_gcn_layer``): ``(tile_info int32
+        [B+1, 8], n_tiles int32 [1])``, built by one small kernel on first use and cached per ``max_rows``.
+        ``None`` when a sentence cannot fit a tile (the caller then runs the unfused kernels)."""
+        if self.max_len > max_rows or self.n_graphs == 0:
+            return None
+        if (self.max_sent_nnz if self.max_sent_nnz is not None else 3 * self.max_len) > 512:
+            return None
+        plans = self.__dict__.setdefault("_plans", {})
+        plan = plans.get(max_rows)
+        if plan is None:
+            dev = self.device
+            info = torch.empty((self.n_graphs + 1, 8), dtype=torch.int32, device=dev)
+            n_tiles = torch.empty(1, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                L.call("edg_tile_plan", L.ptr(self.sent_ptr), L.ptr(self.row_ptr), self.n_graphs, int(max_rows),
+                       L.ptr(info), L.ptr(n_tiles), L.stream())
+            plan = plans[max_rows] = (info, n_tiles)
+        return plan
 
 
 def _i32(t: torch.Tensor, device) -> torch.Tensor:

@@ -78,6 +78,46 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     return out
 
 
+def fused_tile_rows(K: int, Nout: int) -> int:
+    """Rows per tile the fused layer kernel supports for this shape (0: shape not covered)."""
+    return int(L.load().edg_fused_tile_rows(K, Nout))
+
+
+def gcn_layer(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], graph, mode: int, plan, tile_rows: int,
+              want_pool: bool = False, patch=None, want_colsum: bool = False):
+    """``edg_gcn_layer``: ``A^ (x w.T) + bias`` (mode 0, optionally with the per-sentence column maxima
+    ``hmax fp32 [B,Nout]`` / ``harg int32 [B,Nout]``) or ``A^T (x w.T + patch)`` (mode 1, optionally with the
+    column sums of the un-aggregated rows).  ``w`` is ``[Nout, K]`` bf16, ``plan = graph.tile_plan(tile_rows)``.
+    Returns ``(y, hmax, harg, colsum)``."""
+    N, K = x.shape
+    Nout = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
+    B = graph.n_graphs
+    dev = x.device
+    y = alloc_rows(N, Nout, torch.bfloat16, dev)
+    hmax = torch.empty((B, Nout), dtype=torch.float32, device=dev) if want_pool else None
+    harg = torch.empty((B, Nout), dtype=torch.int32, device=dev) if want_pool else None
+    colsum = torch.empty((Nout,), dtype=torch.float32, device=dev) if want_colsum else None
+    ws = torch.empty((148 * Nout,), dtype=torch.float32, device=dev) if want_colsum else None
+    pv, pa = patch if patch is not None else (None, None)
+    info, n_tiles = plan
+    L.call("edg_gcn_layer", L.ptr(x), ld(x), N, K, L.ptr(w), ld(w), Nout, L.ptr(bias), int(mode), L.ptr(graph.row_ptr),
+           L.ptr(graph.col), L.ptr(graph.sent_ptr), L.ptr(info), L.ptr(n_tiles), int(tile_rows), L.ptr(y), ld(y),
+           L.ptr(hmax), L.ptr(harg), Nout, L.ptr(pv), L.ptr(pa), pv.stride(0) if pv is not None else 0, L.ptr(colsum), 0,
+           L.ptr(ws), ws.numel() * 4 if ws is not None else 0, L.stream())
+    return y, hmax, harg, colsum
+
+
+def views_bwd_hmax(hmax: torch.Tensor, gates: torch.Tensor, g_xy, dgates: torch.Tensor, acc_view: int = -1) -> torch.Tensor:
+    """Backward of the pooled views + diversity term from the column maxima: writes ``dgates`` and returns
+    ``patch_val fp32 [B,D]`` (what the arg-max rows of d h_1 receive)."""
+    V, B, D = gates.shape
+    patch_val = torch.empty((B, D), dtype=torch.float32, device=hmax.device)
+    L.call("edg_views_bwd_hmax", L.ptr(hmax), L.ptr(gates), L.ptr(g_xy), V, B, D, L.ptr(patch_val), D, L.ptr(dgates),
+           int(acc_view), L.stream())
+    return patch_val
+
+
 def wgrad(a: torch.Tensor, b: torch.Tensor, bias_of: int = 0):
     """``a.T @ b`` in fp32 (+ column sums of a (1) or b (2))."""
     R, K1 = a.shape

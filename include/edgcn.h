@@ -125,6 +125,42 @@ int edg_aggregate_patched(const void* x, int x_dtype, int64_t ldx, void* y, int 
                           const int32_t* sent_ptr, const int32_t* row_sent, int32_t B, int32_t max_len,
                           const int16_t* patch_loc, const float* patch_val, int32_t ldp, edg_stream stream);
 
+/* One graph-convolution layer as ONE kernel (projection on tcgen05, the degree-normalised aggregation of the
+ * sentence tree and the gated max-pool in its epilogue), replacing the matmul + bmm + divide + bias of
+ * models/gcn.py:33-45 and the torch.max pools of bert_amir5.py:627-640 without materialising `adj @ hidden`:
+ *   mode 0 (forward):  y = A^ (x W^T) + bias,        A^ = D^-1 A   (the reference's own association, gcn.py:34-41)
+ *                      hmax[b,d] = max_t y[t,d] over the sentence's rows (of the bf16-rounded y), harg = the GLOBAL row
+ *                      of that maximum, first row on ties (torch.max), -1 for an empty sentence       (both optional)
+ *   mode 1 (adjoint):  y = A^T (x W^T + patch),      patch[patch_arg[b,d], d] = patch_val[b,d]  (optional: the
+ *                      gradient the pooled views of bert_amir5.py:627-638 route to their arg-max rows; patch_arg < 0 =
+ *                      none); colsum[d] (+)= column sums of (x W^T + patch)  (optional: the bias gradient of the layer
+ *                      below).  With u_l = h_{l-1} W_l the backward pass of layer l is du_l = A^T dh_l,
+ *                      dW_l = h_{l-1}^T du_l, dh_{l-1} = du_l W_l^T, so x = du_l, w = W_l gives y = du_{l-1}.
+ * x bf16 [N, ldx], w bf16 [Nout, ldw] (row n = the weights producing output column n, K contiguous), y bf16
+ * [N, ldy], bias fp32.  K, Nout <= 320.  Rows are processed in tiles of whole sentences (edg_tile_plan with
+ * max_rows <= edg_fused_tile_rows(K, Nout)); every sentence must fit a tile and hold <= 512 CSR entries
+ * (a tree of n tokens has 3n - 2).  ws: 148 * Nout floats when colsum is given.  bf16 only (EDG_ERR_UNSUPPORTED
+ * outside these limits: callers then run edg_aggregate + edg_linear). */
+int edg_fused_tile_rows(int32_t K, int32_t Nout);
+/* Backward of the gated max-pool views of layer 1 + the diversity term (bert_amir5.py:627-638) from the column maxima
+ * hmax [B,D] that edg_gcn_layer returns (pooled_v = gates[v] * hmax; the views share their arg-max row):
+ *   patch_val[b,d] = sum_v gates[v,b,d] * dP_v,   dgates[v,b,d] (+)= dP_v * hmax[b,d]   (+= for v == acc_view, else =)
+ * with dP_v = g_xy / B * sum_{v' != v} pooled_v'.  patch_val (pitch ldp) + the harg of edg_gcn_layer are the patch
+ * arguments of the mode-1 call that produces d h_1.  g_xy: device scalar (NULL = 0). */
+int edg_views_bwd_hmax(const float* hmax, const float* gates, const float* g_xy, int32_t V, int32_t B, int32_t D,
+                       float* patch_val, int64_t ldp, float* dgates, int acc_view, edg_stream stream);
+/* Greedy packing of whole sentences into tiles of <= max_rows rows (<= 8 sentences, <= 512 CSR entries):
+ * tile_info int32 [B+1][8] = {s0, s1, r0, r1, e0, e1, 0, 0} (sentence, row and CSR-entry ranges), n_tiles = device
+ * scalar.  One small kernel, no host synchronisation. */
+int edg_tile_plan(const int32_t* sent_ptr, const int32_t* row_ptr, int32_t B, int32_t max_rows,
+                  int32_t* tile_info, int32_t* n_tiles, edg_stream stream);
+int edg_gcn_layer(const void* x, int64_t ldx, int32_t N, int32_t K, const void* w, int64_t ldw, int32_t Nout,
+                  const float* bias, int mode, const int32_t* row_ptr, const int32_t* col,
+                  const int32_t* sent_ptr, const int32_t* tile_info, const int32_t* n_tiles, int32_t tile_rows,
+                  void* y, int64_t ldy, float* hmax, int32_t* harg, int64_t ldpool, const float* patch_val,
+                  const int32_t* patch_arg, int64_t ldpatch, float* colsum, int colsum_accumulate, void* ws,
+                  size_t ws_bytes, edg_stream stream);
+
 /* C[M,Nout] = act(A[M,K] * W^T + bias), W given as [Nout,K] with K contiguous
  * (nn.Linear layout).  Replaces torch.matmul(text, weight) of gcn.py:34 (with a
  * transposed weight copy) and the nn.Linear calls of the gate MLPs

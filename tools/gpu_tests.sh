@@ -15,4 +15,5 @@ run b_kernels_rest 900 tests/test_gpu_b_kernels.py -k "not f32 and not bf16"
 run c_models 900 tests/test_gpu_c_models.py
 run d_fullsize 900 tests/test_gpu_d_fullsize.py
 run e_neighbours 600 tests/test_gpu_e_neighbours.py
-for f in gpurun_out/[a-e]_*.log; do echo "---- $f"; grep -E "^(FAILED|ERROR)|Error|error|assert " $f | head -12; done
+run f_fused 600 tests/test_gpu_f_fused.py
+for f in gpurun_out/[a-f]_*.log; do echo "---- $f"; grep -E "^(FAILED|ERROR)|Error|error|assert " $f | head -12; done
