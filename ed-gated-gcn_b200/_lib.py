@@ -36,6 +36,8 @@ SIGNATURES = {
     "edg_aggregate_patched": (c_int, [_P, c_int, _L, _P, c_int, _L, _I, _I, _P, _P, c_int, _P, _P, _I, _I, _P, _P, _I, _P]),
     "edg_fused_tile_rows": (c_int, [_I, _I]),
     "edg_views_bwd_hmax": (c_int, [_P, _P, _P, _I, _I, _I, _P, _L, _P, c_int, _P]),
+    "edg_head_du_workspace": (_Z, [_I]),
+    "edg_head_du": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _Z, _P]),
     "edg_tile_plan": (c_int, [_P, _P, _I, _I, _P, _P, _P]),
     "edg_gcn_layer": (c_int, [_P, _L, _I, _I, _P, _L, _I, _P, c_int, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _L, _P, _P,
                               _L, _P, c_int, _P, _Z, _P]),
@@ -54,7 +56,7 @@ SIGNATURES = {
     "edg_views_bwd": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _L, _P, c_int, _P]),
     "edg_views_bwd_parts": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _L, _P, c_int, c_int, _P]),
     "edg_views_patch": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, c_int, _P]),
-    "edg_scores_kl_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "edg_scores_kl_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "edg_fc_head_fwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "edg_fc_head_bwd_workspace": (_Z, [_I, _I, _I]),
     "edg_fc_head_bwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _P, _P, _P, _I, _I, _I, c_int, _P, _L, _P, _P, _L, _P, _P, _Z, _P]),
@@ -120,8 +122,10 @@ def _kernels_of(name: str, args) -> int:
         return 2 + (2 if args[11] else 0)
     if name == "edg_csr_from_heads":
         return 3
-    if name in ("edg_csr_from_dense_count", "edg_diversity_fwd", "edg_colsum", "edg_fc_head_bwd", "edg_wgrad_batch"):
+    if name in ("edg_csr_from_dense_count", "edg_diversity_fwd", "edg_colsum", "edg_fc_head_bwd", "edg_wgrad_batch", "edg_head_du"):
         return 2
+    if name == "edg_gcn_layer":
+        return 2 if args[23] else 1
     if name == "edg_pool_fwd":
         return (args[7] + 3) // 4
     return 1

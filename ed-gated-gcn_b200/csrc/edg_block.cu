@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(128)
 scores_kl_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restrict__ sent_ptr, int B, int D,
                      int chunks, const float* __restrict__ gate, const float* __restrict__ vvec,
                      const float* __restrict__ cvec, const void* __restrict__ dist, float* __restrict__ scores,
-                     float* __restrict__ kl_b, float* __restrict__ dv_unit, float* __restrict__ dc_unit) {
+                     float* __restrict__ kl_b, float* __restrict__ dv_unit, float* __restrict__ dc_unit,
+                     float* __restrict__ u_unit, float* __restrict__ sf_unit) {
   constexpr int E = Vec16<T>::kElems;
   constexpr int kMaxQ = ScoresQ<T>::value;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -304,6 +305,7 @@ scores_kl_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
   for (int t = beg; t < end; ++t) {
     const float u = (expf(scores[t] - ms) / zs) * ((expf(dist_at<I64>(dist, t) - mq) / zq) - klb) * invB;
     dcu += u;
+    if (lane == 0 && u_unit) u_unit[t] = u;
 #pragma unroll
     for (int q = 0; q < kMaxQ; ++q) {
       if (lane + 32 * q < chunks) {
@@ -320,7 +322,10 @@ scores_kl_fwd_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
 #pragma unroll
     for (int k = 0; k < E; ++k)
       if (lane + 32 * q < chunks && c + k < D)
+      {
         dv_unit[(int64_t)b * D + c + k] = dvu[q][k] * __ldg(gate + (int64_t)b * D + c + k);
+        if (sf_unit) sf_unit[(int64_t)b * D + c + k] = dvu[q][k];
+      }
   }
   if (lane == 0 && dc_unit) dc_unit[b] = dcu;
 }
@@ -500,7 +505,7 @@ int pool_fwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const i
 template <typename T>
 int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
                      int max_len, const float* gate, const float* v, const float* c, const void* dist, int dist_i64,
-                     float* scores, float* kl_b, float* dv_unit, float* dc_unit, cudaStream_t s);
+                     float* scores, float* kl_b, float* dv_unit, float* dc_unit, float* u_unit, float* sf_unit, cudaStream_t s);
 template <typename T>
 int head_bwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
                     int max_len, const float* gate, const float* v, const void* dist, int dist_i64, const float* scores,
@@ -651,11 +656,12 @@ extern "C" int edg_views_patch(const float* pooled, const int32_t* arg, const fl
 extern "C" int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                                  int32_t D, const float* gate, const float* v, const float* c,
                                  const void* dist, int dist_i64, float* scores, float* kl_b,
-                                 float* dv_unit, float* dc_unit, const int32_t* row_sent, int32_t N, int32_t max_len,
-                                 edg_stream stream) {
+                                 float* dv_unit, float* dc_unit, float* u_unit, float* sf_unit,
+                                 const int32_t* row_sent, int32_t N, int32_t max_len, edg_stream stream) {
   if (B < 0 || D <= 0) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
   if (!h || !sent_ptr || !gate || !v || !dist || !scores || !kl_b) return EDG_ERR_ARG;
+  if ((u_unit || sf_unit) && !dv_unit) return EDG_ERR_ARG;
   if (!aligned16(h) || !row_pitch_ok(dtype, ldh)) return EDG_ERR_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned blocks = blocks_for(B, 4);
@@ -665,11 +671,11 @@ extern "C" int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const in
     if (chunks > 32 * ScoresQ<T>::value) return EDG_ERR_UNSUPPORTED;
     if (staged_enabled()) {
       const int rc = scores_kl_staged<T>(h, ldh, sent_ptr, row_sent, N, B, D, max_len, gate, v, c, dist, dist_i64, scores, kl_b,
-                                         dv_unit, dc_unit, s);
+                                         dv_unit, dc_unit, u_unit, sf_unit, s);
       if (rc <= 0) return rc;
     }
-    if (dist_i64) scores_kl_fwd_kernel<T, 1><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit);
-    else scores_kl_fwd_kernel<T, 0><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit);
+    if (dist_i64) scores_kl_fwd_kernel<T, 1><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit, u_unit, sf_unit);
+    else scores_kl_fwd_kernel<T, 0><<<blocks, 128, 0, s>>>((const T*)h, ldh, sent_ptr, B, D, chunks, gate, v, c, dist, scores, kl_b, dv_unit, dc_unit, u_unit, sf_unit);
   })
   return check_launch();
 }

@@ -94,7 +94,8 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
                      const int32_t* __restrict__ row_sent, int N, int B, int D, int chunks, int tile_rows, int cap_rows,
                      const float* __restrict__ gate, const float* __restrict__ vvec, const float* __restrict__ cvec,
                      const void* __restrict__ dist, float* __restrict__ scores, float* __restrict__ kl_b,
-                     float* __restrict__ dv_unit, float* __restrict__ dc_unit) {
+                     float* __restrict__ dv_unit, float* __restrict__ dc_unit, float* __restrict__ u_unit,
+                     float* __restrict__ sf_unit) {
   constexpr int E = Vec16<T>::kElems;
   extern __shared__ __align__(128) uint8_t win[];
   __shared__ __align__(8) uint64_t bar;
@@ -176,6 +177,7 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
       for (int t = beg + lane; t < end; t += 32) {
         const float u = (expf(sc_s[t] - ms) / zs) * ((expf(dq_s[t] - mq) / zq) - klb) * invB;
         sc_s[t] = u;
+        if (u_unit) u_unit[w.r0 + t] = u;
         dcu += u;
       }
       dcu = warp_sum(dcu);
@@ -203,7 +205,10 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
       }
 #pragma unroll
       for (int k = 0; k < E; ++k)
-        if (c + k < D) dv_unit[(int64_t)s * D + c + k] = dvu[k] * __ldg(gate + (int64_t)s * D + c + k);
+        if (c + k < D) {
+          dv_unit[(int64_t)s * D + c + k] = dvu[k] * __ldg(gate + (int64_t)s * D + c + k);
+          if (sf_unit) sf_unit[(int64_t)s * D + c + k] = dvu[k];
+        }
     }
   }
 }
@@ -385,21 +390,22 @@ int pool_fwd_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const i
 template <typename T, int I64, int Q>
 static int launch_scores_q(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
                            int chunks, const WindowPlan& p, size_t smem, const float* gate, const float* v, const float* c,
-                           const void* dist, float* scores, float* kl_b, float* dv_unit, float* dc_unit, cudaStream_t s) {
+                           const void* dist, float* scores, float* kl_b, float* dv_unit, float* dc_unit, float* u_unit, float* sf_unit,
+                           cudaStream_t s) {
   static size_t seen = 0;
   int rc = opt_in_smem(scores_staged_kernel<T, I64, Q>, smem, &seen);
   if (rc) return rc;
   const unsigned blocks = (unsigned)((N + p.tile_rows - 1) / p.tile_rows);
   scores_staged_kernel<T, I64, Q><<<blocks, dim3(32, kScoresWarps), smem, s>>>((const T*)h, ldh, sent_ptr, row_sent, N, B, D, chunks,
                                                                    p.tile_rows, p.cap_rows, gate, v, c, dist, scores, kl_b,
-                                                                   dv_unit, dc_unit);
+                                                                   dv_unit, dc_unit, u_unit, sf_unit);
   return check_launch();
 }
 
 template <typename T>
 int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const int32_t* row_sent, int N, int B, int D,
                      int max_len, const float* gate, const float* v, const float* c, const void* dist, int dist_i64,
-                     float* scores, float* kl_b, float* dv_unit, float* dc_unit, cudaStream_t s) {
+                     float* scores, float* kl_b, float* dv_unit, float* dc_unit, float* u_unit, float* sf_unit, cudaStream_t s) {
   constexpr int E = Vec16<T>::kElems;
   const int chunks = (D + E - 1) / E;
   if (!row_sent || max_len <= 0 || chunks > 32 * kSMaxQ) return 1;
@@ -410,9 +416,9 @@ int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const 
   const int Q = (chunks + 31) / 32;
 #define EDG_SC(QQ)                                                                                                       \
   return dist_i64 ? launch_scores_q<T, 1, QQ>(h, ldh, sent_ptr, row_sent, N, B, D, chunks, p, smem, gate, v, c, dist, scores, \
-                                              kl_b, dv_unit, dc_unit, s)                                                 \
+                                              kl_b, dv_unit, dc_unit, u_unit, sf_unit, s)                                                 \
                   : launch_scores_q<T, 0, QQ>(h, ldh, sent_ptr, row_sent, N, B, D, chunks, p, smem, gate, v, c, dist, scores, \
-                                              kl_b, dv_unit, dc_unit, s);
+                                              kl_b, dv_unit, dc_unit, u_unit, sf_unit, s);
   switch (Q) {
     case 1: EDG_SC(1)
     case 2: EDG_SC(2)

@@ -286,7 +286,11 @@ class _GatedStackFn(torch.autograd.Function):
             scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(z, graph, ones, v, c, dist, want_units=True)
             ctx.fc_sig = (z, ones, a_fc)
         else:
-            scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hL, graph, gL, v, c, dist, want_units=True)
+            if fused is not None:
+                scores, kl_b, kl, dvu, dcu, uu, sfu = ops.scores_kl_fwd(hL, graph, gL, v, c, dist, want_units=True, want_rows=True)
+                ctx.kl_rows = (uu, sfu)
+            else:
+                scores, kl_b, kl, dvu, dcu = ops.scores_kl_fwd(hL, graph, gL, v, c, dist, want_units=True)
             ctx.fc_sig = None
         ctx.kl_units = (dvu, dcu)
         x_out = ops.gate_rows(hL, graph, gL, cd) if cfg["return_x_out"] else None
@@ -400,7 +404,21 @@ class _GatedStackFn(torch.autograd.Function):
             dgates[:Lyr - 1].zero_()                                  # no diversity gradient: the other gates get none
         early_gate = early_views              # dgates[L-1] already holds the views' share: head_bwd writes elsewhere
         dgL = torch.empty((B, D), dtype=torch.float32, device=dev) if early_gate else dgates[Lyr - 1]
-        if ctx.fc_sig and need_scores:
+        du_top = db_top = None
+        if fused is not None and g_xout is None:
+            # top of the chain straight in aggregated form: du_L = A^T dh_L, db_L, d gate_L from [N]- and [B,D]-sized
+            # inputs only (h_L is not read again, dh_L never exists)
+            uu, sfu = ctx.kl_rows
+            du_top, db_top, _ = ops.head_du(uu, g_kl if need_scores else None, g_scores, gL, v,
+                                            gp_total.contiguous() if gp_total is not None else None, p_arg, sfu, ctx.hmaxL,
+                                            graph, fused[1], want_dgate=True, dgate_out=dgL)
+            if g_scores is not None:
+                # scores itself carries gradient: d gate_L also needs sum_t g_scores_t h_t -- one sweep over h_L
+                _, _, dv_s, _ = ops.head_bwd(hL, graph, gL, v, dist, scores, kl_b, None, g_scores, None, None, None,
+                                             want_dh=False, want_dv=True)
+                dgL.add_(torch.where(gL != 0, dv_s * v / gL, torch.zeros_like(gL)))
+            dh = None
+        elif ctx.fc_sig and need_scores:
             # scores branch on z = sigmoid(x_out): d z (unit gate), through the sigmoid, then into the x_out path
             z, ones, _ = ctx.fc_sig
             dz, _, _, _ = ops.head_bwd(z, graph, ones, v, dist, scores, kl_b, g_kl, g_scores, None, None, None,
@@ -492,8 +510,11 @@ class _GatedStackFn(torch.autograd.Function):
             # dh_{l-1} = du_l W_l^T.  One fused launch per layer produces du_{l-1} = A^T (du_l W_l^T + views patch) and the
             # column sums of its argument (= db_{l-1}); neither dh_{l-1} nor the aggregated rows exist in HBM.
             rows, plan = fused
-            db_next = ops.colsum(dh)
-            du = ops.aggregate(dh, graph, mode=1)
+            if du_top is not None:
+                du, db_next = du_top, db_top
+            else:                                 # a direct gradient on x_out came in: dh_L exists, aggregate it
+                db_next = ops.colsum(dh)
+                du = ops.aggregate(dh, graph, mode=1)
             patch = None
             if views_active:
                 patch = (ops.views_bwd_hmax(ctx.v_hmax, gates, g_xy, dgates, acc_view=Lyr - 1), v_arg[0])

@@ -118,6 +118,25 @@ def views_bwd_hmax(hmax: torch.Tensor, gates: torch.Tensor, g_xy, dgates: torch.
     return patch_val
 
 
+def head_du(u_unit, g_kl, g_scores, gate, v, g_pooled, arg, sf_unit, hmax, graph, plan, want_dgate: bool = True,
+            dgate_out: Optional[torch.Tensor] = None):
+    """``edg_head_du``: ``du_L = A^T dh_L`` (bf16 rows), ``db_L`` and ``d gate_L`` from per-row scalars and
+    per-sentence vectors only (see include/edgcn.h).  Returns ``(du, dbias, dgate)``."""
+    B, D = gate.shape
+    N = u_unit.shape[0]
+    dev = gate.device
+    du = alloc_rows(N, D, torch.bfloat16, dev)
+    dbias = torch.empty((D,), dtype=torch.float32, device=dev)
+    dgate = (dgate_out if dgate_out is not None else torch.empty((B, D), dtype=torch.float32, device=dev)) if want_dgate else None
+    nbytes = L.load().edg_head_du_workspace(D)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    info, n_tiles = plan
+    L.call("edg_head_du", L.ptr(u_unit), L.ptr(g_kl), L.ptr(g_scores), L.ptr(gate), L.ptr(v), L.ptr(g_pooled), L.ptr(arg),
+           L.ptr(sf_unit), L.ptr(hmax), N, B, D, L.ptr(graph.row_ptr), L.ptr(graph.col), L.ptr(graph.sent_ptr), L.ptr(info),
+           L.ptr(n_tiles), L.ptr(du), ld(du), L.ptr(dgate), L.ptr(dbias), L.ptr(ws), ws.numel() * 4, L.stream())
+    return du, dbias, dgate
+
+
 def wgrad(a: torch.Tensor, b: torch.Tensor, bias_of: int = 0):
     """``a.T @ b`` in fp32 (+ column sums of a (1) or b (2))."""
     R, K1 = a.shape
@@ -295,18 +314,25 @@ def _dist_flag(dist: torch.Tensor) -> int:
     raise L.EdgError("dist_to_target must be int32 or int64")
 
 
-def scores_kl_fwd(h, graph, gate, v, c, dist, want_units: bool = False):
+def scores_kl_fwd(h, graph, gate, v, c, dist, want_units: bool = False, want_rows: bool = False):
+    """``want_units``: also ``dv_unit [B,D]``, ``dc_unit [B]`` (d kl / d v, d kl / d c per unit upstream gradient);
+    ``want_rows`` (with units): also ``u_unit [N]`` = d kl / d scores and ``sf_unit [B,D]`` = sum_t u_t h_t, the
+    inputs of :func:`head_du`."""
     B, D = gate.shape
     N = h.shape[0]
     scores = torch.empty((N,), dtype=torch.float32, device=h.device)
     kl_b = torch.empty((B,), dtype=torch.float32, device=h.device)
     dvu = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_units else None
     dcu = torch.empty((B,), dtype=torch.float32, device=h.device) if want_units else None
+    uu = torch.empty((N,), dtype=torch.float32, device=h.device) if want_units and want_rows else None
+    sfu = torch.empty((B, D), dtype=torch.float32, device=h.device) if want_units and want_rows else None
     L.call("edg_scores_kl_fwd", L.ptr(h), L.dt(h), ld(h), L.ptr(graph.sent_ptr), B, D, L.ptr(gate), L.ptr(v),
-           L.ptr(c), L.ptr(dist), _dist_flag(dist), L.ptr(scores), L.ptr(kl_b), L.ptr(dvu), L.ptr(dcu),
+           L.ptr(c), L.ptr(dist), _dist_flag(dist), L.ptr(scores), L.ptr(kl_b), L.ptr(dvu), L.ptr(dcu), L.ptr(uu), L.ptr(sfu),
            L.ptr(graph.row_sent), graph.n_rows, graph.max_len, L.stream())
     kl = torch.empty((), dtype=torch.float32, device=h.device)
     L.call("edg_sum_scaled", L.ptr(kl_b), B, 1.0 / B, L.ptr(kl), L.stream())
+    if want_units and want_rows:
+        return scores, kl_b, kl, dvu, dcu, uu, sfu
     if want_units:
         return scores, kl_b, kl, dvu, dcu
     return scores, kl_b, kl

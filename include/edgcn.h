@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EDG_ABI_VERSION 1
+#define EDG_ABI_VERSION 2
 
 typedef enum {
   EDG_OK = 0,
@@ -270,12 +270,14 @@ int edg_views_bwd(const float* pooled, const int32_t* arg, const float* gates, c
  *   kl_b[b]   = sum_t softmax_t(scores)*softmax_t(float(dist))
  * dist is packed int32 (dist_i64 = 0) or int64.
  * Optional (NULL to skip): dv_unit[B,D], dc_unit[B] = d kl / d v, d kl / d c per unit upstream
- * gradient, so that the backward pass needs no extra sweep over h when only kl carries gradient. */
+ * gradient, so that the backward pass needs no extra sweep over h when only kl carries gradient; with them (optional)
+ * u_unit[N] = d kl / d scores[i] = P_i (Q_i - kl_b) / B and sf_unit[B,D] = sum_t u_t h[t,:] (dv_unit without the gate),
+ * the per-row scalars and per-sentence vectors edg_head_du builds the top layer's gradient from. */
 int edg_scores_kl_fwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr, int32_t B,
                       int32_t D, const float* gate, const float* v, const float* c,
                       const void* dist, int dist_i64, float* scores, float* kl_b,
-                      float* dv_unit, float* dc_unit, const int32_t* row_sent, int32_t N, int32_t max_len,
-                      edg_stream stream);
+                      float* dv_unit, float* dc_unit, float* u_unit, float* sf_unit,
+                      const int32_t* row_sent, int32_t N, int32_t max_len, edg_stream stream);
 
 /* edg_views_bwd in halves: parts & 1 = the additions into dh only (h, dgates may be NULL), parts & 2 = dgates only
  * (dh may be NULL).  The halves have different consumers (layer 1's backward / the gate MLPs' backward): two launches
@@ -332,6 +334,22 @@ int edg_head_bwd(const void* h, int dtype, int64_t ldh, const int32_t* sent_ptr,
                  const float* g_pooled, const int32_t* arg, const void* g_xout, int64_t ldgx,
                  void* dh, int64_t lddh, float* dgate, float* dv, float* dc, int32_t max_len,
                  const int32_t* row_sent, int32_t N, edg_stream stream);
+
+/* The gradient entering the GCN chain from scores / kl / the final max-pool (bert_amir5.py:639-648), already in the
+ * aggregated form edg_gcn_layer (mode 1) and edg_wgrad consume, without reading h_L and without materialising dh_L:
+ *   dh_L[t,:] = ds_t (gate o v_b) + [t == arg[b,:]] (gate o g_pooled_b),   ds_t = g_kl u_unit[t] (+ g_scores[t])
+ *   du       = A^T dh_L         (bf16 [N, lddu]; mode 1 of edg_aggregate)
+ *   dbias    = colsum(dh_L)     (fp32 [D], optional; fixed summation order)
+ *   dgate    = g_kl v_b o sf_unit_b + g_pooled_b o hmax_b     (fp32 [B,D], optional: d loss / d gate_L)
+ * u_unit [N] and sf_unit [B,D] come from edg_scores_kl_fwd, hmax / arg [B,D] from edg_gcn_layer (mode 0), tile_info /
+ * n_tiles from edg_tile_plan.  g_kl: device scalar or NULL; g_scores [N], g_pooled / arg may be NULL.  D <= 320.
+ * ws: edg_head_du_workspace(D) bytes when dbias is requested. */
+size_t edg_head_du_workspace(int32_t D);
+int edg_head_du(const float* u_unit, const float* g_kl, const float* g_scores, const float* gate, const float* v,
+                const float* g_pooled, const int32_t* arg, const float* sf_unit, const float* hmax, int32_t N,
+                int32_t B, int32_t D, const int32_t* row_ptr, const int32_t* col, const int32_t* sent_ptr,
+                const int32_t* tile_info, const int32_t* n_tiles, void* du, int64_t lddu, float* dgate,
+                float* dbias, void* ws, size_t ws_bytes, edg_stream stream);
 
 /* x_out[i,:] = gate[b(i),:]*h[i,:]  (bert_amir5.py:639), only materialised when a
  * caller asks for the per-token output. */

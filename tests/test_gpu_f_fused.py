@@ -154,3 +154,55 @@ def test_fused_layer_config2_size_invariants():
     ones = torch.ones((1, batch.n_graphs, D), dtype=torch.float32, device=DEV)
     pooled, arg = ops.pool_fwd(y, g, ones)
     assert torch.equal(pooled[0], hmax) and torch.equal(arg[0], harg)
+
+
+@pytest.mark.parametrize("with_scores_grad", [False, True])
+@pytest.mark.parametrize("D", [300, 64])
+def test_head_du_matches_head_bwd_then_aggregate(D, with_scores_grad):
+    """edg_head_du (top-layer gradient generated in aggregated form from row scalars and sentence vectors) against the
+    kernels it replaces: edg_head_bwd (dh_L, d gate_L) -> edg_aggregate mode 1, edg_colsum."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import ops, synth
+    batch = synth.make_batch(211, 1, 50, seed=7 + D)
+    g = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=DEV)
+    B, N = batch.n_graphs, batch.n_rows
+    gen = torch.Generator().manual_seed(3)
+    h = ops.as_rows(torch.randn(N, D, generator=gen).to(DEV), torch.bfloat16)
+    gate = torch.rand(B, D, generator=gen).to(DEV) * 0.9 + 0.05
+    v = (torch.randn(B, D, generator=gen) * 0.2).to(DEV)
+    c = torch.randn(B, generator=gen).to(DEV)
+    gp = torch.randn(B, D, generator=gen).to(DEV)
+    anchor = torch.from_numpy(batch.anchor).to(DEV)
+    dist = E.tree_distance(g, anchor)
+    rows = ops.fused_tile_rows(D, D)
+    plan = g.tile_plan(rows)
+    scores, kl_b, kl, dvu, dcu, uu, sfu = ops.scores_kl_fwd(h, g, gate, v, c, dist, want_units=True, want_rows=True)
+    ones = torch.ones((1, B, D), dtype=torch.float32, device=DEV)
+    hmax_all, arg_all = ops.pool_fwd(h, g, ones)
+    hmax, arg = hmax_all[0].contiguous(), arg_all[0].contiguous()
+    g_kl = torch.tensor(0.37, device=DEV)
+    g_sc = (torch.randn(N, generator=gen) * 0.1).to(DEV) if with_scores_grad else None
+    dh, dgate_ref, _, _ = ops.head_bwd(h, g, gate, v, dist, scores, kl_b, g_kl, g_sc, gp, arg, None, want_dh=True, want_dv=False)
+    want_du = ops.aggregate(dh, g, mode=1, out_dtype=torch.float32)
+    want_db = dh.float().sum(0)
+    du, db, dgate = ops.head_du(uu, g_kl, g_sc, gate, v, gp, arg, sfu, hmax, g, plan)
+    # dh_L itself is rounded to bf16 on the reference side before it is aggregated; head_du rounds once at the end
+    assert rel(du.float(), want_du) < 8e-3
+    assert rel(db, want_db) < 5e-3
+    base = du.as_strided((N, du.stride(0)), (du.stride(0), 1))
+    assert torch.isfinite(base.float()).all() and (base[:, D:] == 0).all()
+    if not with_scores_grad:                 # (with a gradient on scores the caller adds sum_t g_scores_t h_t itself)
+        assert rel(dgate, dgate_ref) < 1e-4
+    # fp64 check of du on a few sentences from the definition
+    ds = (g_kl.double().cpu() * uu.double().cpu()) + (g_sc.double().cpu() if g_sc is not None else 0)
+    for b in range(0, B, 37):
+        lo, hi = int(batch.sent_ptr[b]), int(batch.sent_ptr[b + 1])
+        if hi == lo:
+            continue
+        a = torch.from_numpy(O.dense_adjacency_from_heads(batch.heads_list()[b], hi - lo)).double()
+        ah = a / (a.sum(1, keepdim=True) + 1)
+        q = (gate[b] * v[b]).double().cpu()
+        dh64 = ds[lo:hi, None] * q[None]
+        ar = arg[b].cpu().long() - lo
+        dh64[ar, torch.arange(D)] += (gate[b] * gp[b]).double().cpu()
+        assert rel(du[lo:hi].float(), ah.t() @ dh64) < 8e-3, b
