@@ -6,6 +6,7 @@ tensor is not on a CUDA device, the call raises.
 from __future__ import annotations
 
 import ctypes
+import threading
 import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
@@ -40,7 +41,8 @@ SIGNATURES = {
     "edg_head_du": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _Z, _P]),
     "edg_tile_plan": (c_int, [_P, _P, _I, _I, _P, _P, _P]),
     "edg_gcn_layer": (c_int, [_P, _L, _I, _I, _P, _L, _I, _P, c_int, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _L, _P, _P,
-                              _L, _P, c_int, _P, _Z, _P]),
+                              _L, _P, c_int, _P, _Z, _P, _P]),
+    "edg_row_meta": (c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "edg_linear": (c_int, [_P, c_int, _L, _I, _I, _P, _L, _I, _P, c_int, _P, c_int, _L, _P]),
     "edg_wgrad_workspace": (_Z, [_I, _I, _I, c_int]),
     "edg_wgrad": (c_int, [_P, _L, _I, _P, _L, _I, c_int, _I, _P, _L, _P, c_int, c_int, _P, _Z, _P]),
@@ -135,11 +137,24 @@ LAUNCHES = {"calls": 0, "kernels": 0}
 HOOK = None          # bench.py installs a (name, args, fn) -> rc wrapper to time kernels with CUDA events
 
 
+# Device of the call being assembled.  The argument list of `call(name, ptr(a), ptr(b), ..., stream())` is evaluated
+# left to right before `call` runs: `ptr` records the device of the tensors it sees, `stream()` returns THAT device's
+# current stream, and `call` launches with that device current.  The reference selects its GPU with `--device cuda:N`
+# and never calls set_device (train.py:286), so tensors on cuda:1 with device 0 current is the normal case there.
+_tls = threading.local()
+
+
 def call(name: str, *args) -> None:
     fn = getattr(load(), name)
     LAUNCHES["calls"] += 1
     LAUNCHES["kernels"] += _kernels_of(name, args)
-    check(HOOK(name, args, fn) if HOOK is not None else fn(*args))
+    dev = getattr(_tls, "dev", None)
+    _tls.dev = None
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            check(HOOK(name, args, fn) if HOOK is not None else fn(*args))
+    else:
+        check(HOOK(name, args, fn) if HOOK is not None else fn(*args))
 
 
 def ptr(t):
@@ -148,11 +163,18 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise EdgError("libedgcn takes CUDA tensors only (there is no CPU path)")
+    dev = getattr(_tls, "dev", None)
+    if dev is None:
+        _tls.dev = t.device.index
+    elif dev != t.device.index:
+        _tls.dev = None
+        raise EdgError(f"tensors of one call live on different devices (cuda:{dev} and {t.device})")
     return t.data_ptr()
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    dev = getattr(_tls, "dev", None)
+    return (torch.cuda.current_stream(dev) if dev is not None else torch.cuda.current_stream()).cuda_stream
 
 
 def dt(t_or_dtype) -> int:

@@ -318,12 +318,7 @@ static int launch_aggregate(const void* x, int64_t ldx, void* y, int64_t ldy, in
                            : (big ? aggregate_staged_kernel<TI, TO, 0, false, 1024> : aggregate_staged_kernel<TI, TO, 0, false, 384>);
   else kern = pt ? (big ? aggregate_staged_kernel<TI, TO, 1, true, 1024> : aggregate_staged_kernel<TI, TO, 1, true, 384>)
                  : (big ? aggregate_staged_kernel<TI, TO, 1, false, 1024> : aggregate_staged_kernel<TI, TO, 1, false, 384>);
-  static size_t attr[2][2][2] = {};               // largest dynamic smem opted into so far (per instantiation)
-  size_t& seen = attr[mode][pt][big];
-  if (smem > seen) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
-    seen = smem;
-  }
+  if (int rc_ = ensure_dyn_smem((const void*)kern, smem)) return rc_;
   kern<<<blocks, block, smem, s>>>((const TI*)x, ldx, (TO*)y, ldy, N, B, tile_rows, cap_rows, sent_ptr, row_sent, row_ptr, col, patch);
   return check_launch();
 }

@@ -3,6 +3,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "edg_common.cuh"
 
 namespace edg {
@@ -12,6 +15,21 @@ void set_cuda_error(cudaError_t e) {
   const char* s = cudaGetErrorString(e);
   strncpy(g_cuda_err, s ? s : "unknown", sizeof(g_cuda_err) - 1);
   g_cuda_err[sizeof(g_cuda_err) - 1] = 0;
+}
+
+int ensure_dyn_smem(const void* kernel, size_t smem) {
+  static std::mutex mu;      // (no shortcut for small sizes: static + dynamic shared memory together may exceed 48 KB)
+  static std::unordered_map<uint64_t, size_t> seen;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return check_launch();
+  const uint64_t key = ((uint64_t)(uint32_t)dev << 56) ^ (uint64_t)reinterpret_cast<uintptr_t>(kernel);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = seen[key];
+  if (smem > have) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
+    have = smem;
+  }
+  return EDG_OK;
 }
 
 // edg_gemm_simt.cu

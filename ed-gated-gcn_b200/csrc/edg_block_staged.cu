@@ -338,13 +338,7 @@ head_bwd_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __re
 }
 
 // ---- host launchers (called from the C-ABI functions in edg_block.cu) --------------------------------
-template <typename K> static int opt_in_smem(K kernel, size_t smem, size_t* seen) {
-  if (smem > *seen) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
-    *seen = smem;
-  }
-  return EDG_OK;
-}
+template <typename K> static int opt_in_smem(K kernel, size_t smem, size_t*) { return ensure_dyn_smem((const void*)kernel, smem); }
 
 static inline dim3 chunk_block(int chunks) {
   int y = 256 / chunks;

@@ -27,6 +27,11 @@ inline int check_launch() {
   return EDG_OK;
 }
 
+// Opt a kernel into `smem` bytes of dynamic shared memory (> 48 KB needs cudaFuncSetAttribute).  The attribute is per
+// (device, function): the cache is keyed by both, so a second GPU in the same process gets its own opt-in; thread-safe
+// (autograd calls backward from another host thread).
+int ensure_dyn_smem(const void* kernel, size_t smem);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t dtype_size(int dt) { return dt == EDG_BF16 ? 2 : 4; }
 inline bool row_pitch_ok(int dt, int64_t ld) { return (ld * (int64_t)dtype_size(dt)) % 16 == 0; }

@@ -34,7 +34,7 @@
 namespace edg {
 
 constexpr int kFRows = 128;             // UMMA M
-constexpr int kFMaxSent = 8;            // sentences per tile (pool table rows)
+constexpr int kFMaxSent = 6;            // sentences per tile (pool table rows)
 constexpr int kFMaxNnz = 512;           // CSR entries per tile (a tree of n rows has 3n - 2)
 constexpr int kFAccStages = 3;
 constexpr int kFAccStride = 160;        // TMEM columns per accumulator stage
@@ -69,6 +69,7 @@ struct GcnLayerParams {
   uint32_t idesc[2];
   int pitch;                            // staging row pitch in bytes: columns * 2 + 16 (bf16; an odd number of 16-byte chunks, so the
                                         // row-per-lane stores of phase A and the chunk-per-lane loads of phase B are conflict-free)
+  int box_rows;                         // rows per TMA box of the activation tile (32, 64 or 128)
   int sleep_ns;                         // back-off of the helper warps' long waits
   int prefetch;                         // tiles of look-ahead for the TMA L2 prefetch (0 = off)
   uint32_t off_a, off_s, off_tab, off_csr, off_scr, off_lut, off_bar;   // shared-memory offsets (W at 0)
@@ -118,7 +119,8 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = (P.n_split == 2) ? (int)(blockIdx.x & 1) : 0;
-  const int t_first = (int)blockIdx.x / P.n_split, t_step = (int)gridDim.x / P.n_split;
+  const int t_first = (P.debug & 64) ? (int)blockIdx.x : (int)blockIdx.x / P.n_split;      // bit 64 (bring-up): one tile per CTA, timing only
+  const int t_step = (P.debug & 64) ? (int)gridDim.x : (int)gridDim.x / P.n_split;
   const int n0 = half * P.bn[0];
   const int bn = P.bn[half];
   const int num_kb = P.num_kb;
@@ -187,12 +189,13 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
           for (int kb = 0; kb < num_kb; ++kb)
             asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
                          ::"l"(reinterpret_cast<uint64_t>(&P.map_a)), "r"(kb * 64), "r"(r) : "memory");
-        const int nb32 = (P.debug & 8) ? 0 : (r1 - r0 + 31) >> 5;
+        const int nb32 = (P.debug & 8) ? 0 : (r1 - r0 + P.box_rows - 1) / P.box_rows;
+        const uint32_t box_bytes = (uint32_t)P.box_rows * 128u;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_relaxed(empty(stage), phase ^ 1, (uint32_t)P.sleep_ns);
-          mbar_expect_tx(full(stage), (uint32_t)nb32 * 4096u);
+          mbar_expect_tx(full(stage), (uint32_t)nb32 * box_bytes);
           for (int b = 0; b < nb32; ++b)
-            tma_load_2d(Ablk(stage) + (uint32_t)b * 4096u, &P.map_a, full(stage), kb * 64, r0 + 32 * b);
+            tma_load_2d(Ablk(stage) + (uint32_t)b * box_bytes, &P.map_a, full(stage), kb * 64, r0 + P.box_rows * b);
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -314,6 +317,26 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
     for (int i = et; i < pitch / 4; i += kEpiThreads)             // the zero row: target of the unused neighbour slots
       reinterpret_cast<uint32_t*>(sm + P.off_s + (size_t)P.rows_cap * pitch)[i] = 0u;
     epi_bar(kEpiThreads);
+    // patch entries (adjoint): global arg-max row and value per (sentence of the tile, this thread's column)
+    float pv[kFMaxSent];
+    int pg[kFMaxSent];
+    auto load_patch = [&](const int32_t* h) {
+      const int s0_ = h[3], ns_ = h[2];
+      const int gc = n0 + et;
+#pragma unroll
+      for (int s = 0; s < kFMaxSent; ++s) {
+        pv[s] = 0.f; pg[s] = -1;
+        if (et < cw && gc < P.Nout && s < ns_) {
+          const int64_t o = (int64_t)(s0_ + s) * P.ldpatch + gc;
+          pg[s] = __ldg(P.patch_arg + o);
+          pv[s] = __ldg(P.patch_val + o);
+        }
+      }
+    };
+    if (patch && t_first < n_tiles) {
+      mbar_wait(cfull(0), 0);
+      load_patch(reinterpret_cast<const int32_t*>(sm + P.off_csr));
+    }
     int it = 0;
     for (int t = t_first; t < n_tiles; t += t_step, ++it) {
       const int as = it % kFAccStages;
@@ -329,23 +352,16 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
       mbar_wait(cfull(cb), cphase);
       EDG_TRACE();
       const int r0 = hdr[0], n = hdr[1], ns = hdr[2], s0 = hdr[3];
-      // ---- patch entries of the tile: thread = column, one entry per sentence (tile-local u8 rows, 0xff = none);
-      // issued before the accumulator wait so that the global latency hides behind it and phase A
-      float pv[kFMaxSent];
+      // ---- patch entries of the tile: thread = column, one entry per sentence (tile-local u8 rows, 0xff = none); the
+      // global loads were issued one tile ahead (below), so no DRAM round trip is waited for here
       uint32_t pa_lo = 0xffffffffu, pa_hi = 0xffffffffu;
       if (patch) {
-        const int gc = n0 + et;
 #pragma unroll
         for (int s = 0; s < kFMaxSent; ++s) {
-          pv[s] = 0.f;
-          if (et < cw && gc < P.Nout && s < ns) {
-            const int64_t o = (int64_t)(s0 + s) * P.ldpatch + gc;
-            const int a = __ldg(P.patch_arg + o) - r0;
-            pv[s] = __ldg(P.patch_val + o);
-            const uint32_t lr = (a >= 0 && a < n) ? (uint32_t)a : 0xffu;
-            if (s < 4) pa_lo = (pa_lo & ~(0xffu << (8 * s))) | (lr << (8 * s));
-            else pa_hi = (pa_hi & ~(0xffu << (8 * (s - 4)))) | (lr << (8 * (s - 4)));
-          }
+          const int a = pg[s] - r0;
+          const uint32_t lr = (pg[s] >= 0 && a >= 0 && a < n) ? (uint32_t)a : 0xffu;
+          if (s < 4) pa_lo = (pa_lo & ~(0xffu << (8 * s))) | (lr << (8 * s));
+          else pa_hi = (pa_hi & ~(0xffu << (8 * (s - 4)))) | (lr << (8 * (s - 4)));
         }
       }
       mbar_wait(tfull(as), aphase);
@@ -410,6 +426,11 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
           }
         }
         epi_bar(kEpiThreads);
+        if (t + t_step < n_tiles) {                          // the next tile's entries: in flight during phase B
+          const int cbn = (it + 1) % kFCsrBufs;
+          mbar_wait(cfull(cbn), (uint32_t)((it + 1) / kFCsrBufs) & 1u);
+          load_patch(reinterpret_cast<const int32_t*>(sm + P.off_csr + cbn * kFCsrBytes));
+        }
       }
       // ---- phase B: y_i = sum of the staged rows of i's neighbours; one 16-byte load per neighbour slot
       if (b_active) {
@@ -696,12 +717,22 @@ static FusedPlan plan_fused(int K, int Nout) {
   return p;
 }
 
+// edg_gcn_fused2.cu (the version with the aggregation on the tensor cores; EDG_FUSED_V=1 selects the kernel above)
+static bool fused_v2() { return fused_env("EDG_FUSED_V", 1) == 2; }
+static int fused2_tile_rows(int K, int Nout);
+static int launch_gcn_layer2(const void* x, int64_t ldx, int32_t N, int32_t K, const void* w, int64_t ldw, int32_t Nout,
+                             const float* bias, int mode, const int32_t* row_ptr, const int32_t* col, const int32_t* sent_ptr,
+                             const int32_t* tile_info, const int32_t* n_tiles, int32_t tile_rows, void* y, int64_t ldy, float* hmax,
+                             int32_t* harg, int64_t ldpool, const float* patch_val, const int32_t* patch_arg, int64_t ldpatch,
+                             float* colsum, int colsum_accumulate, void* ws, size_t ws_bytes, const void* row_meta, cudaStream_t s);
+
 }  // namespace edg
 
 using namespace edg;
 
 /* see include/edgcn.h */
 extern "C" int edg_fused_tile_rows(int32_t K, int32_t Nout) {
+  if (fused_v2()) return fused2_tile_rows(K, Nout);
   const FusedPlan p = plan_fused(K, Nout);
   return p.ok ? p.rows_cap : 0;
 }
@@ -723,13 +754,8 @@ extern "C" int edg_tile_plan(const int32_t* sent_ptr, const int32_t* row_ptr, in
   if (B < 0 || max_rows < 1 || max_rows > kFRows) return EDG_ERR_ARG;
   if (!sent_ptr || !row_ptr || !tile_info || !n_tiles) return EDG_ERR_ARG;
   if (B > 200 * 1024) return EDG_ERR_UNSUPPORTED;
-  static size_t seen = 0;
   const size_t smem = (size_t)(B > 0 ? B : 1);
-  if (smem > 48 * 1024 && smem > seen) {
-    if (cudaFuncSetAttribute(tile_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch();
-    seen = smem;
-  }
+  if (int rc_ = ensure_dyn_smem((const void*)tile_plan_kernel, smem)) return rc_;
   tile_plan_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(sent_ptr, row_ptr, B, max_rows, tile_info, n_tiles);
   return check_launch();
 }
@@ -739,7 +765,7 @@ extern "C" int edg_gcn_layer(const void* x, int64_t ldx, int32_t N, int32_t K, c
                              const int32_t* sent_ptr, const int32_t* tile_info, const int32_t* n_tiles, int32_t tile_rows,
                              void* y, int64_t ldy, float* hmax, int32_t* harg, int64_t ldpool, const float* patch_val,
                              const int32_t* patch_arg, int64_t ldpatch, float* colsum, int colsum_accumulate, void* ws,
-                             size_t ws_bytes, edg_stream stream) {
+                             size_t ws_bytes, const void* row_meta, edg_stream stream) {
   if (N < 0 || K <= 0 || Nout <= 0 || (mode != 0 && mode != 1)) return EDG_ERR_ARG;
   if (N == 0) return EDG_OK;
   if (!x || !w || !y || !row_ptr || !col || !sent_ptr || !tile_info || !n_tiles) return EDG_ERR_ARG;
@@ -748,14 +774,20 @@ extern "C" int edg_gcn_layer(const void* x, int64_t ldx, int32_t N, int32_t K, c
   if (mode == 1 && (hmax || bias)) return EDG_ERR_ARG;
   if (ldx < K || ldw < K || ldy < Nout) return EDG_ERR_ARG;
   if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (ldx & 7) || (ldw & 7) || (ldy & 7)) return EDG_ERR_ALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (fused_v2())
+    return launch_gcn_layer2(x, ldx, N, K, w, ldw, Nout, bias, mode, row_ptr, col, sent_ptr, tile_info, n_tiles, tile_rows, y, ldy,
+                             hmax, harg, ldpool, patch_val, patch_arg, ldpatch, colsum, colsum_accumulate, ws, ws_bytes, row_meta, s);
   const FusedPlan p = plan_fused(K, Nout);
   if (!p.ok || tile_rows > p.rows_cap) return EDG_ERR_UNSUPPORTED;
-  cudaStream_t s = (cudaStream_t)stream;
   const int groups = kNumSMs / p.n_split;
   if (colsum && ws_bytes < (size_t)groups * Nout * sizeof(float)) return EDG_ERR_WORKSPACE;
   GcnLayerParams P;
   memset(&P, 0, sizeof(P));
-  int rc = make_map_bf16(&P.map_a, x, N, K, ldx, 64, 32);
+  int box_rows = fused_env("EDG_FUSED_BOXROWS", 32);
+  if (box_rows != 32 && box_rows != 64 && box_rows != 128) box_rows = 32;
+  P.box_rows = box_rows;
+  int rc = make_map_bf16(&P.map_a, x, N, K, ldx, 64, box_rows);
   if (rc) return rc;
   rc = make_map_bf16(&P.map_w, w, Nout, K, ldw, 64, 16);
   if (rc) return rc;
@@ -771,22 +803,15 @@ extern "C" int edg_gcn_layer(const void* x, int64_t ldx, int32_t N, int32_t K, c
   P.idesc[1] = make_idesc_bf16(kFRows, p.bn1 > 0 ? p.bn1 : 16, 0, 0);
   P.pitch = p.pitch;
   P.sleep_ns = fused_env("EDG_FUSED_SLEEP", 64);
-  P.prefetch = fused_env("EDG_FUSED_PF", 2);
-  if (P.prefetch < 0 || P.prefetch > 3) P.prefetch = 2;
+  P.prefetch = fused_env("EDG_FUSED_PF", 0);       // L2 prefetch of the tiles ahead: measured slower (71 vs 66 us), off
+  if (P.prefetch < 0 || P.prefetch > 3) P.prefetch = 0;
   P.off_a = p.off_a; P.off_s = p.off_s; P.off_tab = p.off_tab; P.off_csr = p.off_csr; P.off_scr = p.off_scr; P.off_lut = p.off_lut; P.off_bar = p.off_bar;
   const int grid = groups * p.n_split;
-  static size_t seen[2] = {0, 0};
   if (p.epi_warps == 12) {
-    if (p.smem > seen[1]) {
-      if (cudaFuncSetAttribute(gcn_layer_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return check_launch();
-      seen[1] = p.smem;
-    }
+    if (int rc_ = ensure_dyn_smem((const void*)gcn_layer_kernel<12>, p.smem)) return rc_;
     gcn_layer_kernel<12><<<grid, (4 + 12) * 32, p.smem, s>>>(P);
   } else {
-    if (p.smem > seen[0]) {
-      if (cudaFuncSetAttribute(gcn_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess) return check_launch();
-      seen[0] = p.smem;
-    }
+    if (int rc_ = ensure_dyn_smem((const void*)gcn_layer_kernel<8>, p.smem)) return rc_;
     gcn_layer_kernel<8><<<grid, (4 + 8) * 32, p.smem, s>>>(P);
   }
   rc = check_launch();

@@ -494,273 +494,6 @@ linear_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// linear_wf : the WHOLE weight matrix stationary (D = 300: 5 x [304 x 64] bf16 boxes = 190 KB of shared memory),
-// one CTA computes all N columns of its M tiles, so every activation byte crosses L2 -> SM exactly ONCE.
-// (linear_ws splits N over two CTAs and therefore reads each activation tile twice; at C2 it is bound by that
-// L2 -> SM traffic: 32.7 us even with the output stores removed.)  N = n_a + n_b is issued as two MMAs per K step
-// into TMEM columns [0, n_a) and [n_a, n_a + n_b); the accumulator is single-buffered, the activation ring keeps
-// loading during the epilogue.
-// ---------------------------------------------------------------------------------------------
-struct WfLayout {
-  uint32_t base; int w_bytes_kb; int num_kb; int stages;
-  __device__ uint32_t w(int kb) const { return base + kb * w_bytes_kb; }
-  __device__ uint32_t a(int s) const { return base + num_kb * w_bytes_kb + s * kABytes; }
-  __device__ uint32_t bias() const { return a(stages); }
-  __device__ uint32_t bars(int nbias) const { return bias() + nbias * 4; }
-};
-
-template <typename TC>
-__global__ void __launch_bounds__(kLinThreads, 1)
-linear_wf_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w0,
-                 const __grid_constant__ CUtensorMap map_w1, int M, int K, int Nout, int n_a, int n_b, int m_tiles,
-                 int stages, int nbias, uint32_t idesc_a, uint32_t idesc_b, const float* __restrict__ bias, int act,
-                 TC* __restrict__ C, int64_t ldc) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  WfLayout L;
-  L.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  L.num_kb = (K + kBlockK - 1) / kBlockK;
-  L.w_bytes_kb = (n_a + n_b) * kBlockK * 2;
-  L.stages = stages;
-  const int num_kb = L.num_kb;
-  const uint32_t bars = L.bars(nbias);
-  auto full = [&](int st) { return bars + 8 * st; };
-  auto empty = [&](int st) { return bars + 8 * (kWsMaxStages + st); };
-  const uint32_t tfull = bars + 8 * (2 * kWsMaxStages), tempty = tfull + 8, wfull = tfull + 16, tmem_slot = tfull + 24;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* bias_s = reinterpret_cast<float*>(smem_raw + (L.bias() - smem_u32(smem_raw)));
-
-  for (int i = threadIdx.x; i < nbias; i += kLinThreads) bias_s[i] = (bias && i < Nout) ? bias[i] : 0.f;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_w0);
-    tma_prefetch_desc(&map_w1);
-    for (int s = 0; s < stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(tfull, 1); mbar_init(tempty, 8); mbar_init(wfull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // first activation stages go out before the (large) weight burst so the first MMAs are not delayed by it
-      int stage = 0; uint32_t phase = 0;
-      int mt = blockIdx.x, kb = 0;
-      auto load_a = [&]() {
-        mbar_wait(empty(stage), phase ^ 1);
-        mbar_expect_tx(full(stage), kABytes);
-        tma_load_2d(L.a(stage), &map_a, full(stage), kb * kBlockK, mt * kBlockM);
-        if (++stage == stages) { stage = 0; phase ^= 1; }
-        if (++kb == num_kb) { kb = 0; mt += gridDim.x; }
-      };
-      for (int i = 0; i < stages && mt < m_tiles; ++i) load_a();
-      mbar_expect_tx(wfull, (uint32_t)(num_kb * L.w_bytes_kb));
-      for (int k2 = 0; k2 < num_kb; ++k2) {
-        tma_load_2d(L.w(k2), &map_w0, wfull, k2 * kBlockK, 0);
-        if (n_b > 0) tma_load_2d(L.w(k2) + n_a * kBlockK * 2, &map_w1, wfull, k2 * kBlockK, n_a);
-      }
-      while (mt < m_tiles) load_a();
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(wfull, 0);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
-        mbar_wait(tempty, (uint32_t)(it & 1) ^ 1);      // the epilogue has drained the previous tile
-        tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full(stage), phase);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t ad = make_desc_sw128(L.a(stage) + k * 32, 16, 1024);
-            const uint64_t bd0 = make_desc_sw128(L.w(kb) + k * 32, 16, 1024);
-            umma_bf16(tmem_base, ad, bd0, idesc_a, (kb | k) != 0);
-            if (n_b > 0) {
-              const uint64_t bd1 = make_desc_sw128(L.w(kb) + n_a * kBlockK * 2 + k * 32, 16, 1024);
-              umma_bf16(tmem_base + n_a, ad, bd1, idesc_b, (kb | k) != 0);
-            }
-          }
-          umma_commit(empty(stage));
-          if (++stage == stages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(tfull);
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int n_chunks = (n_a + n_b + 31) / 32;
-    int it = 0;
-    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
-      mbar_wait(tfull, (uint32_t)(it & 1));
-      tc_fence_after();
-      const int row = mt * kBlockM + q * 32 + lane;
-      const bool row_ok = row < M;
-      TC* crow = C + (int64_t)(row_ok ? row : 0) * ldc;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-      uint32_t ra[32], rb[32];
-      int ci = half;
-      if (ci < n_chunks) tmem_ld_32x32_nowait(tbase + ci * 32, ra);
-      while (ci < n_chunks) {
-        tmem_wait_ld();
-        const int nxt = ci + 2;
-        if (nxt < n_chunks) tmem_ld_32x32_nowait(tbase + nxt * 32, rb);
-        if (row_ok && ci * 32 < ldc) epilogue_chunk<TC>(ra, ci * 32, Nout, ldc, act, bias_s, crow);
-        ci = nxt;
-        if (ci >= n_chunks) break;
-        tmem_wait_ld();
-        const int nx2 = ci + 2;
-        if (nx2 < n_chunks) tmem_ld_32x32_nowait(tbase + nx2 * 32, ra);
-        if (row_ok && ci * 32 < ldc) epilogue_chunk<TC>(rb, ci * 32, Nout, ldc, act, bias_s, crow);
-        ci = nx2;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// linear_wsc : linear_ws for n_tiles == 2 as a 2-CTA thread-block cluster.  The two CTAs of a cluster own
-// the two N halves of the SAME M tiles, so they need the same activation tiles: each CTA loads HALF of
-// every [128 x 64] activation box (64 rows) and the TMA MULTICASTS it into both CTAs' shared memory.  Every
-// activation byte then crosses L2 -> SM once instead of twice.  A stage is refilled only after BOTH CTAs'
-// MMAs have consumed it: tcgen05.commit arrives (multicast) on the empty barrier of both CTAs (count 2).
-// ---------------------------------------------------------------------------------------------
-template <typename TC>
-__global__ void __launch_bounds__(kLinThreads, 1)
-linear_wsc_kernel(const __grid_constant__ CUtensorMap map_a_half, const __grid_constant__ CUtensorMap map_w,
-                  int M, int K, int Nout, int block_n, int m_tiles, int stages, uint32_t idesc,
-                  const float* __restrict__ bias, int act, TC* __restrict__ C, int64_t ldc) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  WsLayout L;
-  L.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  L.num_kb = (K + kBlockK - 1) / kBlockK;
-  L.w_bytes_kb = block_n * kBlockK * 2;
-  L.stages = stages;
-  const int num_kb = L.num_kb;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* bias_s = reinterpret_cast<float*>(smem_raw + (L.bias() - smem_u32(smem_raw)));
-  const uint32_t rank = cluster_ctarank();                  // = N half of this CTA
-  const int n0 = (int)rank * block_n;
-  const int m_first = blockIdx.x >> 1, m_step = gridDim.x >> 1;
-
-  for (int i = threadIdx.x; i < kMaxBias; i += kLinThreads) bias_s[i] = (bias && i < Nout) ? bias[i] : 0.f;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a_half);
-    tma_prefetch_desc(&map_w);
-    for (int s = 0; s < stages; ++s) { mbar_init(L.full(s), 1); mbar_init(L.empty(s), 2); }
-    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull(s), 1); mbar_init(L.tempty(s), 8); }
-    mbar_init(L.wfull(), 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(L.tmem_slot(), kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                      // the peer's barriers exist before anything is multicast to them
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(L.tmem_slot()));
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(L.wfull(), (uint32_t)(num_kb * L.w_bytes_kb));
-      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(L.w(kb), &map_w, L.wfull(), kb * kBlockK, n0);
-      int stage = 0; uint32_t phase = 0;
-      for (int mt = m_first; mt < m_tiles; mt += m_step) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(L.empty(stage), phase ^ 1);
-          mbar_expect_tx(L.full(stage), kABytes);            // my half + the peer's half
-          tma_load_2d_mc(L.a(stage) + rank * (kABytes / 2), &map_a_half, L.full(stage), kb * kBlockK,
-                         mt * kBlockM + (int)rank * (kBlockM / 2), (uint16_t)0x3);
-          if (++stage == stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(L.wfull(), 0);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int mt = m_first; mt < m_tiles; mt += m_step, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(L.tempty(as), aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccStride;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(L.full(stage), phase);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t ad = make_desc_sw128(L.a(stage) + k * 32, 16, 1024);
-            const uint64_t bd = make_desc_sw128(L.w(kb) + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
-          }
-          umma_commit_mc(L.empty(stage), (uint16_t)0x3);     // release the stage in BOTH CTAs
-          if (++stage == stages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(L.tfull(as));
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int n_chunks = (block_n + 31) / 32;
-    int it = 0;
-    for (int mt = m_first; mt < m_tiles; mt += m_step, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(L.tfull(as), aphase);
-      tc_fence_after();
-      const int row = mt * kBlockM + q * 32 + lane;
-      const bool row_ok = row < M;
-      TC* crow = C + (int64_t)(row_ok ? row : 0) * ldc;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride;
-      uint32_t ra[32], rb[32];
-      int ci = half;
-      if (ci < n_chunks) tmem_ld_32x32_nowait(tbase + ci * 32, ra);
-      while (ci < n_chunks) {
-        tmem_wait_ld();
-        const int nxt = ci + 2;
-        if (nxt < n_chunks) tmem_ld_32x32_nowait(tbase + nxt * 32, rb);
-        if (row_ok && n0 + ci * 32 < ldc) epilogue_chunk<TC>(ra, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
-        ci = nxt;
-        if (ci >= n_chunks) break;
-        tmem_wait_ld();
-        const int nx2 = ci + 2;
-        if (nx2 < n_chunks) tmem_ld_32x32_nowait(tbase + nx2 * 32, ra);
-        if (row_ok && n0 + ci * 32 < ldc) epilogue_chunk<TC>(rb, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
-        ci = nx2;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(L.tempty(as));
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-  cluster_sync_all();                      // no CTA leaves while its peer may still signal its barriers
-}
-
-// ---------------------------------------------------------------------------------------------
 // wgrad_tc : both operands MN-major (rows of the activation matrices are the GEMM K dimension)
 //   smem stage = 64 activation rows; A = 2 boxes [64 rows x 64 cols], B = block_n/64 such boxes.
 //   canonical MN-major SWIZZLE_128B layout: 64-column atom contiguous (128 B), 8-row groups
@@ -1084,12 +817,7 @@ static int pick_block_n(int Nout, int granule, int* n_tiles) {
 template <typename TC>
 static int launch_linear_tc_t(const CUtensorMap& ma, const CUtensorMap& mw, int M, int K, int Nout, int block_n,
                               int n_tiles, const float* bias, int act, void* C, int64_t ldc, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(linear_tc_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
+  if (int rc_ = ensure_dyn_smem((const void*)linear_tc_kernel<TC>, kSmemBytes)) return rc_;
   const int m_tiles = (M + kBlockM - 1) / kBlockM;
   const int num_tiles = m_tiles * n_tiles;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
@@ -1103,12 +831,7 @@ template <typename TC>
 static int launch_linear_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, int M, int K, int Nout, int block_n,
                               int n_tiles, int stages, size_t smem, const float* bias, int act, void* C, int64_t ldc,
                               cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(linear_ws_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
+  if (int rc_ = ensure_dyn_smem((const void*)linear_ws_kernel<TC>, 227 * 1024)) return rc_;
   const int m_tiles = (M + kBlockM - 1) / kBlockM;
   int groups = kNumSMs / n_tiles;                 // CTAs per N tile
   if (groups > m_tiles) groups = m_tiles;
@@ -1116,68 +839,6 @@ static int launch_linear_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, int 
   linear_ws_kernel<TC><<<groups * n_tiles, kLinThreads, smem, s>>>(ma, mw, M, K, Nout, block_n, n_tiles, m_tiles, stages,
                                                                     idesc, bias, act, (TC*)C, ldc);
   return check_launch();
-}
-
-template <typename TC>
-static int launch_linear_wsc_t(const CUtensorMap& ma_half, const CUtensorMap& mw, int M, int K, int Nout, int block_n,
-                               int stages, size_t smem, const float* bias, int act, void* C, int64_t ldc, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(linear_wsc_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
-  const int m_tiles = (M + kBlockM - 1) / kBlockM;
-  int clusters = kNumSMs / 2;
-  if (clusters > m_tiles) clusters = m_tiles;
-  const uint32_t idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kLinThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TC* Cp = (TC*)C;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, linear_wsc_kernel<TC>, ma_half, mw, M, K, Nout, block_n, m_tiles, stages, idesc,
-                                     bias, act, Cp, ldc);
-  if (e != cudaSuccess) { set_cuda_error(e); return EDG_ERR_CUDA; }
-  return check_launch();
-}
-// Opt-in (EDG_LINEAR_CLUSTER=1): correct (whole GPU suite passes with it) but measured neutral at C2 (43.0 vs
-// 43.2 us) -- at cluster size 2 a multicast TMA load costs L2 as much as two unicast loads.
-static bool cluster_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("EDG_LINEAR_CLUSTER"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
-template <typename TC>
-static int launch_linear_wf_t(const CUtensorMap& ma, const CUtensorMap& mw0, const CUtensorMap& mw1, int M, int K, int Nout,
-                              int n_a, int n_b, int stages, int nbias, size_t smem, const float* bias, int act, void* C,
-                              int64_t ldc, cudaStream_t s) {
-  static size_t seen = 0;
-  if (smem > seen) {
-    if (cudaFuncSetAttribute(linear_wf_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch();
-    seen = smem;
-  }
-  const int m_tiles = (M + kBlockM - 1) / kBlockM;
-  const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
-  linear_wf_kernel<TC><<<grid, kLinThreads, smem, s>>>(ma, mw0, mw1, M, K, Nout, n_a, n_b, m_tiles, stages, nbias,
-                                                       make_idesc_bf16(kBlockM, n_a, 0, 0),
-                                                       make_idesc_bf16(kBlockM, n_b > 0 ? n_b : 16, 0, 0), bias, act, (TC*)C, ldc);
-  return check_launch();
-}
-// Opt-in (EDG_LINEAR_WF=1): correct, but measured SLOWER at C2 (54 us vs 43 us for linear_ws): with 190 KB of weights
-// resident only two activation stages fit and the single TMEM accumulator serialises MMA and epilogue.
-static bool wf_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("EDG_LINEAR_WF"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
 }
 
 // bring-up switch: EDG_LINEAR_WS=0 forces the streaming kernel
@@ -1197,32 +858,6 @@ int launch_linear_tc(const void* A, int64_t lda, int M, int K, const void* W, in
   if (rc) return rc;
   rc = make_map_bf16(&mw, W, Nout, K, ldw, kBlockK, block_n);
   if (rc) return rc;
-  // whole weight resident (activations cross L2 -> SM once) when it fits next to >= 2 activation stages
-  {
-    const int num_kb = (K + kBlockK - 1) / kBlockK;
-    const int total_n = ((Nout + 15) / 16) * 16;
-    const int nbias = ((total_n + 31) / 32) * 32;
-    const size_t w_bytes = (size_t)num_kb * total_n * kBlockK * 2;
-    const size_t fixed = 1024 + (size_t)nbias * 4 + 256;
-    const size_t budget = 227 * 1024;
-    if (wf_enabled() && ws_enabled() && total_n <= 512 && n_tiles >= 2 && w_bytes + fixed + 2 * kABytes <= budget &&
-        M >= 4 * kBlockM) {
-      int stages = (int)((budget - fixed - w_bytes) / kABytes);
-      if (stages > kWsMaxStages) stages = kWsMaxStages;
-      const size_t smem = fixed + w_bytes + (size_t)stages * kABytes;
-      int n_a = ((total_n / 2 + 15) / 16) * 16;
-      if (total_n <= 256) n_a = total_n;
-      const int n_b = total_n - n_a;
-      CUtensorMap mw0, mw1;
-      rc = make_map_bf16(&mw0, W, Nout, K, ldw, kBlockK, n_a);
-      if (rc) return rc;
-      rc = make_map_bf16(&mw1, W, Nout, K, ldw, kBlockK, n_b > 0 ? n_b : 16);
-      if (rc) return rc;
-      if (c_dtype == EDG_F32) return launch_linear_wf_t<float>(ma, mw0, mw1, M, K, Nout, n_a, n_b, stages, nbias, smem, bias, act, C, ldc, s);
-      if (c_dtype == EDG_BF16) return launch_linear_wf_t<__nv_bfloat16>(ma, mw0, mw1, M, K, Nout, n_a, n_b, stages, nbias, smem, bias, act, C, ldc, s);
-      return EDG_ERR_DTYPE;
-    }
-  }
   // weight-stationary variant when one N tile of the weight plus >= 4 activation stages fit in shared memory
   {
     const int num_kb = (K + kBlockK - 1) / kBlockK;
@@ -1233,15 +868,6 @@ int launch_linear_tc(const void* A, int64_t lda, int M, int K, const void* W, in
       int stages = (int)((budget - fixed - w_bytes) / kABytes);
       if (stages > kWsMaxStages) stages = kWsMaxStages;
       const size_t smem = fixed + w_bytes + (size_t)stages * kABytes;
-      if (n_tiles == 2 && cluster_enabled() && M >= 8 * kBlockM) {
-        // 2-CTA cluster: each CTA loads half of every activation box and multicasts it to its peer
-        CUtensorMap mah;
-        rc = make_map_bf16(&mah, A, M, K, lda, kBlockK, kBlockM / 2);
-        if (rc) return rc;
-        if (c_dtype == EDG_F32) return launch_linear_wsc_t<float>(mah, mw, M, K, Nout, block_n, stages, smem, bias, act, C, ldc, s);
-        if (c_dtype == EDG_BF16) return launch_linear_wsc_t<__nv_bfloat16>(mah, mw, M, K, Nout, block_n, stages, smem, bias, act, C, ldc, s);
-        return EDG_ERR_DTYPE;
-      }
       if (c_dtype == EDG_F32) return launch_linear_ws_t<float>(ma, mw, M, K, Nout, block_n, n_tiles, stages, smem, bias, act, C, ldc, s);
       if (c_dtype == EDG_BF16) return launch_linear_ws_t<__nv_bfloat16>(ma, mw, M, K, Nout, block_n, n_tiles, stages, smem, bias, act, C, ldc, s);
       return EDG_ERR_DTYPE;
@@ -1313,21 +939,11 @@ size_t wgrad_tc_workspace(int R, int K1, int K2) {
 
 int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, float* dW,
                     int64_t lddw, float* dbias, int bias_of, int accumulate, float* ws, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
+  if (int rc_ = ensure_dyn_smem((const void*)wgrad_tc_kernel, kSmemBytes)) return rc_;
   const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
   const TallPlan t = plan_wgrad_tall(R, K1e, K2e);
   if (t.ok && tall_enabled()) {
-    static bool tall_attr = false;
-    if (!tall_attr) {
-      if (cudaFuncSetAttribute(wgrad_tall_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTallSmem) != cudaSuccess)
-        return check_launch();
-      tall_attr = true;
-    }
+    if (int rc_ = ensure_dyn_smem((const void*)wgrad_tall_kernel, kTallSmem)) return rc_;
     CUtensorMap ma, mb;
     int rc = make_map_bf16(&ma, A, R, K1, lda, 64, kBlockK);
     if (rc) return rc;
@@ -1372,12 +988,7 @@ size_t wgrad_tc_batch_workspace(int n, int R, int K1, int K2) {
 int launch_wgrad_tc_batch(int n, const void* const* A, int64_t lda, int K1, const void* const* B, int64_t ldb, int K2, int R,
                           float* const* dW, int64_t lddw, float* const* dbias, int bias_of, float* ws, cudaStream_t s) {
   if (n > kWgradBatchMax) return EDG_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_tc_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
+  if (int rc_ = ensure_dyn_smem((const void*)wgrad_tc_batch_kernel, kSmemBytes)) return rc_;
   const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
   WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
   // the problems share the SMs: fewer row splits per problem keep the partial-sum traffic down

@@ -299,7 +299,7 @@ extern "C" int edg_fc_head_fwd(const float* logits, int64_t ldl, const float* fc
   cudaStream_t s = (cudaStream_t)stream;
   auto launch = [&](auto kern, int CP) -> int {
     const size_t smem = (size_t)CP * kHeadPitch * sizeof(float);
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
+    if (int rc_ = ensure_dyn_smem((const void*)kern, smem)) return rc_;
     kern<<<grid, kHeadThreads, smem, s>>>(logits, ldl, fc_w, ldw, fc_b, a, lda, B, D, C, vec4, v, c);
     return check_launch();
   };
@@ -344,7 +344,7 @@ extern "C" int edg_fc_head_bwd(const float* logits, int64_t ldl, const float* fc
   const int vec4 = ((D & 3) == 0 && (ldw & 3) == 0 && (lda & 3) == 0 && aligned16(fc_w) && aligned16(a) && aligned16(dv)) ? 1 : 0;
   auto launch = [&](auto kern, int CP) -> int {
     const size_t smem = (size_t)(CP + kHeadGraphs) * kHeadPitch * sizeof(float);
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
+    if (int rc_ = ensure_dyn_smem((const void*)kern, smem)) return rc_;
     kern<<<dim3(blocks, 2), kHeadThreads, smem, s>>>(logits, ldl, fc_w, ldw, fc_b, a, lda, dv, dc, scale, B, D, C, vec4, parts,
                                                       dlg_part, d_a, partial);
     return check_launch();

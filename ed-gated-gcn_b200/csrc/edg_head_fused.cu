@@ -16,8 +16,9 @@
 
 namespace edg {
 
-constexpr int kHdThreads = 256;
+constexpr int kHdThreads = 512;
 constexpr int kHdMaxD = 320;
+constexpr int kHdCtasPerSm = 2;
 
 struct HeadDuParams {
   const int32_t* tile_info; const int32_t* n_tiles;
@@ -31,62 +32,80 @@ struct HeadDuParams {
   int D, B;
 };
 
-__global__ void __launch_bounds__(kHdThreads, 8)
+// Shared memory (dynamic): the tile of du rows in bf16 with the GLOBAL row pitch (so that it leaves as one contiguous
+// block of 16-byte stores), the per-sentence vectors, and the tile's CSR slice.
+struct HeadDuSmem {
+  float q[kFMaxSent][kHdMaxD];          // gate o v
+  float pg[kFMaxSent][kHdMaxD];         // gate o g_pooled / (deg_arg + 1)
+  uint8_t arg[kFMaxSent][kHdMaxD];      // tile-local arg-max row (0xff = none)
+  uint16_t rp[kFRows + 8];
+  uint8_t cl[kFMaxNnz];
+  float ds[kFRows], dsa[kFRows], dsagg[kFRows], dsum[kFMaxSent];
+  uint8_t srow[kFRows];                 // sentence (tile-local) of each row
+  uint8_t sfirst[kFMaxSent + 8];
+};
+
+// One tile = a run of whole sentences (edg_tile_plan).  Phases (block barriers in between):
+//   0  CSR slice, ds_t, sentence starts                      (coalesced global loads)
+//   1  per row: ds_t / (deg_t + 1), sentence id
+//   2  per row: dsagg_i = sum_{j in N(i)} ds_j / (deg_j + 1);  per (sentence, column): q = g o v, pg, arg, dgate
+//   3  base rows  tile[i][:] = dsagg_i * q_s(i)[:]            thread = (16-byte chunk, row slice);  bias partials
+//   4  patch      tile[j][c] += pg[s][c] for j in N(arg[s][c])  thread = (sentence, column): ~3 rows each, no conflicts
+//   5  tile -> global, 16 bytes per thread, contiguous
+__global__ void __launch_bounds__(kHdThreads, kHdCtasPerSm)
 head_du_kernel(const HeadDuParams P) {
-  __shared__ __align__(16) float q_s[kFMaxSent][kHdMaxD];       // g o v
-  __shared__ __align__(16) float pg_s[kFMaxSent][kHdMaxD];      // g o gp / (deg_arg + 1)
-  __shared__ __align__(16) uint8_t arg_s[kFMaxSent][kHdMaxD];   // tile-local arg-max row (0xff = none)
-  __shared__ __align__(16) uint4 meta_s[kFRows];                // neighbour ids | deg, sentence | first CSR entry
-  __shared__ uint16_t rp_s[kFRows + 8];
-  __shared__ uint8_t cl_s[kFMaxNnz];
-  __shared__ float ds_s[kFRows], dsa_s[kFRows], dsum_s[kFMaxSent];
-  __shared__ uint8_t sfirst_s[kFMaxSent + 8];
+  extern __shared__ __align__(16) uint8_t hd_smem[];
+  HeadDuSmem& S = *reinterpret_cast<HeadDuSmem*>(hd_smem);
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(hd_smem + ((sizeof(HeadDuSmem) + 15) & ~(size_t)15));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = P.D;
+  const int ldt = (int)P.lddu;                        // tile pitch = global pitch (elements)
   const int n_tiles = __ldg(P.n_tiles);
   const float gkl = P.g_kl ? __ldg(P.g_kl) : 0.f;
-  const int nch = (D + 7) >> 3;                       // 8-column chunks per row
-  float dbacc[2] = {0.f, 0.f};                        // columns tid and tid + 256
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int s0 = __ldg(P.tile_info + 8 * t), s1 = __ldg(P.tile_info + 8 * t + 1);
-    const int r0 = __ldg(P.tile_info + 8 * t + 2), r1 = __ldg(P.tile_info + 8 * t + 3);
-    const int e0 = __ldg(P.tile_info + 8 * t + 4), e1 = __ldg(P.tile_info + 8 * t + 5);
+  const int nch = ldt >> 3;                           // 16-byte chunks per row (padding columns included: written as zeros)
+  const int nsl = kHdThreads / nch;
+  const int sl = tid / nch, k8 = tid - sl * nch;
+  float dbacc = 0.f;                                  // column tid (D <= kHdThreads)
+  int t = blockIdx.x;
+  int4 ti0 = make_int4(0, 0, 0, 0); int2 ti1 = make_int2(0, 0);
+  if (t < n_tiles) { ti0 = __ldg(reinterpret_cast<const int4*>(P.tile_info + 8 * t)); ti1 = __ldg(reinterpret_cast<const int2*>(P.tile_info + 8 * t + 4)); }
+  for (; t < n_tiles; t += gridDim.x) {
+    const int s0 = ti0.x, s1 = ti0.y, r0 = ti0.z, r1 = ti0.w, e0 = ti1.x, e1 = ti1.y;
     const int n = r1 - r0, ns = s1 - s0, nnz = min(e1 - e0, kFMaxNnz);
-    __syncthreads();                                  // the previous tile's readers are done
-    // ---- raw CSR slice, ds, sentence starts (coalesced; one latency round)
-    for (int i = tid; i <= n; i += kHdThreads) rp_s[i] = (uint16_t)(__ldg(P.row_ptr + r0 + i) - e0);
-    for (int i = tid; i < nnz; i += kHdThreads) cl_s[i] = (uint8_t)(__ldg(P.col + e0 + i) - r0);
+    const int tn = t + gridDim.x;                     // the next tile's header is in flight during this tile
+    if (tn < n_tiles) { ti0 = __ldg(reinterpret_cast<const int4*>(P.tile_info + 8 * tn)); ti1 = __ldg(reinterpret_cast<const int2*>(P.tile_info + 8 * tn + 4)); }
+    // ---- 0
+    for (int i = tid; i <= n; i += kHdThreads) S.rp[i] = (uint16_t)(__ldg(P.row_ptr + r0 + i) - e0);
+    for (int i = tid; i < nnz; i += kHdThreads) S.cl[i] = (uint8_t)(__ldg(P.col + e0 + i) - r0);
     for (int i = tid; i < n; i += kHdThreads) {
       float d = gkl * __ldg(P.u_unit + r0 + i);
       if (P.g_scores) d += __ldg(P.g_scores + r0 + i);
-      ds_s[i] = d;
+      S.ds[i] = d;
     }
-    if (tid <= ns) sfirst_s[tid] = (uint8_t)(__ldg(P.sent_ptr + s0 + tid) - r0);
+    if (tid <= ns) S.sfirst[tid] = (uint8_t)(__ldg(P.sent_ptr + s0 + tid) - r0);
     __syncthreads();
-    // ---- per row: neighbour word (self first, unused = 0xff) and ds_i / (deg_i + 1)
+    // ---- 1
     for (int i = tid; i < n; i += kHdThreads) {
-      const int e_beg = rp_s[i], deg = rp_s[i + 1] - e_beg;
-      uint64_t ids = (0xffffffffffffff00ull) | (uint64_t)i;
-      int cnt = 0;
-      for (int qq = 0; qq < 8 && qq < deg; ++qq) {
-        const uint32_t j = cl_s[e_beg + qq];
-        if ((int)j != i && cnt < 7) { ++cnt; ids = (ids & ~(0xffull << (8 * cnt))) | ((uint64_t)j << (8 * cnt)); }
-      }
+      const int deg = S.rp[i + 1] - S.rp[i];
+      S.dsa[i] = S.ds[i] * __frcp_rn((float)(deg + 1));
       int s = 0;
-      for (int qq = 1; qq < ns; ++qq) s += (sfirst_s[qq] <= i) ? 1 : 0;
-      meta_s[i] = make_uint4((uint32_t)ids, (uint32_t)(ids >> 32), (uint32_t)deg | ((uint32_t)s << 8), (uint32_t)e_beg);
-      dsa_s[i] = ds_s[i] * __frcp_rn((float)(deg + 1));
-    }
-    // sum_t ds_t per sentence (fixed order)
-    if (warp < ns) {
-      const int s = warp;
-      float a = 0.f;
-      for (int i = sfirst_s[s] + lane; i < sfirst_s[s + 1]; i += 32) a += ds_s[i];
-      a = warp_sum(a);
-      if (lane == 0) dsum_s[s] = a;
+      for (int qq = 1; qq < ns; ++qq) s += (S.sfirst[qq] <= i) ? 1 : 0;
+      S.srow[i] = (uint8_t)s;
     }
     __syncthreads();
-    // ---- per-sentence vectors -> shared memory; dgate and the bias-gradient partials on the way
+    // ---- 2
+    if (tid < n) {
+      const int i = tid;
+      float a = 0.f;
+      for (int e = S.rp[i]; e < S.rp[i + 1]; ++e) a += S.dsa[S.cl[e]];
+      S.dsagg[i] = a;
+    } else if (warp >= kFRows / 32 && warp - kFRows / 32 < ns) {      // sum_t ds_t per sentence (fixed order)
+      const int s = warp - kFRows / 32;
+      float a = 0.f;
+      for (int i = S.sfirst[s] + lane; i < S.sfirst[s + 1]; i += 32) a += S.ds[i];
+      a = warp_sum(a);
+      if (lane == 0) S.dsum[s] = a;
+    }
     for (int idx = tid; idx < ns * D; idx += kHdThreads) {
       const int s = idx / D, d = idx - s * D;
       const int64_t o = (int64_t)(s0 + s) * D + d;
@@ -94,95 +113,72 @@ head_du_kernel(const HeadDuParams P) {
       const float gp = P.gp ? __ldg(P.gp + o) : 0.f;
       const int a = (P.gp && P.arg) ? __ldg(P.arg + o) - r0 : -1;
       const bool has = a >= 0 && a < n;
-      const float qv = g * vv, gg = g * gp;
-      q_s[s][d] = qv;
-      float pg = 0.f;
-      if (has) pg = gg * __frcp_rn((float)(rp_s[a + 1] - rp_s[a] + 1));
-      pg_s[s][d] = pg;
-      arg_s[s][d] = has ? (uint8_t)a : (uint8_t)0xff;
+      S.q[s][d] = g * vv;
+      S.pg[s][d] = has ? g * gp : 0.f;                 // un-scaled here (the bias gradient wants it); phase 4 scales
+      S.arg[s][d] = has ? (uint8_t)a : (uint8_t)0xff;
       if (P.dgate) P.dgate[o] = fmaf(gkl * vv, __ldg(P.sf_unit + o), gp * __ldg(P.hmax + o));
     }
-    // bias gradient: thread = column, sentences in order (deterministic)
-    __syncthreads();
-    for (int c = 0; c < 2; ++c) {
-      const int d = tid + c * kHdThreads;
-      if (d < D) {
-        float a = dbacc[c];
-        for (int s = 0; s < ns; ++s) {
-          const uint8_t ar = arg_s[s][d];
-          float gg = 0.f;
-          if (ar != 0xff) gg = pg_s[s][d] * (float)(rp_s[ar + 1] - rp_s[ar] + 1);
-          a += fmaf(dsum_s[s], q_s[s][d], gg);
-        }
-        dbacc[c] = a;
-      }
-    }
-    // ---- aggregated row scalars: dsagg_i = sum_{j in N(i)} ds_j / (deg_j + 1)   (overwrites ds_s)
-    for (int i = tid; i < n; i += kHdThreads) {
-      const uint4 m = meta_s[i];
-      const int deg = m.z & 0xff;
-      float a = 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const uint32_t j = (m.x >> (8 * u)) & 0xff; if (j != 0xff) a += dsa_s[j]; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const uint32_t j = (m.y >> (8 * u)) & 0xff; if (j != 0xff) a += dsa_s[j]; }
-      if (deg > 8) {
-        int cnt = 0;
-        for (int e = 0; e < deg; ++e) {
-          const int j = cl_s[m.w + e];
-          if (j == i) continue;
-          if (cnt++ < 7) continue;
-          a += dsa_s[j];
-        }
-      }
-      ds_s[i] = a;
+    if (D < ldt) {                                      // padding columns of q: the base rows write zeros there
+      for (int idx = tid; idx < ns * (ldt - D); idx += kHdThreads) { const int s = idx / (ldt - D); S.q[s][D + idx - s * (ldt - D)] = 0.f; }
     }
     __syncthreads();
-    // ---- rows: thread = (row, 8-column chunk)
-    for (int task = tid; task < n * nch; task += kHdThreads) {
-      const int i = task / nch, k8 = task - i * nch;
-      const uint4 m = meta_s[i];
-      const int deg = m.z & 0xff, s = (m.z >> 8) & 0xff;
-      const float dsi = ds_s[i];
-      const float4 q0 = *reinterpret_cast<const float4*>(&q_s[s][8 * k8]), q1 = *reinterpret_cast<const float4*>(&q_s[s][8 * k8 + 4]);
-      const float4 p0 = *reinterpret_cast<const float4*>(&pg_s[s][8 * k8]), p1 = *reinterpret_cast<const float4*>(&pg_s[s][8 * k8 + 4]);
-      const uint2 ab = *reinterpret_cast<const uint2*>(&arg_s[s][8 * k8]);
-      const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-      const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-      float o[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t a = ((k < 4 ? ab.x : ab.y) >> (8 * (k & 3))) & 0xffu;
-        const uint32_t rep = a * 0x01010101u;
-        bool hit = (__vcmpeq4(m.x, rep) | __vcmpeq4(m.y, rep)) != 0u;       // arg-max row among the first 8 entries of N(i)
-        if (deg > 8 && !hit && a != 0xffu) {
-          int cnt = 0;
-          for (int e = 0; e < deg; ++e) {
-            const uint32_t j = cl_s[m.w + e];
-            if ((int)j == i) continue;
-            if (cnt++ < 7) continue;
-            hit |= (j == a);
-          }
+    // ---- 3
+    if (sl < nsl) {
+      int cur_s = -1;
+      float qv[8];
+      for (int i = sl; i < n; i += nsl) {
+        const int s = S.srow[i];
+        if (s != cur_s) {
+          cur_s = s;
+          const float4 q0 = *reinterpret_cast<const float4*>(&S.q[s][8 * k8]), q1 = *reinterpret_cast<const float4*>(&S.q[s][8 * k8 + 4]);
+          qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
         }
-        o[k] = fmaf(dsi, qv[k], (hit && a != 0xffu) ? pv[k] : 0.f);
-        if (8 * k8 + k >= D) o[k] = 0.f;
+        const float dsi = S.dsagg[i];
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = dsi * qv[k];
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]); w[k] = *reinterpret_cast<uint32_t*>(&h); }
+        *reinterpret_cast<uint4*>(tile + (size_t)i * ldt + 8 * k8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      Vec16<__nv_bfloat16>::store(P.du + (int64_t)(r0 + i) * P.lddu + 8 * k8, o);
     }
-  }
-  if (P.db_part) {
-    for (int c = 0; c < 2; ++c) {
-      const int d = tid + c * kHdThreads;
-      if (d < D) P.db_part[(int64_t)blockIdx.x * D + d] = dbacc[c];
+    if (tid < D) {                                      // bias gradient: thread = column, sentences in order (deterministic)
+      float a = dbacc;
+      for (int s = 0; s < ns; ++s) a += fmaf(S.dsum[s], S.q[s][tid], S.pg[s][tid]);
+      dbacc = a;
     }
+    __syncthreads();
+    // ---- 4
+    for (int idx = tid; idx < ns * D; idx += kHdThreads) {
+      const int s = idx / D, d = idx - s * D;
+      const int a = S.arg[s][d];
+      if (a != 0xff) {
+        const int eb = S.rp[a], ee = S.rp[a + 1];
+        const float pgv = S.pg[s][d] * __frcp_rn((float)(ee - eb + 1));
+        for (int e = eb; e < ee; ++e) {
+          __nv_bfloat16* p = tile + (size_t)S.cl[e] * ldt + d;
+          *p = __float2bfloat16_rn(__bfloat162float(*p) + pgv);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 5
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(tile);
+      uint4* dst = reinterpret_cast<uint4*>(P.du + (int64_t)r0 * P.lddu);
+      const int total = n * nch;
+      for (int i = tid; i < total; i += kHdThreads) dst[i] = src[i];
+    }
+    // (the next tile's phases 0-2 touch neither `tile` nor anything phase 5 reads; its phase 3 comes after three barriers)
   }
+  if (P.db_part && tid < D) P.db_part[(int64_t)blockIdx.x * D + tid] = dbacc;
 }
 
 }  // namespace edg
 
 using namespace edg;
 
-constexpr int kHdCtasPerSm = 8;      // latency-bound phases (five dependent rounds per tile): occupancy hides them
 extern "C" size_t edg_head_du_workspace(int32_t D) { return (size_t)kHdCtasPerSm * kNumSMs * (size_t)D * sizeof(float); }
 
 /* see include/edgcn.h */
@@ -196,7 +192,7 @@ extern "C" int edg_head_du(const float* u_unit, const float* g_kl, const float* 
   if (!u_unit || !gate || !v || !row_ptr || !col || !sent_ptr || !tile_info || !n_tiles || !du) return EDG_ERR_ARG;
   if (g_pooled && !arg) return EDG_ERR_ARG;
   if (dgate && (!sf_unit || !hmax)) return EDG_ERR_ARG;
-  if (D > kHdMaxD || D > 2 * kHdThreads) return EDG_ERR_UNSUPPORTED;
+  if (D > kHdMaxD || D > kHdThreads || lddu > kHdMaxD) return EDG_ERR_UNSUPPORTED;
   if (lddu < ((D + 7) / 8) * 8 || (lddu & 7) || !aligned16(du)) return EDG_ERR_ALIGN;
   const int grid = kHdCtasPerSm * kNumSMs;
   if (dbias && ws_bytes < (size_t)grid * D * sizeof(float)) return EDG_ERR_WORKSPACE;
@@ -206,7 +202,9 @@ extern "C" int edg_head_du(const float* u_unit, const float* g_kl, const float* 
   P.sf_unit = sf_unit; P.hmax = hmax; P.du = (__nv_bfloat16*)du; P.lddu = lddu; P.dgate = dgate;
   P.db_part = dbias ? (float*)ws : nullptr; P.D = D; P.B = B;
   cudaStream_t s = (cudaStream_t)stream;
-  head_du_kernel<<<grid, kHdThreads, 0, s>>>(P);
+  const size_t smem = ((sizeof(HeadDuSmem) + 15) & ~(size_t)15) + (size_t)kFRows * lddu * sizeof(__nv_bfloat16);
+  if (int rc_ = ensure_dyn_smem((const void*)head_du_kernel, smem)) return rc_;
+  head_du_kernel<<<grid, kHdThreads, smem, s>>>(P);
   int rc = check_launch();
   if (rc) return rc;
   if (dbias) {

@@ -275,12 +275,7 @@ extern "C" int edg_mlp_chain(int mode, int32_t n_groups, int32_t n_stages, const
   }
   const size_t smem = 1024 + (size_t)num_kb * kABytes + (size_t)kChainWStages * n_half * 256 +
                       (size_t)kChainMaxStages * kChainBiasPitch * 4 + 128;
-  static size_t seen = 0;
-  if (smem > seen) {
-    if (cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch();
-    seen = smem;
-  }
+  if (int rc_ = ensure_dyn_smem((const void*)mlp_chain_kernel, smem)) return rc_;
   const int m_tiles = (M + kBlockM - 1) / kBlockM;
   const uint32_t idesc = make_idesc_bf16(kBlockM, n_half, 0, 0);
   mlp_chain_kernel<<<dim3(m_tiles, n_groups), kChainThreads, smem, (cudaStream_t)stream>>>(P, M, D, n_stages, mode, n_half,

@@ -119,6 +119,23 @@ class _Side:
             self.dirty = False
 
 
+def _check_head_leaves(logits: torch.Tensor, inner, declared) -> None:
+    """``logits_fn`` may only depend on its two arguments and on the parameters passed as ``head_params``: anything else
+    would silently train with a zero gradient (the block is one autograd node; the head's graph lives inside it)."""
+    ok = {id(t) for t in inner} | {id(t) for t in declared}
+    seen, todo = set(), [logits.grad_fn]
+    while todo:
+        fn = todo.pop()
+        if fn is None or fn in seen:
+            continue
+        seen.add(fn)
+        var = getattr(fn, "variable", None)
+        if var is not None and var.requires_grad and id(var) not in ok:
+            raise L.EdgError("logits_fn depends on a trainable tensor that was not passed in head_params "
+                             f"(shape {tuple(var.shape)}): its gradient would be lost")
+        todo.extend(f for f, _ in fn.next_functions)
+
+
 StackOutput = namedtuple("StackOutput", ["logits", "xy", "kl", "scores", "pooled", "x_out", "pooled_arg", "view_arg"])
 
 
@@ -148,6 +165,8 @@ class _GatedStackFn(torch.autograd.Function):
                   for g in range(Lyr)]
         o += 2 * Lyr * pairs
         fc_w, fc_b = params[o], params[o + 1]
+        n_head = cfg["n_head"]                 # the caller's classifier-head parameters ride along as inputs (their gradients
+        params = params[:len(params) - n_head] if n_head else params     # are returned by backward: autograd accumulates them)
 
         # x is [N, D], or the whole padded allocation [N, pitch >= D] (then dx comes back in the same dense
         # layout and autograd can keep it without a copy)
@@ -271,6 +290,8 @@ class _GatedStackFn(torch.autograd.Function):
             a_leaf = a_raw.detach().requires_grad_(True)
             p_leaf = pooled.detach().requires_grad_(True)
             logits = logits_fn(a_leaf, p_leaf)
+        if logits.requires_grad and cfg["grad_enabled"]:
+            _check_head_leaves(logits, (a_leaf, p_leaf), cfg["head_params"])
         lg = logits.detach().float().contiguous()
         fcw32, fcb32 = fc_w.detach().float().contiguous(), fc_b.detach().float().contiguous()
         fc_sig = cfg["fc_sigmoid"]
@@ -301,6 +322,7 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.head = (a_leaf, p_leaf, logits, lg, a_raw, v)
         ctx.gate_saved = gate_saved
         ctx.n_params = len(params)
+        ctx.n_head = n_head
         ctx.x_dtype = x.dtype
         ctx.x_cols = x.shape[1]
         ctx.v_hmax = v_hmax
@@ -383,17 +405,17 @@ class _GatedStackFn(torch.autograd.Function):
                 _, _, d_fcw, d_fcb = ops.fc_head_bwd(lg, fcw32, fcb32, a_fc, dv_in, dc_in, scale, parts=2)
             if ctx.fc_sig:
                 da_fc = da_fc * a_fc * (1.0 - a_fc)                   # through sigmoid(a)
-            d_fcw, d_fcb = d_fcw.to(fc_w.dtype), d_fcb.to(fc_b.dtype)
             g_lg = d_lg if g_lg is None else g_lg + d_lg
         # ---- host head backward through logits_fn: d a, d pooled, and .grad of the parameters it closes over
         ga_head = gp_head = None
+        head_grads: List[Optional[torch.Tensor]] = [None] * ctx.n_head
         if g_lg is not None and logits.requires_grad:
-            cap = [p for p in cfg["head_params"] if p.requires_grad]
-            res = torch.autograd.grad([logits], [a_leaf, p_leaf] + cap, [g_lg.to(logits.dtype)], allow_unused=True)
+            cap = [(i, p) for i, p in enumerate(cfg["head_params"]) if p.requires_grad]
+            res = torch.autograd.grad([logits], [a_leaf, p_leaf] + [p for _, p in cap], [g_lg.to(logits.dtype)],
+                                      allow_unused=True, retain_graph=True)
             ga_head, gp_head = res[0], res[1]
-            for p, g in zip(cap, res[2:]):
-                if g is not None:
-                    p.grad = g if p.grad is None else p.grad + g
+            for (i, _), g in zip(cap, res[2:]):
+                head_grads[i] = g
         if da_fc is not None:
             ga_head = da_fc if ga_head is None else ga_head.float() + da_fc
         gp_total = g_pooled
@@ -566,6 +588,8 @@ class _GatedStackFn(torch.autograd.Function):
             da = da_gate if da is None else da + da_gate
         if da is not None:
             ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
+        if d_fcw is not None:                 # produced on the side stream: cast only after the join above
+            d_fcw, d_fcb = d_fcw.to(fc_w.dtype), d_fcb.to(fc_b.dtype)
         grads_out[-2], grads_out[-1] = d_fcw, d_fcb
         if ctx.x_padded:        # hand back the whole [N, pitch] allocation (padding columns are finite)
             dx = dx.as_strided((N, dx.stride(0)), (dx.stride(0), 1))
@@ -575,7 +599,7 @@ class _GatedStackFn(torch.autograd.Function):
                 dx = full
         if dx.dtype != ctx.x_dtype:
             dx = dx.to(ctx.x_dtype)
-        return (None, dx) + tuple(grads_out)
+        return (None, dx) + tuple(grads_out) + tuple(head_grads)
 
 
 class GatedGCNStack(nn.Module):
@@ -645,9 +669,11 @@ class GatedGCNStack(nn.Module):
             raise L.EdgError(f"expected {self.hidden} feature columns (or the padded pitch), got {x.shape[-1]}")
         cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
-                   head_params=list(head_params), relu=self.relu, return_x_out=return_x_out, gated=self.gated,
+                   head_params=list(head_params), n_head=len(list(head_params)), grad_enabled=torch.is_grad_enabled(),
+                   relu=self.relu, return_x_out=return_x_out, gated=self.gated,
                    drop_p=drop_p, seed=seed, fc_sigmoid=self.fc_sigmoid)
-        logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params())
+        logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params(),
+                                                                                 *cfg["head_params"])
         if shape3 is not None:
             scores = scores.reshape(shape3[0], shape3[1])
             if x_out is not None:

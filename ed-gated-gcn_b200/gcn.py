@@ -10,7 +10,7 @@ The dense adjacency is converted once per batch to a packed CSR (cached, so
 from __future__ import annotations
 
 import math
-from collections import OrderedDict
+import weakref
 from typing import Optional
 
 import torch
@@ -30,22 +30,20 @@ def _compute_dtype(x) -> torch.dtype:
     return _COMPUTE[str(x)]
 
 
-# adjacency -> CSR cache: the reference calls gc1(x, adj) and gc2(gcn1, adj) with the same
-# tensor (bert_amir5.py:626,639); key on storage identity + version so in-place edits miss.
-_GRAPH_CACHE: "OrderedDict[tuple, DepGraph]" = OrderedDict()
-_GRAPH_CACHE_SIZE = 8
+# adjacency -> CSR cache: the reference calls gc1(x, adj) and gc2(gcn1, adj) with the SAME tensor object
+# (bert_amir5.py:589, :626, :639).  Entries are tied to that object's lifetime (weak reference, identity checked on
+# every hit) and to its version counter, so neither a freed-and-reallocated block at the same address (train.py:108
+# makes a fresh `.to(device)` batch per step) nor an in-place edit can ever return a stale graph.
+_GRAPH_CACHE: "dict[int, tuple]" = {}
 
 
 def cached_graph_from_dense(adj: torch.Tensor) -> DepGraph:
-    key = (adj.data_ptr(), tuple(adj.shape), tuple(adj.stride()), adj.dtype, adj._version, adj.device.index)
-    g = _GRAPH_CACHE.get(key)
-    if g is None:
-        g = graph_from_dense(adj)
-        _GRAPH_CACHE[key] = g
-        while len(_GRAPH_CACHE) > _GRAPH_CACHE_SIZE:
-            _GRAPH_CACHE.popitem(last=False)
-    else:
-        _GRAPH_CACHE.move_to_end(key)
+    key = id(adj)
+    ent = _GRAPH_CACHE.get(key)
+    if ent is not None and ent[0]() is adj and ent[1] == adj._version:
+        return ent[2]
+    g = graph_from_dense(adj)
+    _GRAPH_CACHE[key] = (weakref.ref(adj, lambda _r, k=key: _GRAPH_CACHE.pop(k, None)), adj._version, g)
     return g
 
 

@@ -78,6 +78,9 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     return out
 
 
+FUSED_MAX_SENTENCES = 6     # sentences per tile of edg_tile_plan (kFMaxSent in csrc/edg_gcn_fused.cu)
+
+
 def fused_tile_rows(K: int, Nout: int) -> int:
     """Rows per tile the fused layer kernel supports for this shape (0: shape not covered)."""
     return int(L.load().edg_fused_tile_rows(K, Nout))
@@ -104,7 +107,7 @@ def gcn_layer(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], gr
     L.call("edg_gcn_layer", L.ptr(x), ld(x), N, K, L.ptr(w), ld(w), Nout, L.ptr(bias), int(mode), L.ptr(graph.row_ptr),
            L.ptr(graph.col), L.ptr(graph.sent_ptr), L.ptr(info), L.ptr(n_tiles), int(tile_rows), L.ptr(y), ld(y),
            L.ptr(hmax), L.ptr(harg), Nout, L.ptr(pv), L.ptr(pa), pv.stride(0) if pv is not None else 0, L.ptr(colsum), 0,
-           L.ptr(ws), ws.numel() * 4 if ws is not None else 0, L.stream())
+           L.ptr(ws), ws.numel() * 4 if ws is not None else 0, L.ptr(graph.row_meta()), L.stream())
     return y, hmax, harg, colsum
 
 

@@ -159,7 +159,12 @@ int edg_gcn_layer(const void* x, int64_t ldx, int32_t N, int32_t K, const void* 
                   const int32_t* sent_ptr, const int32_t* tile_info, const int32_t* n_tiles, int32_t tile_rows,
                   void* y, int64_t ldy, float* hmax, int32_t* harg, int64_t ldpool, const float* patch_val,
                   const int32_t* patch_arg, int64_t ldpatch, float* colsum, int colsum_accumulate, void* ws,
-                  size_t ws_bytes, edg_stream stream);
+                  size_t ws_bytes, const void* row_meta, edg_stream stream);
+/* row_meta [N][2] 16-byte words for edg_gcn_layer, 32 bytes per packed row: the sentence-local ids (u8) of the row itself and
+ * of its first fifteen other neighbours in CSR order (0xff = unused) | the number of CSR entries of the row, its sentence, 0, 0.
+ * Depends on the graph only: build it once per batch next to the CSR (graph.py:62-75 builds the dense matrix instead). */
+int edg_row_meta(const int32_t* row_ptr, const int32_t* col, const int32_t* row_sent, const int32_t* sent_ptr,
+                 int32_t N, void* row_meta, edg_stream stream);
 
 /* C[M,Nout] = act(A[M,K] * W^T + bias), W given as [Nout,K] with K contiguous
  * (nn.Linear layout).  Replaces torch.matmul(text, weight) of gcn.py:34 (with a

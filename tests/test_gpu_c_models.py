@@ -69,6 +69,31 @@ def test_graph_convolution_two_layers_share_one_csr_and_state_dict_keys():
     assert rel(h2, want) < 1e-5
 
 
+def test_graph_convolution_cache_never_returns_a_stale_graph():
+    """train.py:108 makes a fresh `.to(device)` adjacency per batch: the caching allocator hands the freed block to the
+    next batch at the same address, same shape, version 0.  The CSR cache must key on the tensor OBJECT, not its address."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import gcn as G
+    from ed_gated_gcn_b200 import synth
+    layer = E.GraphConvolution(16, 16, None).to(DEV)
+    w, b = layer.weight.detach().cpu(), layer.bias.detach().cpu()
+    seen_ptrs = set()
+    for seed in (21, 22, 23, 24):
+        batch = synth.make_batch(6, 12, 12, seed=seed)                # same shapes every time, different trees
+        x, adj, T = dense_inputs(batch, 16, seed=seed)
+        adj_d = adj.to(DEV)
+        seen_ptrs.add(adj_d.data_ptr())
+        y = layer(x.to(DEV), adj_d)
+        assert rel(y, O.gcn_layer_ref(x, adj, w, b)) < 1e-5, seed
+        # an in-place edit of the same object must miss as well
+        adj_d[:, 0, 1] = 1.0; adj_d[:, 1, 0] = 1.0
+        adj2 = adj.clone(); adj2[:, 0, 1] = 1.0; adj2[:, 1, 0] = 1.0
+        assert rel(layer(x.to(DEV), adj_d), O.gcn_layer_ref(x, adj2, w, b)) < 1e-5, seed
+        del adj_d, y
+    assert len(G._GRAPH_CACHE) == 0                                  # entries die with their tensors
+    assert len(seen_ptrs) < 4                                        # the allocator did reuse an address (the bug's precondition)
+
+
 def test_graph_convolution_relu_option_defaults_off():
     import ed_gated_gcn_b200 as E
     from ed_gated_gcn_b200 import synth
@@ -479,8 +504,12 @@ def test_stack_training_mode_gate_dropout_vs_oracle(dtype, Lyr):
     _compare(out, loss, x.grad, stack, dense, ora, ora_g, tol, Lyr)
     # eval mode = no dropout
     stack.eval()
-    out_e = stack(xp.to(DEV), graph, anchor, dist, lambda a, q: dense(torch.cat([a, q], 1)), return_x_out=True)
+    with torch.no_grad():
+        out_e = stack(xp.to(DEV), graph, anchor, dist, lambda a, q: dense(torch.cat([a, q], 1)), return_x_out=True)
     assert float((out_e.x_out == 0).float().mean()) < 0.01
+    # a trainable head that is not declared would train with a zero gradient: refused
+    with pytest.raises(E.EdgError, match="head_params"):
+        stack(xp.to(DEV), graph, anchor, dist, lambda a, q: dense(torch.cat([a, q], 1)))
 
 
 def test_stack_rejects_cpu_tensors():

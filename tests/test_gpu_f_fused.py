@@ -38,6 +38,7 @@ def _dense_ops(batch):
 
 
 def test_tile_plan_covers_every_sentence_once():
+    from ed_gated_gcn_b200 import ops
     batch, g, _, _, _, rows, plan = _setup(700, 1, 50, 3, 64, 64)
     info, n_tiles = plan
     nt = int(n_tiles.item())
@@ -48,12 +49,12 @@ def test_tile_plan_covers_every_sentence_once():
     assert np.array_equal(info[1:, 0], info[:-1, 1])
     assert np.array_equal(info[:, 2], sp[info[:, 0]]) and np.array_equal(info[:, 3], sp[info[:, 1]])
     assert np.array_equal(info[:, 4], rp[info[:, 2]]) and np.array_equal(info[:, 5], rp[info[:, 3]])
-    assert ((info[:, 3] - info[:, 2]) <= rows).all() and ((info[:, 1] - info[:, 0]) <= 8).all()
+    assert ((info[:, 3] - info[:, 2]) <= rows).all() and ((info[:, 1] - info[:, 0]) <= ops.FUSED_MAX_SENTENCES).all()
     assert ((info[:, 1] - info[:, 0]) >= 1).all()
     # greedy: the next sentence would not have fitted (rows) unless the sentence cap stopped the tile
     for t in range(nt - 1):
         s1 = info[t, 1]
-        full = (sp[s1 + 1] - info[t, 2] > rows) or (info[t, 1] - info[t, 0] == 8)
+        full = (sp[s1 + 1] - info[t, 2] > rows) or (info[t, 1] - info[t, 0] == ops.FUSED_MAX_SENTENCES)
         assert full
 
 

@@ -55,8 +55,13 @@ bench("linear (unfused)", lambda i: ops.linear(xs[i], w, bias))
 bench("pool_fwd V=1 (unfused)", lambda i: ops.pool_fwd(xs[i], graph, gates), N * D * 2)
 bench("torch copy (ref)", lambda i: xs[(i + 1) % RING].copy_(xs[i]), 2 * N * D * 2)
 
-KEYS = ("EPI_WARPS", "STAGES", "ROWS", "PF", "DEBUG", "SLEEP")
-sweeps = [dict(SLEEP=0), dict(SLEEP=0, DEBUG=31), dict(SLEEP=0, DEBUG=7), dict(SLEEP=20, DEBUG=31), dict(SLEEP=0, DEBUG=31, STAGES=2), dict(SLEEP=0, PF=0)]
+KEYS = ("V", "EPI_WARPS", "STAGES", "ROWS", "PF", "DEBUG", "SLEEP", "BOXROWS")
+sweeps = [dict(V=2), dict(V=2, STAGES=2), dict(V=1, PF=0)]
+only_plain = False
+if len(sys.argv) > 1 and sys.argv[1] == "pipe":       # load-pipeline study: epilogue work switched off
+    only_plain = True
+    sweeps = [dict(DEBUG=d, PF=0, BOXROWS=b) for d in (3, 23, 23 + 64, 3 + 64) for b in (32, 64, 128)]
+    sweeps += [dict(DEBUG=23 + 64, PF=0, STAGES=s) for s in (2, 3)] + [dict(DEBUG=0, PF=0, BOXROWS=b) for b in (32, 128)]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":      # one configuration taken from the environment (ncu runs)
     sweeps = [{k: int(os.environ["EDG_FUSED_" + k]) for k in KEYS if "EDG_FUSED_" + k in os.environ}]
 for sw in sweeps:
@@ -71,6 +76,9 @@ for sw in sweeps:
     tag = f"{sw} rows={rows} tiles={nt}"
     y, hmax, harg, _ = ops.gcn_layer(xs[0], w, bias, graph, 0, plan, rows, want_pool=True)
     pa = harg.clone()
+    if only_plain:
+        bench(f"fused fwd no pool     {tag}", lambda i: ops.gcn_layer(xs[i], w, bias, graph, 0, plan, rows))
+        continue
     bench(f"fused fwd + pool      {tag}", lambda i: ops.gcn_layer(xs[i], w, bias, graph, 0, plan, rows, want_pool=True))
     bench(f"fused fwd no pool     {tag}", lambda i: ops.gcn_layer(xs[i], w, bias, graph, 0, plan, rows))
     bench(f"fused adjoint+colsum  {tag}", lambda i: ops.gcn_layer(xs[i], w, None, graph, 1, plan, rows, want_colsum=True))
