@@ -204,8 +204,15 @@ def run_b200(args):
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)   # train.py:239-243 (Adam)
+    # train.py:239-243 trains with Adam: the same update rule as ONE launch of this package (edg_adam_multi);
+    # --torch-adam keeps torch.optim.Adam(fused, capturable) for comparison
+    if args.torch_adam:
+        opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+    else:
+        opt = E.FusedAdam(params, lr=1e-3)
     reducer = parallel.GradientAllReducer(params)
+    if world > 1:
+        stack.grad_ready_hook = reducer.hook          # per-layer all-reduce from inside the backward pass
     logits_fn = lambda a, p: dense(torch.cat([a, p], 1))
     head_params = list(dense.parameters())
 
@@ -519,6 +526,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused, capturable) instead of edg_adam_multi")
     ap.add_argument("--no-graph", action="store_true", help="enqueue kernels from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()

@@ -43,6 +43,7 @@ SIGNATURES = {
     "edg_gcn_layer": (c_int, [_P, _L, _I, _I, _P, _L, _I, _P, c_int, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _L, _P, _P,
                               _L, _P, c_int, _P, _Z, _P, _P]),
     "edg_row_meta": (c_int, [_P, _P, _P, _P, _I, _P, _P]),
+    "edg_adam_multi": (c_int, [_I, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float, _P]),
     "edg_linear": (c_int, [_P, c_int, _L, _I, _I, _P, _L, _I, _P, c_int, _P, c_int, _L, _P]),
     "edg_wgrad_workspace": (_Z, [_I, _I, _I, c_int]),
     "edg_wgrad": (c_int, [_P, _L, _I, _P, _L, _I, c_int, _I, _P, _L, _P, c_int, c_int, _P, _Z, _P]),
@@ -128,6 +129,8 @@ def _kernels_of(name: str, args) -> int:
         return 2
     if name == "edg_gcn_layer":
         return 2 if args[23] else 1
+    if name == "edg_adam_multi":
+        return 2 if args[0] else 0
     if name == "edg_pool_fwd":
         return (args[7] + 3) // 4
     return 1

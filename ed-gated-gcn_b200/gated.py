@@ -363,6 +363,7 @@ class _GatedStackFn(torch.autograd.Function):
         if g_xout is not None:
             g_xout = ops.as_rows(g_xout, cd)
         need_scores = g_kl is not None or g_scores is not None
+        grad_hook = cfg.get("grad_hook") or (lambda ts: None)
         gated = cfg["gated"]
         views_active = g_xy is not None and Lyr > 1 and gated
         dgates = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
@@ -403,6 +404,8 @@ class _GatedStackFn(torch.autograd.Function):
             d_lg, da_fc, _, _ = ops.fc_head_bwd(lg, fcw32, fcb32, a_fc, dv_in, dc_in, scale, parts=1)
             with side.region():       # nothing downstream waits for the fc parameter gradients: side stream
                 _, _, d_fcw, d_fcb = ops.fc_head_bwd(lg, fcw32, fcb32, a_fc, dv_in, dc_in, scale, parts=2)
+                d_fcw, d_fcb = d_fcw.to(fc_w.dtype), d_fcb.to(fc_b.dtype)
+                grad_hook([d_fcw, d_fcb])
             if ctx.fc_sig:
                 da_fc = da_fc * a_fc * (1.0 - a_fc)                   # through sigmoid(a)
             g_lg = d_lg if g_lg is None else g_lg + d_lg
@@ -416,6 +419,7 @@ class _GatedStackFn(torch.autograd.Function):
             ga_head, gp_head = res[0], res[1]
             for (i, _), g in zip(cap, res[2:]):
                 head_grads[i] = g
+            grad_hook([g for g in head_grads if g is not None and g.dtype == torch.float32])
         if da_fc is not None:
             ga_head = da_fc if ga_head is None else ga_head.float() + da_fc
         gp_total = g_pooled
@@ -494,6 +498,7 @@ class _GatedStackFn(torch.autograd.Function):
                         w, b = params[o + 2 * (g * pairs + i)], params[o + 2 * (g * pairs + i) + 1]
                         grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
                         grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
+                grad_hook(grads_out[o:o + 2 * Lyr * pairs])
                 return da_parts.sum(0) if Lyr > 1 else da_parts[0]
             for g in range(Lyr):
                 acts = ctx.gate_saved[g]
@@ -517,6 +522,7 @@ class _GatedStackFn(torch.autograd.Function):
                     else:
                         dlast = ops.linear(dz, wt, None, out_dtype=torch.float32)
                         da_g = dlast if da_g is None else da_g + dlast
+            grad_hook(grads_out[o:o + 2 * Lyr * pairs])
             return da_g
 
         # ---- GCN chain backward (gcn.py:33-45); the gate MLPs' backward runs on the side stream next to it
@@ -547,6 +553,7 @@ class _GatedStackFn(torch.autograd.Function):
                 w, b = params[2 * l], params[2 * l + 1]
                 dW, _ = ops.wgrad(hs[l - 1] if l > 0 else xr, du, bias_of=0)
                 grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db_next.to(b.dtype)
+                grad_hook(grads_out[2 * l:2 * l + 2])
                 wk = ctx.w_n[l]                                                 # [in,out] = B operand of du W^T
                 if l > 0:
                     du, _, _, db_next = ops.gcn_layer(du, wk, None, graph, 1, plan, rows,
@@ -575,6 +582,7 @@ class _GatedStackFn(torch.autograd.Function):
                 with side_w.region():
                     dW, db = ops.wgrad(ms[l], dh, bias_of=2)
                     grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db.to(b.dtype)
+                    grad_hook(grads_out[2 * l:2 * l + 2])
                 wk = ctx.w_n[l]                                                     # [in,out] = B operand of dh W^T
                 dm = ops.linear(dh, wk, None)
                 if l == 1 and patch is not None and patch_ev is not None:
@@ -588,8 +596,6 @@ class _GatedStackFn(torch.autograd.Function):
             da = da_gate if da is None else da + da_gate
         if da is not None:
             ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
-        if d_fcw is not None:                 # produced on the side stream: cast only after the join above
-            d_fcw, d_fcb = d_fcw.to(fc_w.dtype), d_fcb.to(fc_b.dtype)
         grads_out[-2], grads_out[-1] = d_fcw, d_fcb
         if ctx.x_padded:        # hand back the whole [N, pitch] allocation (padding columns are finite)
             dx = dx.as_strided((N, dx.stride(0)), (dx.stride(0), 1))
@@ -622,6 +628,9 @@ class GatedGCNStack(nn.Module):
         for l in range(1, n_layers + 1):
             setattr(self, f"gc{l}", GraphConvolution(hidden, hidden, None, compute_dtype=self.compute_dtype))
             setattr(self, f"gate{l}", make_gate(hidden, gate_arch))
+        # data parallelism: called inside the backward pass with every group of parameter gradients the moment it exists
+        # (parallel.GradientAllReducer.hook all-reduces it in place while the layers below still run); None = single GPU
+        self.grad_ready_hook = None
         self.fc_sigmoid = fc_sigmoid
         if fc_sigmoid:                                                   # BertAmir54, bert_amir5.py:464-465 (keys fc.1.*)
             self.fc = nn.Sequential(nn.Sigmoid(), nn.Linear(2 * hidden, n_classes))
@@ -669,7 +678,7 @@ class GatedGCNStack(nn.Module):
             raise L.EdgError(f"expected {self.hidden} feature columns (or the padded pitch), got {x.shape[-1]}")
         cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
-                   head_params=list(head_params), n_head=len(list(head_params)), grad_enabled=torch.is_grad_enabled(),
+                   head_params=list(head_params), n_head=len(list(head_params)), grad_enabled=torch.is_grad_enabled(), grad_hook=self.grad_ready_hook,
                    relu=self.relu, return_x_out=return_x_out, gated=self.gated,
                    drop_p=drop_p, seed=seed, fc_sigmoid=self.fc_sigmoid)
         logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params(),

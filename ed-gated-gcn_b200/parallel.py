@@ -39,53 +39,65 @@ def shard_tree_batch(batch, world_size: int, rank: int):
 
 
 class GradientAllReducer:
-    """Averages parameter gradients across ranks with as few collectives as possible:
-    gradients are packed into flat fp32 buckets (default: one bucket, <= 28 MB for
-    the configs of SURVEY 8e) and all-reduced asynchronously; ``wait()`` unpacks."""
+    """Averages parameter gradients across ranks, overlapped with the backward pass.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
-                 bucket_bytes: int = 64 << 20):
+    ``hook(tensors)`` is what a backward pass calls the moment a group of gradients exists (``GatedGCNStack`` does so
+    per layer, per gate-MLP batch and for the classifier head: set ``stack.grad_ready_hook = reducer.hook``): the group is
+    all-reduced IN PLACE and asynchronously -- one coalesced collective per group, ordered after the stream that produced
+    it -- while the layers below are still running.  ``__call__()`` after ``loss.backward()`` reduces whatever was not
+    announced through the hook (as one more group) and waits for everything.  No flat copy, no unpack: the tensors handed
+    to the hook are the ones autograd installs as ``.grad``.  NCCL averages inside the collective; gloo (the CPU tests)
+    sums and the scale is applied on wait."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
-        self.bucket_bytes = bucket_bytes
         self._pending = []
+        self._done = set()          # data_ptr of the gradients reduced through the hook in this step
 
-    def _buckets(self) -> List[List[torch.nn.Parameter]]:
-        out, cur, size = [], [], 0
-        for p in self.params:
-            if p.grad is None:
-                continue
-            n = p.grad.numel() * 4
-            if cur and size + n > self.bucket_bytes:
-                out.append(cur)
-                cur, size = [], 0
-            cur.append(p)
-            size += n
-        if cur:
-            out.append(cur)
-        return out
+    def _active(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _reduce(self, tensors: List[torch.Tensor]) -> None:
+        avg = dist.get_backend(self.group) == "nccl"
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+        if len(tensors) > 1 and hasattr(dist, "all_reduce_coalesced"):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                work = dist.all_reduce_coalesced(tensors, op=op, group=self.group, async_op=True)
+            self._pending.append(([work], tensors, avg))
+        else:
+            works = [dist.all_reduce(t, op=op, group=self.group, async_op=True) for t in tensors]
+            self._pending.append((works, tensors, avg))
+
+    def hook(self, tensors) -> None:
+        """Called from inside a backward pass with freshly produced fp32 gradient tensors (any stream)."""
+        if not self._active():
+            return
+        ts = [t for t in tensors if t is not None and t.numel() > 0]
+        if not ts:
+            return
+        for t in ts:
+            self._done.add(t.data_ptr())
+        self._reduce(ts)
 
     def start(self) -> None:
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+        if not self._active():
             return
-        for bucket in self._buckets():
-            flat = torch.cat([p.grad.reshape(-1).float() for p in bucket])
-            # NCCL averages inside the collective; gloo (the CPU tests) only sums
-            avg = dist.get_backend(self.group) == "nccl"
-            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._pending.append((work, flat, bucket, avg))
+        rest = [p.grad for p in self.params if p.grad is not None and p.grad.data_ptr() not in self._done]
+        if rest:
+            self._reduce(rest)
 
     def wait(self) -> None:
-        if not self._pending:
-            return
-        world = dist.get_world_size(self.group)
-        for work, flat, bucket, avg in self._pending:
-            work.wait()
+        world = dist.get_world_size(self.group) if self._pending else 1
+        for works, tensors, avg in self._pending:
+            for w in works:
+                w.wait()
             if not avg:
-                flat.mul_(1.0 / world)
-            views = [v.view_as(p.grad) for v, p in zip(flat.split([p.grad.numel() for p in bucket]), bucket)]
-            torch._foreach_copy_([p.grad for p in bucket], views)        # one multi-tensor launch, not one per parameter
+                torch._foreach_mul_(tensors, 1.0 / world)
         self._pending = []
+        self._done = set()
 
     def __call__(self) -> None:
         self.start()

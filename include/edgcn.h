@@ -419,6 +419,21 @@ int edg_lr_pool_bwd(const float* g, const int32_t* arg, int32_t B, int32_t D, vo
 int edg_dropout_rows(const void* x, int dtype, int64_t ldx, void* y, int64_t ldy, int32_t N, int32_t D,
                      const int64_t* seed, int32_t stream_id, float p, int accumulate, edg_stream stream);
 
+/* ------------------------------------------------------------------------- */
+/* Optimiser step (train.py:239-243 trains with torch.optim.Adam)             */
+/* ------------------------------------------------------------------------- */
+
+/* One Adam step over n <= 32 fp32 tensors in one launch (torch.optim.Adam semantics: bias-corrected, eps added to
+ * sqrt(v / bc2); weight_decay is the L2 form; no amsgrad):
+ *   g = grad * grad_scale (+ weight_decay * p);  m = beta1 m + (1 - beta1) g;  v = beta2 v + (1 - beta2) g^2
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+ * param / grad / exp_avg / exp_avg_sq / step / numel are HOST arrays of length n (device pointers inside).  step[i]:
+ * device fp32 scalar, the tensor's own step count t (on the device so that a captured step replays correctly; per tensor
+ * as in torch, where a parameter without gradient does not advance); incremented by one before the update. */
+int edg_adam_multi(int32_t n, void* const* param, const void* const* grad, void* const* exp_avg,
+                   void* const* exp_avg_sq, void* const* step, const int64_t* numel, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, edg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -337,3 +337,27 @@ def test_views_bwd_in_halves_equals_one_call(dtype):
     ops.views_bwd(pooled, arg, gates, h, g_xy, None, dh_b, None, parts=1)
     assert torch.equal(dh_a, dh_b) and torch.equal(dg_a, dg_b)
     assert not torch.equal(dh_a, dh0)
+
+
+def test_fused_adam_matches_torch_adam():
+    """edg_adam_multi (one launch for all tensors, device step counter) against torch.optim.Adam, the optimiser of
+    train.py:239-243, over several steps incl. tensors that are not a multiple of the 1024-element chunk."""
+    import ed_gated_gcn_b200 as E
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(300, 300), (300,), (34, 600), (1,), (1025,), (7, 3)] + [(17,)] * 30       # > 32 tensors: two launches
+    ref = [torch.nn.Parameter(torch.randn(*s, generator=gen).to(DEV)) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    o_mine = E.FusedAdam(mine, lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(5):
+        for a, b in zip(ref, mine):
+            g = torch.randn(a.shape, generator=gen).to(DEV) * (10.0 ** (step - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        if step == 3:
+            ref[1].grad = None; mine[1].grad = None            # a parameter without gradient is skipped
+        o_ref.step(); o_mine.step()
+        for a, b in zip(ref, mine):
+            assert rel(b, a) < 2e-6, (step, tuple(a.shape))
+    assert o_mine.step_count.tolist() == [5.0, 4.0] + [5.0] * (len(shapes) - 2)
+    with pytest.raises(E.EdgError):
+        E.FusedAdam([torch.nn.Parameter(torch.zeros(3))])      # CPU parameter: no fallback

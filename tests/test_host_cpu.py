@@ -145,8 +145,15 @@ sub, idx = parallel.shard_tree_batch(batch, world, rank)
 rows = torch.cat([x[batch.sent_ptr[i]:batch.sent_ptr[i + 1]] for i in idx])
 Wl = torch.nn.Parameter(w.clone()); Bl = torch.nn.Parameter(b.clone())
 loss_of(sub, rows, Wl, Bl).backward()
-parallel.GradientAllReducer([Wl, Bl])()
+red = parallel.GradientAllReducer([Wl, Bl])
+red.hook([Wl.grad])          # what a backward pass does as soon as a layer's gradient exists (overlapped reduction) ...
+red()                        # ... and the rest (here: the bias) after backward; then wait for everything
 ok = torch.allclose(Wl.grad, W.grad, atol=1e-6) and torch.allclose(Bl.grad, Bv.grad, atol=1e-6)
+# a second step must start clean (no gradient skipped because of the first step's bookkeeping)
+Wl.grad = None; Bl.grad = None
+loss_of(sub, rows, Wl, Bl).backward()
+red()
+ok = ok and torch.allclose(Wl.grad, W.grad, atol=1e-6) and torch.allclose(Bl.grad, Bv.grad, atol=1e-6)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 3)
