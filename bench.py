@@ -211,7 +211,7 @@ def run_b200(args):
     else:
         opt = E.FusedAdam(params, lr=1e-3)
     reducer = parallel.GradientAllReducer(params)
-    if world > 1:
+    if world > 1 and args.overlap_allreduce:
         stack.grad_ready_hook = reducer.hook          # per-layer all-reduce from inside the backward pass
     logits_fn = lambda a, p: dense(torch.cat([a, p], 1))
     head_params = list(dense.parameters())
@@ -526,6 +526,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="all-reduce every gradient group from inside the backward pass (GradientAllReducer.hook) instead of "
+                         "one coalesced in-place all-reduce after it")
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused, capturable) instead of edg_adam_multi")
     ap.add_argument("--no-graph", action="store_true", help="enqueue kernels from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

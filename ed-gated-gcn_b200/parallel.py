@@ -39,15 +39,23 @@ def shard_tree_batch(batch, world_size: int, rank: int):
 
 
 class GradientAllReducer:
-    """Averages parameter gradients across ranks, overlapped with the backward pass.
+    """Averages parameter gradients across ranks.
 
-    ``hook(tensors)`` is what a backward pass calls the moment a group of gradients exists (``GatedGCNStack`` does so
-    per layer, per gate-MLP batch and for the classifier head: set ``stack.grad_ready_hook = reducer.hook``): the group is
-    all-reduced IN PLACE and asynchronously -- one coalesced collective per group, ordered after the stream that produced
-    it -- while the layers below are still running.  ``__call__()`` after ``loss.backward()`` reduces whatever was not
-    announced through the hook (as one more group) and waits for everything.  No flat copy, no unpack: the tensors handed
-    to the hook are the ones autograd installs as ``.grad``.  NCCL averages inside the collective; gloo (the CPU tests)
-    sums and the scale is applied on wait."""
+    ``__call__()`` after ``loss.backward()``: ONE all-reduce over one flat fp32 bucket (2.3 MB at config 2), after which
+    every parameter's ``.grad`` is re-pointed at its slice of the reduced buffer -- one small pack kernel, one collective,
+    nothing copied back.  Measured on 2 B200 (weak scaling, whole step in a CUDA graph): 0.894 ms/step against 0.854 on one
+    GPU; a coalesced group of the 22 separate tensors costs 0.923.
+
+    ``hook(tensors)`` is the overlapped alternative: a backward pass calls it the moment a group of gradients exists
+    (``GatedGCNStack`` does so per layer, per gate-MLP batch and for the classifier head when
+    ``stack.grad_ready_hook = reducer.hook``) and the group is all-reduced in place, asynchronously, ordered after the
+    stream that produced it; ``__call__()`` then only reduces what was not announced and waits.  With this package's
+    persistent one-CTA-per-SM kernels the collectives cannot run NEXT to the compute (no SM is free, and a kernel with a
+    static tile assignment is delayed by whatever occupies one of its SMs), so it measured slower (0.947 ms/step); it is
+    kept for configurations whose backward pass leaves SMs idle.  Requires ``.grad = None`` before backward (autograd
+    must install the announced tensors, not accumulate into older ones).
+
+    NCCL averages inside the collective; gloo (the CPU tests) sums and the scale is applied on wait."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -85,9 +93,22 @@ class GradientAllReducer:
     def start(self) -> None:
         if not self._active():
             return
-        rest = [p.grad for p in self.params if p.grad is not None and p.grad.data_ptr() not in self._done]
-        if rest:
-            self._reduce(rest)
+        rest = [p for p in self.params if p.grad is not None and p.grad.data_ptr() not in self._done]
+        if not rest:
+            return
+        if len(rest) == 1:
+            self._reduce([rest[0].grad])
+            return
+        # one flat bucket: a single collective over one contiguous buffer (measured at 2 GPUs: 0.923 ms/step for a
+        # coalesced group of 22 small tensors, less for one flat 2.3 MB all-reduce); nothing is copied back -- each
+        # parameter's .grad is re-pointed at its slice of the reduced buffer
+        flat = torch.cat([p.grad.reshape(-1).float() for p in rest])
+        self._reduce([flat])
+        off = 0
+        for p in rest:
+            n = p.grad.numel()
+            p.grad = flat[off:off + n].view_as(p.grad) if p.grad.dtype == torch.float32 else flat[off:off + n].view_as(p.grad).to(p.grad.dtype)
+            off += n
 
     def wait(self) -> None:
         world = dist.get_world_size(self.group) if self._pending else 1
