@@ -271,8 +271,10 @@ def test_stack_matches_full_reference_forward_backward(dtype):
                                  dict(L=4, arch="sig-3", D=128, C=5, B=6, lo=30, hi=90),
                                  # config-4 shape: sentences too long for a shared-memory window (per-sentence / flat
                                  # kernels), D = 768 (streaming tcgen05 GEMM, 7 M tiles in wgrad), a hub of degree ~n/2
-                                 dict(L=2, arch="sig-2", D=768, C=5, B=4, lo=200, hi=512, skewed=True)],
-                         ids=["C1", "L3", "L1", "L4", "C4long"])
+                                 dict(L=2, arch="sig-2", D=768, C=5, B=4, lo=200, hi=512, skewed=True),
+                                 # config-3 shape: 768-d BERT-base features into a 3-layer gated stack, sentences <= 50 tokens
+                                 dict(L=3, arch="sig-2", D=768, C=34, B=12, lo=5, hi=50)],
+                         ids=["C1", "L3", "L1", "L4", "C4long", "C3"])
 def test_stack_packed_rows_vs_oracle(dtype, cfg):
     """Packed layout (no pad rows): the oracle is run per sentence with T = n_b, which is the
     same convention (SURVEY hard part 2)."""
@@ -344,9 +346,41 @@ def test_bert_amir54_variant_matches_full_reference_forward_backward(dtype):
         got = dict(stack.named_parameters())
         got.update({"dense." + n: p for n, p in dense.named_parameters()})
         for k in z.files:
-            if k.startswith("g_") and k != "g_fc.1.bias":
-                # fc.1.weight: a ~1e-6 gradient whose aspect half cancels inside the softmax (rounding noise)
-                assert rel(got[k[2:]].grad, z[k]) < (2e-3 if k == "g_fc.1.weight" else tol), k
+            if k.startswith("g_") and k not in ("g_fc.1.bias", "g_fc.1.weight"):
+                assert rel(got[k[2:]].grad, z[k]) < tol, k
+        # fc.1.weight: d kl / d fc.weight = sum_b sum_t ds_bt logits_b (x) sigmoid(cat[x_out_t, a_b]) with sum_t ds_bt = 0
+        # (a softmax derivative): a 2.9e-6 remainder of summands that add up to 4.9e-4 in absolute value.  The
+        # reference's OWN fp32 value is 1.6e-5 away from an fp64 evaluation of the same lines, i.e. outside the 1e-5
+        # bar -- so this tensor is judged against fp64, with the error bound of the cancelling sum it is: a few dozen
+        # fp32 roundings of the summands' magnitude (64 eps x sum |summand|), not 1e-5 of the remainder.
+        g64, sum_abs = _fp64_fc_weight_grad_block54(z)
+        bound = 64 * 1.1920929e-07 * sum_abs
+        err = (got["fc.1.weight"].grad.detach().cpu().double() - g64).abs().max().item()
+        err_ref = (torch.from_numpy(z["g_fc.1.weight"]).double() - g64).abs().max().item()
+        assert err_ref < bound                                          # the reference's fp32 run obeys the same bound
+        assert err < bound, (err, bound, err_ref)
+
+
+def _fp64_fc_weight_grad_block54(z):
+    """fp64 evaluation of the reference block on the block54 fixture (oracle restatement of bert_amir5.py:515-540 with
+    fc = Sequential(Sigmoid, Linear)): d loss / d fc.1.weight and max_cj sum_bt |ds_bt logits_bc sigmoid(cat)_j|."""
+    P = {k[2:]: torch.from_numpy(z[k]).double().requires_grad_(True) for k in z.files if k.startswith("p_")}
+    D = z["x"].shape[2]
+    x, adj = torch.from_numpy(z["x"]).double(), torch.from_numpy(z["adj"]).double()
+    po = torch.from_numpy(z["dense_in"][:, 2 * D:]).double()
+    gcn_p = [(P["gc1.weight"], P["gc1.bias"]), (P["gc2.weight"], P["gc2.bias"])]
+    gate_p = [[(P[f"gate{l}.1.weight"], P[f"gate{l}.1.bias"]), (P[f"gate{l}.3.weight"], P[f"gate{l}.3.bias"])] for l in (1, 2)]
+    fn = lambda a, p: (torch.cat([a, p, po], 1) @ P["dense.0.weight"].t() + P["dense.0.bias"]) @ P["dense.1.weight"].t() \
+        + P["dense.1.bias"]
+    o = O.gated_block_ref(x, adj, torch.from_numpy(z["anchor"]).long(), torch.from_numpy(z["dist"]).long(), gcn_p, gate_p,
+                          P["fc.1.weight"], P["fc.1.bias"], fn, lead_sigmoid=True, fc_sigmoid=True)
+    o["scores"].retain_grad()
+    loss = torch.nn.functional.cross_entropy(o["logits"], torch.from_numpy(z["targets"]).long()) + 0.01 * o["xy"] + 0.01 * o["kl"]
+    loss.backward()
+    B, T, _ = x.shape
+    cat = torch.sigmoid(torch.cat([o["x_out"].detach(), o["aspect"].detach()[:, None, :].expand(B, T, D)], 2))
+    sum_abs = torch.einsum("bt,bc,btj->cj", o["scores"].grad.abs(), o["logits"].detach().abs(), cat).max().item()
+    return P["fc.1.weight"].grad, sum_abs
 
 
 def test_ungated_ablation_matches_oracle():

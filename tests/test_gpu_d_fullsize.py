@@ -153,3 +153,97 @@ def test_config5_shaped_aggregation_chunk_against_dense_reference():
         want = O.aggregation_only_ref(xu[lo:hi][None], adj[None])[0]
         worst = max(worst, rel(y[lo:hi], want))
     assert worst < 8e-3
+
+
+def test_c2_bf16_block_against_the_oracle_at_the_benchmarked_size():
+    """The benchmarked configuration itself (C2: 4096 trees <= 50 tokens, D = 300, L = 2, bf16, fused layer kernels)
+    against the CPU oracle: every output (logits, scores, x_out, xy, kl, loss) and every gradient (all rows of dx, all
+    parameters) within the bf16 bar of 2e-2.  The oracle runs the reference block (bert_amir5.py:615-648) on sub-batches
+    of equal-length sentences (46 calls instead of 4096); the batch means are re-weighted by the group sizes.  Gradients
+    are compared under the CUDA path's max-pool routing, and every re-routed position must be a near-tie."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import synth
+    from oracle import ref_oracle as O
+    from test_gpu_c_models import _oracle_params, _local_args
+    tol, near = 2e-2, 2e-2
+    batch = synth.config_batch("C2")
+    D, C, Lyr = 300, 34, 2
+    B, N = batch.n_graphs, batch.n_rows
+    torch.manual_seed(14181)
+    stack = E.GatedGCNStack(D, n_layers=Lyr, n_classes=C, gate_arch="sig-2", compute_dtype="bf16").to(DEV)
+    dense = torch.nn.Linear(2 * D, C).to(DEV)
+    gen = torch.Generator().manual_seed(14181)
+    O.reference_init_(list(stack.parameters()) + list(dense.parameters()), gen)          # train.py:75-84
+    xp = torch.randn(N, D, generator=gen)
+    targets = torch.arange(B) % C
+    graph = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=DEV)
+    assert graph.tile_plan(__import__("ed_gated_gcn_b200").ops.fused_tile_rows(D, D)) is not None     # the fused path is the one under test
+    anchor = torch.from_numpy(batch.anchor).to(DEV)
+    dist = E.tree_distance(graph, anchor)
+    x = xp.to(DEV).requires_grad_(True)
+    out = stack(x, graph, anchor, dist, lambda a, p: dense(torch.cat([a, p], 1)), head_params=list(dense.parameters()),
+                return_x_out=True)
+    loss = torch.nn.functional.cross_entropy(out.logits, targets.to(DEV)) + 0.01 * out.xy + 0.01 * out.kl
+    loss.backward()
+
+    sp = batch.sent_ptr.astype(np.int64)
+    fa, va = _local_args(out, sp[:-1])                                  # sentence-local arg-max rows of the CUDA path
+    dist_cpu = dist.cpu()
+    heads = batch.heads_list()
+    sd, dw, db, gcn_p, gate_p, lead = _oracle_params(stack, dense)
+    logits_fn = lambda a, p: torch.cat([a, p], 1) @ dw.t() + db
+    want = dict(logits=torch.empty(B, C), scores=torch.empty(N), x_out=torch.empty(N, D), dx=torch.empty(N, D))
+    xy_u = kl_u = 0.0
+    logits_f, xy_f, kl_f, leaves, n_flip = [None] * B, 0.0, 0.0, [], 0
+    for n in np.unique(batch.lengths):
+        idx = np.nonzero(batch.lengths == n)[0]
+        rows = (sp[idx][:, None] + np.arange(n)[None, :]).reshape(-1)
+        xb = xp[rows].view(len(idx), n, D)
+        adj = torch.from_numpy(np.stack([O.dense_adjacency_from_heads(heads[b], n) for b in idx])).float()
+        anc = torch.from_numpy(batch.anchor[idx].astype(np.int64))
+        db_ = dist_cpu[rows].view(len(idx), n).long()
+        with torch.no_grad():                                            # forward as the reference computes it
+            o = O.gated_block_ref(xb, adj, anc, db_, gcn_p, gate_p, sd["fc.0.weight"], sd["fc.0.bias"], logits_fn,
+                                  lead_sigmoid=lead)
+        want["logits"][idx] = o["logits"]
+        want["scores"][rows] = o["scores"].reshape(-1)
+        want["x_out"][rows] = o["x_out"].reshape(-1, D)
+        xy_u += float(o["xy"]) * len(idx) / B
+        kl_u += float(o["kl"]) * len(idx) / B
+        # routing: the CUDA path may differ from torch.max only at near-ties
+        for vals, arg in [(o["x_out"], fa[idx])] + [(o["hs"][0] * o["gates"][v][:, None, :], va[v][idx]) for v in range(Lyr)]:
+            best, best_arg = vals.max(1)
+            mine = vals.gather(1, arg[:, None, :])[:, 0]
+            flip = arg != best_arg
+            n_flip += int(flip.sum())
+            # near-tie = within the bf16 bar of the tensor (2e-2 of the sentence's largest entry, the way the parity gate
+            # measures activations): the rounding error of an entry of h_L is set by the O(1) entries of h_{L-1} it sums,
+            # not by its own size, so a column of small values is re-ordered by the same absolute error
+            scale = vals.abs().amax((1, 2)).clamp_min(1e-6)[:, None].expand_as(best)
+            assert ((best - mine)[flip] <= near * scale[flip]).all(), "re-routed position is not a near-tie"
+        # gradients: the same block with the CUDA path's routing
+        xg = xb.clone().requires_grad_(True)
+        of = O.gated_block_ref(xg, adj, anc, db_, gcn_p, gate_p, sd["fc.0.weight"], sd["fc.0.bias"], logits_fn,
+                               lead_sigmoid=lead, forced_view_arg=va[:, idx], forced_final_arg=fa[idx])
+        for k, b in enumerate(idx):
+            logits_f[b] = of["logits"][k:k + 1]
+        xy_f = xy_f + of["xy"] * (len(idx) / B)
+        kl_f = kl_f + of["kl"] * (len(idx) / B)
+        leaves.append((xg, rows))
+    assert n_flip <= 0.06 * (Lyr + 1) * B * D, n_flip
+    loss_u = torch.nn.functional.cross_entropy(want["logits"], targets) + 0.01 * xy_u + 0.01 * kl_u      # train.py:115-118
+    loss_f = torch.nn.functional.cross_entropy(torch.cat(logits_f), targets) + 0.01 * xy_f + 0.01 * kl_f
+    loss_f.backward()
+    for xg, rows in leaves:
+        want["dx"][rows] = xg.grad.reshape(-1, D)
+    assert rel(out.logits, want["logits"]) < tol
+    assert rel(out.scores, want["scores"]) < tol
+    assert rel(out.x_out, want["x_out"]) < tol
+    assert abs(float(out.xy.detach()) - xy_u) < tol * abs(xy_u) and abs(float(out.kl.detach()) - kl_u) < tol * abs(kl_u)
+    assert abs(float(loss.detach()) - float(loss_u)) < tol * abs(float(loss_u))
+    assert rel(x.grad, want["dx"]) < tol, "dx"
+    for name, p in list(stack.named_parameters()) + [("dense.weight", dense.weight), ("dense.bias", dense.bias)]:
+        g = (dw.grad if name == "dense.weight" else db.grad if name == "dense.bias" else sd[name].grad)
+        if name == "fc.0.bias" or g is None or g.abs().max() < 1e-9:
+            continue                  # c_b cancels inside the softmax: that gradient is rounding noise
+        assert rel(p.grad, g) < tol, name
