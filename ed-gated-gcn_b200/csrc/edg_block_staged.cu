@@ -74,19 +74,17 @@ pool_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __restri
 }
 
 // ---- importance scores, softmax product, and d kl / d (v, c) units (bert_amir5.py:645-648) ----------
-// blockDim = (32, 8); Q = 16-byte chunks per lane (ceil(chunks / 32)).  Window-wide phases, every sentence of the
-// window in parallel, three block barriers per window:
-//   P0 float(dist) of the window's rows -> smem (overlaps the bulk copy)
-//   P1 scores: warp per ROW (lanes = chunks, dot product by warp shuffles)
-//   P2 softmax statistics, kl_b and u_t = P_t (Q_t - kl_b) / B: warp per SENTENCE
-//   P3 dv_unit = gate * sum_t u_t h_t: thread = (chunk, sentence lane)
-constexpr int kSMaxQ = 4;
-#ifndef EDG_SCORES_WARPS
-#define EDG_SCORES_WARPS 8
-#endif
-constexpr int kScoresWarps = EDG_SCORES_WARPS;     // warps per block (P1: one row per warp iteration); 12 / 16 measured
-                                                   // slower than 8 at C2 (51.4 / 53.2 vs 50.5 us)
-constexpr int kWCache = 8;      // sentences per window whose gate*v vector is cached in shared memory
+// One WARP per sentence of the window, no block barrier after the window has landed:
+//   P1 scores: LANE = ROW.  Every lane walks its own row's 16-byte chunks (the sentence's weights gate*v are broadcast
+//      reads of a per-warp shared-memory copy), so a row's dot product needs no shuffle reduction and the scores end up
+//      one per lane -- the layout the softmax wants.  Four accumulators keep the FMA chain short.
+//   P2 softmax statistics over the lanes: kl_b and u_t = P_t (Q_t - kl_b) / B.
+//   P3 sf = sum_t u_t h_t: lanes = chunks, u_t broadcast by shuffle from the lane that owns row t.
+// (The first version -- window-wide phases, warp per ROW in P1, three block barriers -- spent 32 % of its samples in
+// barriers and needed 25.5 M warp instructions per launch at config 2; this one needs ~8 M.)
+constexpr int kSMaxQ = 4;                  // 16-byte chunks per lane in P3 (chunks <= 128)
+constexpr int kSMaxPass = 4;               // rows per sentence <= 128 (lane = row, four passes)
+constexpr int kScoresWarps = 4;            // warps per block: a 72 KB window holds ~2.6 sentences of config 2
 
 template <typename T, int I64, int Q>
 __global__ void __launch_bounds__(32 * kScoresWarps)
@@ -103,114 +101,151 @@ scores_staged_kernel(const T* __restrict__ h, int64_t ldh, const int32_t* __rest
   const RowWindow w = stage_window<T>(h, ldh, N, B, tile_rows, sent_ptr, row_sent, win, &bar, sh);
   if (w.r1 <= w.r0) return;
   const int pitch = (int)(ldh * (int64_t)sizeof(T));
-  const int n = w.r1 - w.r0;
-  float* sc_s = reinterpret_cast<float*>(win + (size_t)cap_rows * pitch);      // [cap_rows] scores, then u_t
-  float* dq_s = sc_s + cap_rows;                                               // [cap_rows] float(dist)
-  int32_t* rs_s = reinterpret_cast<int32_t*>(dq_s + cap_rows);                 // [cap_rows] sentence of each row
-  float* w_s = reinterpret_cast<float*>(rs_s + cap_rows);                      // [kWCache][chunks*E] gate*v of the first sentences
-  const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+  const int lane = threadIdx.x, warp = threadIdx.y;
   const int width = chunks * E;
+  float* w_s = reinterpret_cast<float*>(win + (size_t)cap_rows * pitch) + (size_t)warp * width;   // this warp's gate*v
+  const uint32_t w_a = stg_smem_u32(w_s);
   const uint32_t xs = stg_smem_u32(win);
-  // P0 (overlaps the bulk copy): small per-row / per-sentence data -> shared memory, coalesced
-  for (int i = tid; i < n; i += 32 * kScoresWarps) { dq_s[i] = sdist_at<I64>(dist, w.r0 + i); rs_s[i] = __ldg(row_sent + w.r0 + i); }
-  {
-    const int ns = min(w.s1 - w.s0, kWCache);
-    for (int i = tid; i < ns * width; i += 32 * kScoresWarps) {
-      const int si = i / width, d = i - si * width;
-      w_s[i] = d < D ? __ldg(gate + (int64_t)(w.s0 + si) * D + d) * __ldg(vvec + (int64_t)(w.s0 + si) * D + d) : 0.f;
-    }
-  }
-  __syncthreads();
-  wait_window(&bar);
-  // P1: one row per warp iteration; consecutive rows mostly share the sentence, so its weights stay in registers
-  {
-    int cur = -1;
-    float wq[Q][E];
-    float cb = 0.f;
-    for (int lr = warp; lr < n; lr += kScoresWarps) {
-      const int s = rs_s[lr];
-      if (s != cur) {
-        cur = s;
-        const int si = s - w.s0;
+  const float invB = 1.0f / (float)B;
+  bool waited = false;
+  for (int s = w.s0 + warp; s < w.s1; s += kScoresWarps) {
+    const int beg = __ldg(sent_ptr + s) - w.r0, end = __ldg(sent_ptr + s + 1) - w.r0;
+    const int n = end - beg;
+    // the sentence's weights and distances do not depend on the window: their loads are issued before the bulk-copy wait
+    __syncwarp();
+    float gq[Q][E];                                       // this lane's gate entries (chunks lane, lane + 32, ...)
+    {
+      float vq[Q][E];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const int c = (lane + 32 * q) * E;
+      for (int q = 0; q < Q; ++q)                         // all loads first: ONE global round trip per sentence
 #pragma unroll
-          for (int k = 0; k < E; ++k) {
-            const bool ok = (lane + 32 * q < chunks) && (c + k < D);
-            if (si < kWCache) wq[q][k] = ok ? w_s[si * width + c + k] : 0.f;
-            else wq[q][k] = ok ? __ldg(gate + (int64_t)s * D + c + k) * __ldg(vvec + (int64_t)s * D + c + k) : 0.f;
-          }
+        for (int k = 0; k < E; ++k) {
+          const int i = (lane + 32 * q) * E + k;
+          const bool ok = lane + 32 * q < chunks && i < D;
+          gq[q][k] = ok ? __ldg(gate + (int64_t)s * D + i) : 0.f;
+          vq[q][k] = ok ? __ldg(vvec + (int64_t)s * D + i) : 0.f;
         }
-        cb = cvec ? __ldg(cvec + s) : 0.f;
-      }
-      float acc = 0.f;
 #pragma unroll
       for (int q = 0; q < Q; ++q)
         if (lane + 32 * q < chunks) {
-          float f[E];
-          SVec16<T>::load(xs + (uint32_t)(lr * pitch + (lane + 32 * q) * 16), f);
 #pragma unroll
-          for (int k = 0; k < E; ++k) acc = fmaf(f[k], wq[q][k], acc);
+          for (int k = 0; k < E; ++k) w_s[(lane + 32 * q) * E + k] = gq[q][k] * vq[q][k];
         }
-      acc = warp_sum(acc) + cb;
-      if (lane == 0) { sc_s[lr] = acc; scores[w.r0 + lr] = acc; }
     }
-  }
-  __syncthreads();
-  // P2
-  const float invB = 1.0f / (float)B;
-  for (int s = w.s0 + warp; s < w.s1; s += kScoresWarps) {
-    const int beg = __ldg(sent_ptr + s) - w.r0, end = __ldg(sent_ptr + s + 1) - w.r0;
+    const float cb = cvec ? __ldg(cvec + s) : 0.f;
+    float dq[kSMaxPass];
+#pragma unroll
+    for (int p = 0; p < kSMaxPass; ++p) dq[p] = (32 * p + lane < n) ? sdist_at<I64>(dist, w.r0 + beg + 32 * p + lane) : -INFINITY;
+    __syncwarp();
+    if (!waited) { wait_window(&bar); waited = true; }
+    // ---- P1
+    float sc[kSMaxPass];
+#pragma unroll
+    for (int p = 0; p < kSMaxPass; ++p) {
+      sc[p] = -INFINITY;
+      if (32 * p < n) {                                   // warp-uniform
+        const int t = 32 * p + lane;
+        if (t < n) {
+          const uint32_t ra = xs + (uint32_t)((beg + t) * pitch);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+          for (int c = 0; c < chunks; ++c) {
+            float f[E], g[E];
+            SVec16<T>::load(ra + (uint32_t)c * 16u, f);
+#pragma unroll
+            for (int k = 0; k < E; k += 4) SVec16<float>::load(w_a + (uint32_t)(c * E + k) * 4u, *reinterpret_cast<float(*)[4]>(&g[k]));
+#pragma unroll
+            for (int k = 0; k < E; k += 4) {
+              a0 = fmaf(f[k], g[k], a0); a1 = fmaf(f[k + 1], g[k + 1], a1);
+              a2 = fmaf(f[k + 2], g[k + 2], a2); a3 = fmaf(f[k + 3], g[k + 3], a3);
+            }
+          }
+          const float v = ((a0 + a1) + (a2 + a3)) + cb;
+          sc[p] = v;
+          scores[w.r0 + beg + t] = v;
+        }
+      }
+    }
+    // ---- P2
     float ms = -INFINITY, mq = -INFINITY;
-    for (int t = beg + lane; t < end; t += 32) { ms = fmaxf(ms, sc_s[t]); mq = fmaxf(mq, dq_s[t]); }
+#pragma unroll
+    for (int p = 0; p < kSMaxPass; ++p) { ms = fmaxf(ms, sc[p]); mq = fmaxf(mq, dq[p]); }
     ms = warp_max(ms); mq = warp_max(mq);
-    float zs = 0.f, zq = 0.f;
-    for (int t = beg + lane; t < end; t += 32) { zs += expf(sc_s[t] - ms); zq += expf(dq_s[t] - mq); }
+    float es[kSMaxPass], eq[kSMaxPass], zs = 0.f, zq = 0.f;
+#pragma unroll
+    for (int p = 0; p < kSMaxPass; ++p) {
+      const bool ok = 32 * p + lane < n;
+      es[p] = ok ? expf(sc[p] - ms) : 0.f;
+      eq[p] = ok ? expf(dq[p] - mq) : 0.f;
+      zs += es[p]; zq += eq[p];
+    }
     zs = warp_sum(zs); zq = warp_sum(zq);
     float kacc = 0.f;
-    for (int t = beg + lane; t < end; t += 32) kacc += (expf(sc_s[t] - ms) / zs) * (expf(dq_s[t] - mq) / zq);
-    const float klb = warp_sum(kacc);
+#pragma unroll
+    for (int p = 0; p < kSMaxPass; ++p) kacc += (es[p] / zs) * (eq[p] / zq);
+    const float klb = n > 0 ? warp_sum(kacc) : 0.f;
     if (lane == 0) kl_b[s] = klb;
-    if (dv_unit) {
-      float dcu = 0.f;
-      for (int t = beg + lane; t < end; t += 32) {
-        const float u = (expf(sc_s[t] - ms) / zs) * ((expf(dq_s[t] - mq) / zq) - klb) * invB;
-        sc_s[t] = u;
-        if (u_unit) u_unit[w.r0 + t] = u;
-        dcu += u;
-      }
-      dcu = warp_sum(dcu);
-      if (lane == 0 && dc_unit) dc_unit[s] = dcu;
+    if (dv_unit == nullptr) continue;
+    float u[kSMaxPass], dcu = 0.f;
+#pragma unroll
+    for (int p = 0; p < kSMaxPass; ++p) {
+      const bool ok = 32 * p + lane < n;
+      u[p] = ok ? (es[p] / zs) * ((eq[p] / zq) - klb) * invB : 0.f;
+      if (ok && u_unit) u_unit[w.r0 + beg + 32 * p + lane] = u[p];
+      dcu += u[p];
     }
-  }
-  if (dv_unit == nullptr) return;
-  __syncthreads();
-  // P3
-  const int ylanes = (32 * kScoresWarps) / chunks;
-  const int x = tid % chunks, y = tid / chunks;
-  if (y < ylanes) {
-    const int c = x * E;
-    for (int s = w.s0 + y; s < w.s1; s += ylanes) {
-      const int beg = __ldg(sent_ptr + s) - w.r0, end = __ldg(sent_ptr + s + 1) - w.r0;
-      float dvu[E];
+    dcu = warp_sum(dcu);
+    if (lane == 0 && dc_unit) dc_unit[s] = dcu;
+    // ---- P3
+    float dvu[Q][E];
 #pragma unroll
-      for (int k = 0; k < E; ++k) dvu[k] = 0.f;
-      for (int t = beg; t < end; ++t) {
-        const float u = sc_s[t];
-        float f[E];
-        SVec16<T>::load(xs + (uint32_t)(t * pitch + x * 16), f);
+    for (int q = 0; q < Q; ++q)
 #pragma unroll
-        for (int k = 0; k < E; ++k) dvu[k] = fmaf(u, f[k], dvu[k]);
-      }
+      for (int k = 0; k < E; ++k) dvu[q][k] = 0.f;
 #pragma unroll
-      for (int k = 0; k < E; ++k)
-        if (c + k < D) {
-          dv_unit[(int64_t)s * D + c + k] = dvu[k] * __ldg(gate + (int64_t)s * D + c + k);
-          if (sf_unit) sf_unit[(int64_t)s * D + c + k] = dvu[k];
+    for (int p = 0; p < kSMaxPass; ++p) {
+      if (32 * p < n) {
+        const int cnt = min(32, n - 32 * p);
+        const uint32_t ra = xs + (uint32_t)((beg + 32 * p) * pitch) + (uint32_t)lane * 16u;
+        // four rows per step: their shuffles and shared-memory loads are independent (one warp per sentence has no
+        // other warp of the same sentence to hide a dependent chain)
+#pragma unroll 1
+        for (int t0 = 0; t0 < cnt; t0 += 4) {
+          float ut[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) ut[r] = __shfl_sync(0xffffffffu, u[p], (t0 + r) & 31);
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            if (lane + 32 * q < chunks) {
+              float f[4][E];
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+                if (t0 + r < cnt) SVec16<T>::load(ra + (uint32_t)((t0 + r) * pitch) + (uint32_t)q * 512u, f[r]);
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+                if (t0 + r < cnt) {
+#pragma unroll
+                  for (int k = 0; k < E; ++k) dvu[q][k] = fmaf(ut[r], f[r][k], dvu[q][k]);
+                }
+            }
+          }
         }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int c = (lane + 32 * q) * E;
+      if (lane + 32 * q < chunks) {
+#pragma unroll
+        for (int k = 0; k < E; ++k)
+          if (c + k < D) {
+            dv_unit[(int64_t)s * D + c + k] = dvu[q][k] * gq[q][k];
+            if (sf_unit) sf_unit[(int64_t)s * D + c + k] = dvu[q][k];
+          }
+      }
     }
   }
+  if (!waited) wait_window(&bar);        // never leave a bulk copy in flight into a dead block
 }
 
 // ---- head backward (scores/kl, final max-pool, optional direct x_out gradient) -----------------------
@@ -402,11 +437,11 @@ int scores_kl_staged(const void* h, int64_t ldh, const int32_t* sent_ptr, const 
                      float* scores, float* kl_b, float* dv_unit, float* dc_unit, float* u_unit, float* sf_unit, cudaStream_t s) {
   constexpr int E = Vec16<T>::kElems;
   const int chunks = (D + E - 1) / E;
-  if (!row_sent || max_len <= 0 || chunks > 32 * kSMaxQ) return 1;
-  const size_t wcache = (size_t)kWCache * chunks * E * sizeof(float);
-  const WindowPlan p = plan_window((size_t)ldh * sizeof(T), max_len, 12, wcache);
+  if (!row_sent || max_len <= 0 || chunks > 32 * kSMaxQ || max_len > 32 * kSMaxPass) return 1;
+  const size_t wbuf = (size_t)kScoresWarps * chunks * E * sizeof(float);          // per-warp gate*v of the current sentence
+  const WindowPlan p = plan_window((size_t)ldh * sizeof(T), max_len, 0, wbuf);
   if (p.tile_rows < 8) return 1;
-  const size_t smem = p.smem_rows + (size_t)p.cap_rows * 3 * sizeof(float) + wcache;
+  const size_t smem = p.smem_rows + wbuf;
   const int Q = (chunks + 31) / 32;
 #define EDG_SC(QQ)                                                                                                       \
   return dist_i64 ? launch_scores_q<T, 1, QQ>(h, ldh, sent_ptr, row_sent, N, B, D, chunks, p, smem, gate, v, c, dist, scores, \
