@@ -110,9 +110,30 @@ def algo_bytes_of_call(name, args):
     if name == "edg_wgrad":       # both row matrices read once
         _, _, K1, _, _, K2, dt, R = args[:8]
         return R * (K1 + K2) * es(dt)
-    if name in ("edg_pool_fwd", "edg_scores_kl_fwd"):
+    if name == "edg_gcn_layer":   # x read + y write + 16 B/row of graph structure + the weight slice (fused form)
+        _, _, N, K, _, _, Nout = args[:7]
+        return N * K * 2 + N * Nout * 2 + 16 * N + Nout * K * 2
+    if name == "edg_head_du":     # du written once; seven [B,D] fp32 side arrays
+        N, B, D = args[9:12]
+        return N * D * 2 + 7 * B * D * 4
+    if name in ("edg_pool_fwd", "edg_scores_kl_fwd"):       # one read of the row matrix
         _, dt, _, _, B, D = args[:6]
-        return None
+        N = args[18] if name == "edg_scores_kl_fwd" else args[11]
+        return N * D * es(dt)
+    if name == "edg_head_bwd":    # h read, dh written
+        _, dt, _, _, B, D = args[:6]
+        return 2 * args[-2] * D * es(dt) if args[18] else args[-2] * D * es(dt)
+    return None
+
+
+def algo_flops_of_call(name, args):
+    """Tensor-core flops of one C-ABI call (2 * M * N * K of its GEMM), None for the streaming kernels."""
+    if name == "edg_linear":
+        return 2 * args[3] * args[4] * args[7]
+    if name == "edg_gcn_layer":
+        return 2 * args[2] * args[3] * args[6]
+    if name == "edg_wgrad":
+        return 2 * args[7] * args[2] * args[5]
     return None
 
 
@@ -151,7 +172,8 @@ class KernelTimer:
             elif name == "edg_wgrad":
                 key = f"edg_wgrad[R={args[7]}]"
             ms = a.elapsed_time(b)
-            e = agg.setdefault(key, dict(ms=0.0, n=0, bytes=algo_bytes_of_call(name, args), name=name))
+            e = agg.setdefault(key, dict(ms=0.0, n=0, bytes=algo_bytes_of_call(name, args), flops=algo_flops_of_call(name, args),
+                                         name=name))
             e["ms"] += ms
             e["n"] += 1
         for e in agg.values():
@@ -383,17 +405,29 @@ def run_b200(args):
             achieved = top["bytes"] / (top["us_per_launch"] * 1e-6) / 1e9
         share = top["ms_per_step"] / sum(e["ms_per_step"] for e in ktable.values())
         traffic = None                  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
         if os.path.exists(tpath):
             t = json.load(open(tpath)).get(top_key)
             if t:
                 traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
-        roof = {"bound": "hbm", "kernel": top_key, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": (achieved / peaks["hbm"]) if achieved else None, "traffic": traffic,
-                "peak_source": peaks["src"], "us_per_launch": top["us_per_launch"],
-                "launches_per_step": top["launches_per_step"], "share_of_kernel_time": share,
-                "algorithmic_bytes_per_launch": top["bytes"]}
         bpg, fpg = algorithmic_per_graph(c, batch)
+        # which roofline binds this configuration: bytes / HBM peak against flops / sustained tensor peak
+        tensor_bound = fpg / (peaks["tf_sust"] * 1e12) > bpg / (peaks["hbm"] * 1e9)
+        if tensor_bound and top.get("flops"):
+            tf = top["flops"] / (top["us_per_launch"] * 1e-6) / 1e12
+            roof = {"bound": "tensor", "kernel": top_key, "achieved": tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                    "frac": tf / peaks["tf_sust"], "traffic": traffic}
+        else:
+            roof = {"bound": "hbm", "kernel": top_key, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": (achieved / peaks["hbm"]) if achieved else None, "traffic": traffic}
+        roof.update({"peak_source": peaks["src"], "us_per_launch": top["us_per_launch"],
+                     "launches_per_step": top["launches_per_step"], "share_of_kernel_time": share,
+                     "algorithmic_bytes_per_launch": top["bytes"], "hbm_gbps": achieved,
+                     "hbm_frac": (achieved / peaks["hbm"]) if achieved else None})
+        # every row-streaming kernel against the HBM peak (algorithmic bytes / measured time)
+        roof["row_kernels"] = {k: {"us": round(v["us_per_launch"], 1), "gbps": round(v["bytes"] / (v["us_per_launch"] * 1e-6) / 1e9),
+                                   "hbm_frac": round(v["bytes"] / (v["us_per_launch"] * 1e-6) / 1e9 / peaks["hbm"], 3)}
+                               for k, v in ktable.items() if v["bytes"]}
         roof["whole_step"] = {
             "algorithmic_bytes_per_graph": bpg, "algorithmic_flops_per_graph": fpg,
             "hbm_frac": bpg * (value / world) / (peaks["hbm"] * 1e9),
@@ -420,7 +454,9 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,
                     "note": "pinned host inputs -> H2D (copy stream, double-buffered: batch i+1 copies while batch i "
-                            "computes) -> heads->CSR + distance kernels -> fwd+bwd+Adam -> loss D2H + host sync every step"},
+                            "computes) -> heads->CSR + distance kernels -> fwd+bwd+Adam -> loss D2H + host sync every step; the host rows "
+                            "are already bf16 with the padded pitch (a caller holding the reference's fp32 features pays a "
+                            "cast or twice the bytes)"},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "kernels": {k: {"us_per_launch": round(v["us_per_launch"], 2), "launches_per_step": v["launches_per_step"],

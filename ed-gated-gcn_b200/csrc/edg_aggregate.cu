@@ -235,6 +235,11 @@ aggregate_staged_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ 
       const int j = col_s[e];
       uint32_t w0, w1, w2, w3;
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(xs + (uint32_t)(j * pitch)));
+      if (sizeof(TI) == 2 && MODE == 0) {              // plain sum of bf16 rows: one mixed-precision add per element
+        add_bf16x2(w0, acc[0], acc[1]); add_bf16x2(w1, acc[2], acc[3]);
+        add_bf16x2(w2, acc[4], acc[5]); add_bf16x2(w3, acc[6], acc[7]);
+        continue;
+      }
       float v[8];
       if (sizeof(TI) == 2) {
         v[0] = __uint_as_float(w0 << 16); v[1] = __uint_as_float(w0 & 0xffff0000u);

@@ -83,6 +83,14 @@ template <> struct Vec16<__nv_bfloat16> {
   }
 };
 
+// lo += bf16(low half of w), hi += bf16(high half): the mixed-precision add of sm_100 (`add.f32.bf16`, SASS FHADD.BF16
+// with a half-register operand) -- one instruction per element where shift/mask + FADD needs two, bit-identical result
+// (bf16 -> fp32 is exact).  The row-summing loops of this library are issue-slot bound on exactly that unpack.
+__device__ __forceinline__ void add_bf16x2(uint32_t w, float& lo, float& hi) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tadd.rn.f32.bf16 %0, l, %0;\n\tadd.rn.f32.bf16 %1, h, %1;\n\t}"
+      : "+f"(lo), "+f"(hi) : "r"(w));
+}
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);

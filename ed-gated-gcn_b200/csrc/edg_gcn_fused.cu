@@ -466,11 +466,11 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
           }
           float acc[8];
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            acc[2 * w] = (__uint_as_float(v[0][w] << 16) + __uint_as_float(v[1][w] << 16)) +
-                         (__uint_as_float(v[2][w] << 16) + __uint_as_float(v[3][w] << 16));
-            acc[2 * w + 1] = (__uint_as_float(v[0][w] & 0xffff0000u) + __uint_as_float(v[1][w] & 0xffff0000u)) +
-                             (__uint_as_float(v[2][w] & 0xffff0000u) + __uint_as_float(v[3][w] & 0xffff0000u));
+          for (int w = 0; w < 4; ++w) {                      // FHADD.BF16: no unpack instructions (edg_common.cuh)
+            acc[2 * w] = __uint_as_float(v[0][w] << 16);
+            acc[2 * w + 1] = __uint_as_float(v[0][w] & 0xffff0000u);
+#pragma unroll
+            for (int u = 1; u < 4; ++u) add_bf16x2(v[u][w], acc[2 * w], acc[2 * w + 1]);
           }
           if (deg > 4) {                                     // one row in eight: four more slots
             uint32_t x[4][4];
@@ -480,12 +480,9 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[u][0]), "=r"(x[u][1]), "=r"(x[u][2]), "=r"(x[u][3]) : "r"(aT + ro));
             }
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              acc[2 * w] += (__uint_as_float(x[0][w] << 16) + __uint_as_float(x[1][w] << 16)) +
-                            (__uint_as_float(x[2][w] << 16) + __uint_as_float(x[3][w] << 16));
-              acc[2 * w + 1] += (__uint_as_float(x[0][w] & 0xffff0000u) + __uint_as_float(x[1][w] & 0xffff0000u)) +
-                                (__uint_as_float(x[2][w] & 0xffff0000u) + __uint_as_float(x[3][w] & 0xffff0000u));
-            }
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) add_bf16x2(x[u][w], acc[2 * w], acc[2 * w + 1]);
             if (deg > 8) {                                   // hubs: the rest of the row's entries from the global CSR
               int cnt = 0;
               for (int e = 0; e < deg; ++e) {
@@ -495,7 +492,7 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
                 uint32_t z[4];
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(z[0]), "=r"(z[1]), "=r"(z[2]), "=r"(z[3]) : "r"(aT + (uint32_t)j * (uint32_t)pitch));
 #pragma unroll
-                for (int w = 0; w < 4; ++w) { acc[2 * w] += __uint_as_float(z[w] << 16); acc[2 * w + 1] += __uint_as_float(z[w] & 0xffff0000u); }
+                for (int w = 0; w < 4; ++w) add_bf16x2(z[w], acc[2 * w], acc[2 * w + 1]);
               }
             }
           }
