@@ -90,15 +90,24 @@ __device__ __forceinline__ void lds_v4(uint32_t addr, float (&v)[4]) {
 }
 __device__ __forceinline__ void epi_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-// wait with back-off for the long waits of the helper warps (ring slot / buffer / accumulator stage free): a tight
-// try_wait loop would take issue slots from the epilogue warps of the same scheduler
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns = 64) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (ns) __nanosleep(ns);
-    if (++spins > (1u << 22)) __trap();
+// wait on an mbarrier phase; the hardware may park the thread for up to `hint_ns` per attempt (it wakes on completion),
+// so a waiting warp costs a few instructions per microsecond instead of a tight polling loop
+__device__ __forceinline__ void f2_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 1000) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 20)) __trap();
   }
 }
+
+// (the helper warps' long waits used to poll with __nanosleep back-off: 20 % of the kernel's executed instructions were
+// polling loops competing with the epilogue warps of the same scheduler)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t = 0) { f2_wait(bar, parity); }
 
 // order-preserving key of a bf16 value held in the UPPER 16 bits of x (lower 16 ignored) | low field
 __device__ __forceinline__ uint32_t pool_key(uint32_t x, uint32_t low) {
@@ -204,7 +213,7 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = P.idesc[half];
-      mbar_wait(wfull, 0);
+      f2_wait(wfull, 0);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int t = t_first; t < n_tiles; t += t_step, ++it) {
@@ -214,7 +223,7 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kFAccStride);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full(stage), phase);
+          f2_wait(full(stage), phase);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -334,7 +343,7 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
       }
     };
     if (patch && t_first < n_tiles) {
-      mbar_wait(cfull(0), 0);
+      f2_wait(cfull(0), 0);
       load_patch(reinterpret_cast<const int32_t*>(sm + P.off_csr));
     }
     int it = 0;
@@ -349,7 +358,7 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
       const uint8_t* sfirst = cs + 16;
       const uint32_t meta_s = cs_s + 32;
       EDG_TRACE();
-      mbar_wait(cfull(cb), cphase);
+      f2_wait(cfull(cb), cphase);
       EDG_TRACE();
       const int r0 = hdr[0], n = hdr[1], ns = hdr[2], s0 = hdr[3];
       // ---- patch entries of the tile: thread = column, one entry per sentence (tile-local u8 rows, 0xff = none); the
@@ -364,7 +373,7 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
           else pa_hi = (pa_hi & ~(0xffu << (8 * (s - 4)))) | (lr << (8 * (s - 4)));
         }
       }
-      mbar_wait(tfull(as), aphase);
+      f2_wait(tfull(as), aphase);
       EDG_TRACE();
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kFAccStride);
@@ -428,7 +437,7 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
         epi_bar(kEpiThreads);
         if (t + t_step < n_tiles) {                          // the next tile's entries: in flight during phase B
           const int cbn = (it + 1) % kFCsrBufs;
-          mbar_wait(cfull(cbn), (uint32_t)((it + 1) / kFCsrBufs) & 1u);
+          f2_wait(cfull(cbn), (uint32_t)((it + 1) / kFCsrBufs) & 1u);
           load_patch(reinterpret_cast<const int32_t*>(sm + P.off_csr + cbn * kFCsrBytes));
         }
       }

@@ -50,21 +50,6 @@ struct GcnLayer2Params {
   uint32_t off_a, off_u, off_adj, off_tab, off_meta, off_vec, off_bar;
 };
 
-// wait on an mbarrier phase; the hardware may park the thread for up to `hint_ns` per attempt (it wakes on completion),
-// so a waiting warp costs a few instructions per microsecond instead of a tight polling loop
-__device__ __forceinline__ void f2_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 1000) {
-  uint32_t ok = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
-    if (ok) break;
-    if (++spins > (1u << 20)) __trap();
-  }
-}
-
 __device__ __forceinline__ void f2_zero16(uint32_t addr) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }

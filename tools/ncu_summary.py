@@ -4,24 +4,41 @@
 """
 import collections, csv, subprocess, sys
 
-def launches(path):
+def _bytes(v, u):
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+
+def launches(path, steps=None):
+    """Per kernel: launches, isolated duration, DRAM bytes (when the list was taken with dram__bytes_*).  With `steps`,
+    only the launches after the last spin kernel (= the graph replays of the timed steps) are counted and per-step totals
+    are printed."""
     lines = [l for l in open(path) if not l.startswith("==")]
-    agg = collections.OrderedDict(); n = 0
-    for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
+    rows = list(csv.DictReader(lines))
+    ids = [int(r["ID"]) for r in rows if "spin_kernel" in r["Kernel Name"]]
+    first = (max(ids) + 1) if (steps and ids) else 0
+    agg = collections.OrderedDict(); seen = set()
+    for row in rows:
+        if "spin_kernel" in row["Kernel Name"] or int(row["ID"]) < first:   # bench.py's preload of the per-kernel pass
             continue
-        if "spin_kernel" in row["Kernel Name"]:       # bench.py's preload of the per-kernel pass, not part of a step
-            continue
+        a = agg.setdefault(row["Kernel Name"][:90], [0, 0.0, 0.0])
         v = float(row["Metric Value"].replace(",", ""))
-        v = v / 1000 if row["Metric Unit"] == "ns" else v * 1000 if row["Metric Unit"] == "ms" else v
-        a = agg.setdefault(row["Kernel Name"][:90], [0, 0.0]); a[0] += 1; a[1] += v; n += 1
+        if row.get("Metric Name") == "gpu__time_duration.sum":
+            a[1] += v / 1000 if row["Metric Unit"] == "ns" else v * 1000 if row["Metric Unit"] == "ms" else v
+            a[0] += 1
+        elif row.get("Metric Name", "").startswith("dram__bytes"):
+            a[2] += _bytes(v, row["Metric Unit"])
+    n = sum(a[0] for a in agg.values())
     tot = sum(a[1] for a in agg.values())
-    print(f"ncu launch list ({path}): {n} launches, {tot:.0f} us of kernel time (cold-cache, serialised: compare shares)\n")
-    print("| share | launches | avg us | kernel |\n|---:|---:|---:|---|")
+    dram = sum(a[2] for a in agg.values())
+    print(f"ncu launch list ({path}): {n} launches, {tot:.0f} us of kernel time (cold-cache, serialised: compare shares)")
+    if steps:
+        print(f"per step ({steps} steps): {n / steps:.0f} launches, {tot / steps:.0f} us serialised, "
+              f"{dram / steps / 1e6:.0f} MB of DRAM traffic (read + write)")
+    print("\n| share | launches | avg us | DRAM MB / launch | kernel |\n|---:|---:|---:|---:|---|")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         if a[1] / tot < 0.002:
             continue
-        print(f"| {a[1] / tot * 100:.1f}% | {a[0]} | {a[1] / a[0]:.1f} | `{k}` |")
+        print(f"| {a[1] / tot * 100:.1f}% | {a[0]} | {a[1] / a[0]:.1f} | {a[2] / a[0] / 1e6:.1f} | `{k}` |")
 
 WANT = [("gpu__time_duration.sum", "dur us"), ("dram__bytes_read.sum", "dram rd MB"), ("dram__bytes_write.sum", "dram wr MB"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
@@ -57,4 +74,7 @@ def full(path):
         print(f"| `{d[hdr.index('Kernel Name')][:60]}` | " + " | ".join(cells) + " |")
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else None)
+    else:
+        full(sys.argv[2])
