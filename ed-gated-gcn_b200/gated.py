@@ -544,11 +544,18 @@ class _GatedStackFn(torch.autograd.Function):
                 db_next = ops.colsum(dh)
                 du = ops.aggregate(dh, graph, mode=1)
             patch = None
-            if views_active:
-                patch = (ops.views_bwd_hmax(ctx.v_hmax, gates, g_xy, dgates, acc_view=Lyr - 1), v_arg[0])
+            patch_ready = None
             if gated:
-                with side.region():               # dgates are complete from here on
-                    da_gate = gate_backward()
+                # side stream, behind edg_head_du (which wrote d gate_L): the views' share of d gates / the patch for d h_1,
+                # then the gate MLPs' backward; this stream goes straight on to the weight gradient of layer L and only
+                # waits for the patch where it is consumed (the layer-1 launch below)
+                with side.region():
+                    if views_active:
+                        patch = (ops.views_bwd_hmax(ctx.v_hmax, gates, g_xy, dgates, acc_view=Lyr - 1), v_arg[0])
+                        if side.enabled:
+                            patch_ready = torch.cuda.Event()
+                            patch_ready.record(side.side)
+                    da_gate = gate_backward()     # dgates are complete from here on
             for l in range(Lyr - 1, -1, -1):
                 w, b = params[2 * l], params[2 * l + 1]
                 dW, _ = ops.wgrad(hs[l - 1] if l > 0 else xr, du, bias_of=0)
@@ -556,6 +563,8 @@ class _GatedStackFn(torch.autograd.Function):
                 grad_hook(grads_out[2 * l:2 * l + 2])
                 wk = ctx.w_n[l]                                                 # [in,out] = B operand of du W^T
                 if l > 0:
+                    if l == 1 and patch_ready is not None:
+                        torch.cuda.current_stream(dev).wait_event(patch_ready)
                     du, _, _, db_next = ops.gcn_layer(du, wk, None, graph, 1, plan, rows,
                                                       patch=patch if l == 1 else None, want_colsum=True)
                 else:
