@@ -75,13 +75,35 @@ _FUSED = os.environ.get("EDG_FUSED", "1") != "0"
 def _fused_plan(cfg, cd, D, graph, drop_p):
     """(tile_rows, plan) when the whole GCN chain can run on ``edg_gcn_layer``: bf16, no ReLU, no gate dropout, no
     BertAmir54 head, every sentence fits a tile.  Otherwise None (the unfused kernels cover everything)."""
-    if not _FUSED or cd != torch.bfloat16 or cfg["relu"] or drop_p > 0 or cfg["fc_sigmoid"]:
+    if not _FUSED or cd != torch.bfloat16 or cfg["relu"] or drop_p > 0 or cfg["fc_sigmoid"] or cfg.get("view_len") is not None:
         return None
     rows = ops.fused_tile_rows(D, D)
     if rows <= 0:
         return None
     plan = graph.tile_plan(rows)
     return None if plan is None else (rows, plan)
+
+
+def _masked_view_pool(h, graph: DepGraph, gates: torch.Tensor, view_len: torch.Tensor):
+    """The two view pools of BertAmir / BertAmir2 (bert_amir.py:141-142, :282-283): ``masked_fill(mask, -1e12)`` before
+    ``torch.max``, with ``mask`` = zeros then ones (data_utils.py:463-464), i.e. only the first ``view_len[b]`` rows of
+    sentence b take part.  Runs the ordinary pooling kernel on a graph of 2B sentences (prefix, masked rest, prefix, ...)
+    and keeps the prefixes; a sentence with nothing unmasked pools to the fill value and routes no gradient."""
+    V, B, D = gates.shape
+    sp = graph.sent_ptr.long()
+    vl = torch.minimum(view_len.to(device=sp.device, dtype=torch.int64).clamp_min(0), sp[1:] - sp[:-1])
+    sp2 = torch.empty(2 * B + 1, dtype=torch.int32, device=sp.device)
+    sp2[0::2] = sp.int()
+    sp2[1::2] = (sp[:-1] + vl).int()
+    rs = graph.row_sent.long()
+    local = torch.arange(graph.n_rows, device=sp.device) - sp[rs]
+    rs2 = (2 * rs + (local >= vl[rs]).long()).int()
+    g2 = DepGraph(sp2, graph.row_ptr, graph.col, rs2, 2 * B, graph.n_rows, graph.max_len)
+    gg = gates.repeat_interleave(2, dim=1).contiguous()
+    pooled, arg = ops.pool_fwd(h, g2, gg)
+    pooled, arg = pooled[:, 0::2].contiguous(), arg[:, 0::2].contiguous()
+    empty = (vl == 0)[None, :, None]
+    return torch.where(empty, torch.full_like(pooled, -1e12), pooled), torch.where(empty, torch.full_like(arg, -1), arg)
 
 
 def _side_stream(device: torch.device, which: int = 0) -> "torch.cuda.Stream":
@@ -152,7 +174,7 @@ class _GatedStackFn(torch.autograd.Function):
     then fc.weight, fc.bias.  ``cfg`` carries the non-tensor arguments."""
 
     @staticmethod
-    def forward(ctx, cfg, x, *params):
+    def forward(ctx, cfg, x, aspect, *params):
         graph: DepGraph = cfg["graph"]
         cd: torch.dtype = cfg["cdtype"]
         Lyr, pairs, lead = cfg["L"], cfg["pairs"], cfg["lead"]
@@ -184,7 +206,14 @@ class _GatedStackFn(torch.autograd.Function):
         gated = cfg["gated"]
         drop_p, seed = (cfg["drop_p"], cfg["seed"]) if gated else (0.0, None)
         h1m = None
-        a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
+        ctx.ext_aspect = aspect is not None
+        if aspect is not None:
+            # the trigger vector comes from the caller (BertAmir / BertAmir2: max-pool of the LSTM output over the
+            # trigger's word pieces, bert_amir.py:118) instead of the trigger row of x (bert_amir5.py:615-618)
+            a_raw = aspect.detach().float().contiguous()
+            s0 = ops.as_rows(torch.sigmoid(a_raw) if lead else a_raw, cd)
+        else:
+            a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
         gate_saved = []
         if gated:
             gates = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
@@ -267,6 +296,8 @@ class _GatedStackFn(torch.autograd.Function):
                             for v in range(Lyr):
                                 pv, av = ops.pool_fwd(h1m[v], graph, gates[v:v + 1])
                                 v_pooled[v], v_arg[v] = pv[0], av[0]
+                        elif cfg.get("view_len") is not None:
+                            v_pooled, v_arg = _masked_view_pool(hs[0], graph, gates, cfg["view_len"])
                         elif _PATCH_VIEWS:
                             v_pooled, v_arg, v_hmax = ops.pool_fwd(hs[0], graph, gates, want_hmax=True)
                         else:
@@ -603,8 +634,12 @@ class _GatedStackFn(torch.autograd.Function):
         da = ga_head.float() if ga_head is not None else None
         if da_gate is not None:
             da = da_gate if da is None else da + da_gate
+        d_aspect = None
         if da is not None:
-            ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
+            if ctx.ext_aspect:
+                d_aspect = da
+            else:
+                ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
         grads_out[-2], grads_out[-1] = d_fcw, d_fcb
         if ctx.x_padded:        # hand back the whole [N, pitch] allocation (padding columns are finite)
             dx = dx.as_strided((N, dx.stride(0)), (dx.stride(0), 1))
@@ -614,7 +649,7 @@ class _GatedStackFn(torch.autograd.Function):
                 dx = full
         if dx.dtype != ctx.x_dtype:
             dx = dx.to(ctx.x_dtype)
-        return (None, dx) + tuple(grads_out) + tuple(head_grads)
+        return (None, dx, d_aspect) + tuple(grads_out) + tuple(head_grads)
 
 
 class GatedGCNStack(nn.Module):
@@ -660,11 +695,18 @@ class GatedGCNStack(nn.Module):
 
     def forward(self, x: torch.Tensor, graph: DepGraph, anchor_index: torch.Tensor, dist_to_target: torch.Tensor,
                 logits_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
-                head_params: Sequence[torch.Tensor] = (), return_x_out: bool = False) -> StackOutput:
+                head_params: Sequence[torch.Tensor] = (), return_x_out: bool = False,
+                aspect: Optional[torch.Tensor] = None, view_len: Optional[torch.Tensor] = None) -> StackOutput:
         """x [N,D] packed rows (or [B,T,D] with a dense-compat graph), graph, sentence-local
         trigger index [B], distances (packed [N] or [B,T] for a dense-compat graph; int32/int64),
         ``logits_fn(a [B,D], pooled [B,D]) -> [B,C]`` = the model's ``dense`` head (:643), and the
-        parameters ``logits_fn`` closes over (so their gradients are delivered)."""
+        parameters ``logits_fn`` closes over (so their gradients are delivered).
+
+        ``aspect [B,D]`` (optional): the trigger vector, when the model computes it itself (BertAmir / BertAmir2 pool the
+        LSTM output over the trigger's word pieces, bert_amir.py:118, :259) instead of taking the trigger row of ``x``;
+        its gradient is returned through autograd.  ``view_len int [B]`` (optional): the two diversity pools only see the
+        first ``view_len[b]`` rows of sentence b -- ``masked_fill(mask, -1e12)`` of bert_amir.py:141-142 with the
+        reference's zeros-then-ones mask (``view_len = (mask == 0).sum(1)``); the final pool stays unmasked (:146)."""
         if not x.is_cuda:
             raise L.EdgError("GatedGCNStack runs on CUDA tensors only (there is no CPU path)")
         drop_p, seed = 0.0, None
@@ -689,8 +731,8 @@ class GatedGCNStack(nn.Module):
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
                    head_params=list(head_params), n_head=len(list(head_params)), grad_enabled=torch.is_grad_enabled(), grad_hook=self.grad_ready_hook,
                    relu=self.relu, return_x_out=return_x_out, gated=self.gated,
-                   drop_p=drop_p, seed=seed, fc_sigmoid=self.fc_sigmoid)
-        logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, *self._flat_params(),
+                   drop_p=drop_p, seed=seed, fc_sigmoid=self.fc_sigmoid, view_len=view_len)
+        logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, aspect, *self._flat_params(),
                                                                                  *cfg["head_params"])
         if shape3 is not None:
             scores = scores.reshape(shape3[0], shape3[1])

@@ -48,7 +48,18 @@ def _install_stubs() -> None:
 
     mod("layers")
     mod("layers.squeeze_embedding", SqueezeEmbedding=_Missing)
-    mod("layers.dynamic_rnn", DynamicLSTM=_Missing)
+    class _LstmStandIn(torch.nn.Module):
+        """Stands for layers/dynamic_rnn.py (not in the repository): an LSTM over the padded batch; the lengths are
+        ignored.  Only BertAmir / BertAmir2 use it, upstream of the block whose input the fixture captures."""
+        def __init__(self, input_size, hidden_size, num_layers=1, batch_first=True, bidirectional=False, **kw):
+            super().__init__()
+            self.rnn = torch.nn.LSTM(input_size, hidden_size, num_layers=num_layers, batch_first=batch_first,
+                                     bidirectional=bidirectional)
+
+        def forward(self, x, x_len):
+            return self.rnn(x)
+
+    mod("layers.dynamic_rnn", DynamicLSTM=_LstmStandIn)
     mod("spacy")
     mod("pytorch_pretrained_bert", BertTokenizer=_Missing, BertModel=_Missing)
     sys.path.insert(0, REF)
@@ -279,6 +290,98 @@ def golden_bertdm(BertDM) -> None:
     print("bertdm.npz", {k: v.shape for k, v in out.items()})
 
 
+def golden_bert_amir(BertAmir) -> None:
+    """The WHOLE ``BertAmir.forward`` + backward (models/bert_amir.py:83-156) with a stub BERT and a stand-in for the
+    absent ``layers.dynamic_rnn.DynamicLSTM`` (an nn.LSTM that ignores the lengths: the LSTM is upstream of the block,
+    its output is captured as the block's input).  What the fixture pins: the masked diversity pools
+    (``masked_fill(mask, -1e12)``, :141-142), the word-piece-pooled trigger vector (:118) feeding the 3 x (Linear,
+    Sigmoid) gates (:31-36), ``fc`` as a plain Linear (:38) and the ``dense`` head over cat[pooled_output, out] (:149)."""
+    from ed_gated_gcn_b200 import synth
+    from oracle import ref_oracle as O
+    torch.manual_seed(31)
+    B, ORI_ML, BERT_ML, C, H = 6, 20, 30, 5, 32
+    batch = synth.make_batch(B, 4, 14, seed=31)
+    T = int(batch.lengths.max())
+    rng = np.random.default_rng(31)
+    pieces = [rng.integers(1, 3, size=int(n)).tolist() for n in batch.lengths]        # word pieces per word
+
+    class StubBert(torch.nn.Module):
+        def forward(self, ids, seg, output_all_encoded_layers=True):
+            g = torch.Generator().manual_seed(9)
+            Bb, Lb = ids.shape
+            return [torch.randn(Bb, Lb, 768, generator=g) * 0.5 for _ in range(12)], torch.randn(Bb, 768, generator=g)
+
+    opt = types.SimpleNamespace(device="cpu", dropout=0.0, polarities_dim=C, n_layer=1, bert_dim=768, hidden_dim=H)
+    model = BertAmir(StubBert(), opt)
+    g = torch.Generator().manual_seed(313)
+    O.reference_init_([p for n, p in model.named_parameters()], g)      # train.py:75-84
+    model.train()
+
+    # inputs as data_utils.py:455-505 lays them out: [CLS] pieces [SEP] trigger pieces [SEP]
+    transform = np.zeros((B, ORI_ML, BERT_ML), dtype=np.float32)
+    aspect_mask = np.ones((B, BERT_ML), dtype=np.float32)
+    cls_mask = np.ones((B, BERT_ML), dtype=np.float32)
+    cls_len = np.zeros(B, dtype=np.int64)
+    for b in range(B):
+        tr = O.wordpiece_transform_ref(pieces[b], ORI_ML, BERT_ML)
+        transform[b] = np.asarray(tr, dtype=np.float32)
+        starts = 1 + np.concatenate([[0], np.cumsum(pieces[b])[:-1]])
+        a0, al = int(starts[batch.anchor[b]]), int(pieces[b][batch.anchor[b]])
+        aspect_mask[b, a0:a0 + al] = 0.0                                  # data_utils.py:470-472
+        cls_len[b] = 1 + sum(pieces[b]) + 1 + al + 1
+        cls_mask[b, :cls_len[b]] = 0.0                                    # data_utils.py:463-464
+    # make the mask bite: shorten one sentence's unmasked prefix below the padded length T (the reference's mask is
+    # indexed by WORD position but built from the WORD-PIECE length, so it only ever removes pad rows)
+    adj = np.stack([O.dense_adjacency_from_heads(h, ORI_ML) for h in batch.heads_list()]).astype(np.float32)
+    dist = [O.pad_distance(O.tree_distance_bfs(h, int(batch.anchor[b])), ORI_ML, "max+1") for b, h in enumerate(batch.heads_list())]
+    inputs = {
+        "sentence_length": torch.tensor(batch.lengths, dtype=torch.long),
+        "cls_text_sep_aspect_sep_length": torch.tensor(cls_len, dtype=torch.long),
+        "cls_text_sep_aspect_sep_indices": torch.zeros(B, BERT_ML, dtype=torch.long),
+        "cls_text_sep_aspect_sep_segments_ids": torch.zeros(B, BERT_ML, dtype=torch.long),
+        "cls_text_sep_aspect_sep_aspect_mask": torch.tensor(aspect_mask),
+        "cls_text_sep_aspect_sep_mask": torch.tensor(cls_mask),
+        "transform": torch.tensor(transform),
+        "anchor_index": torch.tensor(batch.anchor, dtype=torch.long),
+        "dist_to_target": torch.tensor(dist, dtype=torch.long),
+        "dependency_graph": torch.tensor(adj),
+    }
+    targets = torch.tensor(np.arange(B) % C, dtype=torch.long)
+    cap = {}
+
+    def gate_pre(mod, inp):
+        if "aspect" not in cap:
+            inp[0].retain_grad()
+            cap["aspect"] = inp[0]
+
+    def gc1_pre(mod, inp):
+        inp[0].retain_grad()
+        cap["x"] = inp[0]
+
+    model.gate1.register_forward_pre_hook(gate_pre)
+    model.gc1.register_forward_pre_hook(gc1_pre)
+    model.dense.register_forward_pre_hook(lambda mod, inp: cap.__setitem__("dense_in", inp[0]))
+    logits, xy, kl = model(inputs)                                       # bert_amir.py:83-156
+    loss = torch.nn.functional.cross_entropy(logits, targets) + 0.01 * xy + 0.01 * kl
+    loss.backward()
+    L = int(cls_len.max())
+    out = {
+        "heads": batch.heads, "sent_ptr": batch.sent_ptr, "anchor": batch.anchor, "T": np.int64(T), "targets": targets.numpy(),
+        "x": cap["x"].detach().numpy(), "dx": cap["x"].grad.numpy(),
+        "aspect": cap["aspect"].detach().numpy(), "daspect": cap["aspect"].grad.numpy(),
+        "adj": adj[:, :T, :T], "dist": np.asarray(dist, dtype=np.int64)[:, :T], "view_mask": cls_mask[:, :T],
+        "pooled_output": cap["dense_in"].detach().numpy()[:, :768],
+        "logits": logits.detach().numpy(), "xy": xy.detach().numpy(), "kl": kl.detach().numpy(), "loss": loss.detach().numpy(),
+    }
+    for n, p in model.named_parameters():
+        if n.startswith(("gc1.", "gc2.", "gate1.", "gate2.", "fc.", "dense.")):
+            out["p_" + n] = p.detach().numpy()
+            out["g_" + n] = p.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "bert_amir.npz"), **out)
+    print("bert_amir.npz", {k: v.shape for k, v in out.items() if k[:2] not in ("p_", "g_")},
+          "masked positions inside T:", int(cls_mask[:, :T].sum()))
+
+
 def main() -> None:
     os.makedirs(GOLD, exist_ok=True)
     _install_stubs()
@@ -292,6 +395,8 @@ def main() -> None:
     golden_block55(BertAmir54, "block54.npz", seed=54)
     from models.bertdm import BertDM                   # reference, unmodified
     golden_bertdm(BertDM)
+    from models.bert_amir import BertAmir              # reference, unmodified (DynamicLSTM: stand-in below)
+    golden_bert_amir(BertAmir)
 
 
 if __name__ == "__main__":

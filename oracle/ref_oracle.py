@@ -227,7 +227,8 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
                     lead_sigmoid: bool = True, forced_view_arg: Optional[torch.Tensor] = None,
                     forced_final_arg: Optional[torch.Tensor] = None,
                     gate_masks: Optional[Sequence[torch.Tensor]] = None,
-                    fc_sigmoid: bool = False) -> Dict[str, torch.Tensor]:
+                    fc_sigmoid: bool = False, aspect: Optional[torch.Tensor] = None,
+                    view_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """The canonical block, bert_amir5.py:615-648, for ``L = len(gcn_params)``
     layers (the reference has L = 2: gc1, gc2).
 
@@ -251,11 +252,16 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
     the broadcast gates (:624-625) with the random draw made explicit; ``None`` = dropout p = 0 / eval mode.
 
     ``fc_sigmoid`` = BertAmir54, whose ``fc`` is ``Sequential(Sigmoid, Linear)`` (:464-465, applied at :538).
+
+    ``aspect [B,D]`` / ``view_mask [B,T] bool`` = BertAmir and BertAmir2 (models/bert_amir.py): the trigger vector is
+    the max-pool of the LSTM output over the trigger's word pieces (:118) and is handed in, and the two diversity
+    pools run on ``masked_fill(mask, -1e12)`` (:141-142, INFINITY_NUMBER = 1e12, :11); the final pool is unmasked (:146).
     """
     B, T, D = x.shape
     L = len(gcn_params)
     # :604-605, :615-618 -- the trigger row of the LSTM output
-    aspect = x[torch.arange(B), anchor_index]                       # [B,D]
+    if aspect is None:
+        aspect = x[torch.arange(B), anchor_index]                   # [B,D]
     gates = [gate_mlp_ref(aspect, gp, lead_sigmoid) for gp in gate_params]   # :621-622 (dropout p=0)
     h = x
     hs = []
@@ -270,7 +276,10 @@ def gated_block_ref(x: torch.Tensor, adj: torch.Tensor, anchor_index: torch.Tens
 
     # :621-625 -- gates broadcast over the tokens (`.repeat(1,T).view`), then dropped per (token, column)
     gb = [g[:, None, :].expand(B, T, D) * (1.0 if gate_masks is None else gate_masks[i]) for i, g in enumerate(gates)]
-    views = [pool(h1 * gb[i], None if forced_view_arg is None else forced_view_arg[i])
+    def masked(t):                                                    # bert_amir.py:141-142
+        return t if view_mask is None else t.masked_fill(view_mask.bool()[:, :, None], -1e12)
+
+    views = [pool(masked(h1 * gb[i]), None if forced_view_arg is None else forced_view_arg[i])
              for i in range(L)]                                       # :627-636
     xy = x.new_zeros(())
     for i in range(L):

@@ -165,3 +165,32 @@ def test_block54_matches_full_reference_forward_backward():
             assert rel_err(p.grad, z["g_" + name]) < 1e-4, name
             continue
         assert rel_err(p.grad, z["g_" + name]) < 1e-5, name
+
+
+def test_bert_amir_block_matches_full_reference_forward_backward():
+    """BertAmir (models/bert_amir.py:83-156): masked diversity pools (``masked_fill(mask, -1e12)``, :141-142), the
+    word-piece-pooled trigger vector (:118), 3 x (Linear, Sigmoid) gates without a leading Sigmoid (:31-36), ``fc`` a
+    plain Linear (:38), ``dense`` over cat[pooled_output, out] (:149) -- against the reference's own forward + backward."""
+    z = np.load(os.path.join(GOLDEN, "bert_amir.npz"))
+    P = {k[2:]: torch.tensor(z[k], requires_grad=True) for k in z.files if k.startswith("p_")}
+    x = torch.tensor(z["x"], requires_grad=True)
+    aspect = torch.tensor(z["aspect"], requires_grad=True)
+    pooled_output = torch.tensor(z["pooled_output"])
+    assert z["view_mask"].sum() > 0                      # the mask removes rows inside the padded length
+    logits_fn = lambda a, pooled: torch.cat([pooled_output, pooled], dim=1) @ P["dense.weight"].t() + P["dense.bias"]
+    out = O.gated_block_ref(
+        x, torch.tensor(z["adj"]), torch.tensor(z["anchor"], dtype=torch.long), torch.tensor(z["dist"]),
+        [(P["gc1.weight"], P["gc1.bias"]), (P["gc2.weight"], P["gc2.bias"])],
+        [[(P[f"gate{l}.{i}.weight"], P[f"gate{l}.{i}.bias"]) for i in (0, 2, 4)] for l in (1, 2)],
+        P["fc.weight"], P["fc.bias"], logits_fn, lead_sigmoid=False, aspect=aspect, view_mask=torch.tensor(z["view_mask"]))
+    loss = O.block_loss_ref(out, torch.tensor(z["targets"]))
+    loss.backward()
+    for k in ("logits", "xy", "kl"):
+        assert rel_err(out[k], z[k]) < 2e-6, k
+    assert rel_err(loss, z["loss"]) < 2e-6
+    assert rel_err(x.grad, z["dx"]) < 1e-5
+    assert rel_err(aspect.grad, z["daspect"]) < 1e-5
+    for name, p in P.items():
+        if name == "fc.bias":
+            continue
+        assert rel_err(p.grad, z["g_" + name]) < 1e-5, name
