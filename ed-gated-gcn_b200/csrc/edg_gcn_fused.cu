@@ -455,16 +455,20 @@ gcn_layer_kernel(const __grid_constant__ GcnLayerParams P) {
             atomicMax(tab + cbase + 1, pool_key(vmax[w], 0xffffu - (varg[w] >> 16)));
           }
         };
-        __nv_bfloat16* yp = P.y + (int64_t)(r0 + sl) * P.ldy + gc8;
-        const int64_t ystep = (int64_t)nsl * P.ldy;
+        // a slice owns a CONTIGUOUS block of rows: it then crosses a sentence boundary (= one flush of eight shared-memory
+        // atomics) once or twice per tile instead of once per sentence of the tile
+        const int rps = (n + nsl - 1) / nsl;                  // rows per slice
+        const int i_beg = sl * rps, i_end = (P.debug & 1) ? 0 : min(n, i_beg + rps);
+        __nv_bfloat16* yp = P.y + (int64_t)(r0 + i_beg) * P.ldy + gc8;
+        const int64_t ystep = P.ldy;
         uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-        if (sl < n) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(meta_s + 16u * sl));
+        if (i_beg < n) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(meta_s + 16u * i_beg));
 #pragma unroll 1
-        for (int i = sl; i < ((P.debug & 1) ? 0 : n); i += nsl, yp += ystep) {
+        for (int i = i_beg; i < i_end; ++i, yp += ystep) {
           const uint32_t nb_lo = m0, nb_hi = m1, info = m2, e_glob = m3;
           const int deg = info & 0xffu, s = (info >> 8) & 0xffu;
-          if (i + nsl < n)
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(meta_s + 16u * (i + nsl)));
+          if (i + 1 < i_end)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(meta_s + 16u * (i + 1)));
           float inv;
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(inv) : "r"(lut_s + 4u * deg));
           uint32_t v[4][4];
