@@ -171,9 +171,9 @@ def wgrad_batch(a_list, b_list, bias_of: int = 0):
     nbytes = L.load().edg_wgrad_batch_workspace(n, R, K1, K2)
     ws = torch.empty((nbytes + 255) // 4, dtype=torch.float32, device=dev)
     P = ctypes.c_void_p * n
-    L.call("edg_wgrad_batch", n, P(*[a.data_ptr() for a in a_list]), lda, K1, P(*[b.data_ptr() for b in b_list]), ldb, K2,
-           L.dt(a_list[0]), R, P(*[dW[i].data_ptr() for i in range(n)]), K2,
-           P(*[db[i].data_ptr() for i in range(n)]) if bias_of else None, bias_of, L.ptr(ws), ws.numel() * 4, L.stream())
+    L.call("edg_wgrad_batch", n, P(*[L.ptr(a) for a in a_list]), lda, K1, P(*[L.ptr(b) for b in b_list]), ldb, K2,
+           L.dt(a_list[0]), R, P(*[L.ptr(dW[i]) for i in range(n)]), K2,
+           P(*[L.ptr(db[i]) for i in range(n)]) if bias_of else None, bias_of, L.ptr(ws), ws.numel() * 4, L.stream())
     return [dW[i] for i in range(n)], ([db[i] for i in range(n)] if bias_of else [None] * n)
 
 
@@ -192,13 +192,13 @@ def mlp_chain(mode: int, a0_list, stages, M: int, D: int) -> None:
         for s_i, st in enumerate(stages[g]):
             e = arr[g * n_stages + s_i]
             w, y, out, bias = st["w"], st.get("y"), st.get("out"), st.get("bias")
-            e.w, e.ldw = w.data_ptr(), ld(w)
-            e.bias = bias.data_ptr() if bias is not None else None
-            e.y, e.ldy = (y.data_ptr(), ld(y)) if y is not None else (None, 0)
-            e.out, e.ldo = (out.data_ptr(), ld(out)) if out is not None else (None, 0)
+            e.w, e.ldw = L.ptr(w), ld(w)
+            e.bias = L.ptr(bias)
+            e.y, e.ldy = (L.ptr(y), ld(y)) if y is not None else (None, 0)
+            e.out, e.ldo = (L.ptr(out), ld(out)) if out is not None else (None, 0)
             e.out_dtype = L.dt(out) if out is not None else 0
     P = ctypes.c_void_p * n_groups
-    L.call("edg_mlp_chain", mode, n_groups, n_stages, P(*[a.data_ptr() for a in a0_list]), ld(a0_list[0]), arr, M, D,
+    L.call("edg_mlp_chain", mode, n_groups, n_stages, P(*[L.ptr(a) for a in a0_list]), ld(a0_list[0]), arr, M, D,
            L.stream())
 
 
@@ -238,7 +238,7 @@ def cast_weights_batch(items, dtype: torch.dtype):
         m = min(32, n - i0)
         P, I32, I64 = ctypes.c_void_p * m, ctypes.c_int32 * m, ctypes.c_int64 * m
         sl = slice(i0, i0 + m)
-        L.call("edg_cast_batch", m, P(*[w.data_ptr() for w in ws[sl]]), P(*[o.data_ptr() for o in outs[sl]]),
+        L.call("edg_cast_batch", m, P(*[L.ptr(w) for w in ws[sl]]), P(*[L.ptr(o) for o in outs[sl]]),
                I32(*[w.shape[0] for w in ws[sl]]), I32(*[w.shape[1] for w in ws[sl]]),
                I64(*[w.stride(0) for w in ws[sl]]), I64(*lds[sl]), I32(*[int(tr) for _, tr in items[sl]]),
                L.dt(dtype), L.stream())

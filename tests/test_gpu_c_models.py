@@ -593,3 +593,41 @@ def test_stack_rejects_cpu_tensors():
     stack = E.GatedGCNStack(8, 2, 2, dropout=0.25)
     with pytest.raises(EdgError):
         stack(torch.zeros(3, 8), None, torch.zeros(1), torch.zeros(3), lambda a, p: a)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_on_a_second_gpu_with_device_0_current():
+    """The reference selects its GPU with `--device cuda:N` and never calls set_device (train.py:286): tensors live on
+    cuda:1 while device 0 is current.  Every launch must go to the tensors' device and its current stream, and the
+    shared-memory opt-in of the kernels must happen per device."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import synth
+    assert torch.cuda.current_device() == 0
+    dev1 = torch.device("cuda", 1)
+    batch = synth.make_batch(40, 3, 30, seed=12)
+    D, C = 300, 5
+    outs = []
+    for dev in (torch.device("cuda", 0), dev1):
+        torch.manual_seed(9)
+        stack = E.GatedGCNStack(D, 2, C, compute_dtype="bf16").to(dev)
+        dense = torch.nn.Linear(2 * D, C).to(dev)
+        gen = torch.Generator().manual_seed(4)
+        O.reference_init_(list(stack.parameters()) + list(dense.parameters()), gen)
+        x = torch.randn(batch.n_rows, D, generator=gen).to(dev).requires_grad_(True)
+        graph = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=dev)
+        anchor = torch.from_numpy(batch.anchor).to(dev)
+        out = stack(x, graph, anchor, E.tree_distance(graph, anchor), lambda a, p: dense(torch.cat([a, p], 1)),
+                    head_params=list(dense.parameters()))
+        loss = out.logits.square().mean() + out.xy + out.kl
+        loss.backward()
+        torch.cuda.synchronize(dev)
+        assert x.grad.device == dev
+        outs.append((out.logits.detach().cpu(), float(out.kl), x.grad.cpu(), stack.gc1.weight.grad.cpu()))
+        # the drop-in layer with a dense adjacency on that device as well
+        layer = E.GraphConvolution(16, 16, None).to(dev)
+        xs, adj, T = dense_inputs(synth.make_batch(5, 3, 9, seed=1), 16, seed=1)
+        y = layer(xs.to(dev), adj.to(dev))
+        assert rel(y, O.gcn_layer_ref(xs, adj, layer.weight.detach().cpu(), layer.bias.detach().cpu())) < 1e-5
+    assert torch.cuda.current_device() == 0
+    for a, b in zip(outs[0], outs[1]):              # same arithmetic on both devices: bitwise equal
+        assert (torch.equal(a, b) if torch.is_tensor(a) else a == b)
