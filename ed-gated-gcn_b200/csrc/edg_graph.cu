@@ -7,8 +7,13 @@ namespace edg {
 constexpr int kMaxSentence = 4096;
 constexpr int kUnreachablePlusOne = 100001;   // data_utils.py:311 + the final "+1" of :323
 
-__device__ __forceinline__ int clean_head(int h, int i, int n) {
-  return (h < 0 || h >= n || h == i) ? -1 : h;   // malformed heads are treated as roots
+// head of token i of a sentence whose raw heads start at `hs`.  Malformed heads (out of range, self) are treated as
+// roots; of a mutual pair h[i] = j, h[j] = i the higher token becomes a root, so the edge is stored ONCE -- the set
+// semantics of graph.py:73-74 (`m[s][t] = m[t][s] = 1`), and what keeps count and fill kernels consistent.
+__device__ __forceinline__ int clean_head(const int32_t* __restrict__ hs, int i, int n) {
+  const int h = hs[i];
+  if (h < 0 || h >= n || h == i) return -1;
+  return (hs[h] == i && i > h) ? -1 : h;
 }
 
 // ---- heads -> CSR ----------------------------------------------------------
@@ -20,7 +25,7 @@ __global__ void heads_count_kernel(const int32_t* __restrict__ heads, const int3
   int lane = threadIdx.x & 31;
   int base = sent_ptr[b], n = sent_ptr[b + 1] - base;
   int cnt = 0;
-  for (int i = lane; i < n; i += 32) cnt += 1 + 2 * (clean_head(heads[base + i], i, n) >= 0);
+  for (int i = lane; i < n; i += 32) cnt += 1 + 2 * (clean_head(heads + base, i, n) >= 0);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) sent_nnz[b] = cnt;
@@ -68,14 +73,15 @@ __global__ void scan_exclusive_kernel(const int32_t* in, int32_t* out, int n) { 
 // in ascending token order, which yields the ascending column order directly.
 __global__ void heads_fill_kernel(const int32_t* __restrict__ heads, const int32_t* __restrict__ sent_ptr,
                                   const int32_t* __restrict__ sent_off, int32_t* __restrict__ row_ptr,
-                                  int32_t* __restrict__ col, int32_t* __restrict__ row_sent, int B, int N) {
+                                  int32_t* __restrict__ col, int32_t* __restrict__ row_sent, int B, int N, int cap) {
   extern __shared__ int32_t sm[];
   const int b = blockIdx.x;
   const int base = sent_ptr[b], n = sent_ptr[b + 1] - base;
+  if (n > cap) __trap();      // the caller's max_len (it sizes the shared arrays) is smaller than this sentence: fail loudly
   int32_t* h = sm;            // cleaned heads [n]
   int32_t* deg = sm + n;      // row lengths -> exclusive offsets [n+1]
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    h[i] = clean_head(heads[base + i], i, n);
+    h[i] = clean_head(heads + base, i, n);
     deg[i] = 0;
   }
   __syncthreads();
@@ -166,10 +172,11 @@ __global__ void dense_fill_kernel(const T* __restrict__ adj, int rows, int Tn, i
 // equals data_utils.py:302-323 on trees and forests).
 __global__ void tree_dist_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                  const int32_t* __restrict__ sent_ptr, const int32_t* __restrict__ anchor,
-                                 int32_t* __restrict__ dist) {
+                                 int32_t* __restrict__ dist, int cap) {
   extern __shared__ int32_t d[];
   const int b = blockIdx.x;
   const int base = sent_ptr[b], n = sent_ptr[b + 1] - base;
+  if (n > cap) __trap();      // max_len smaller than this sentence (see heads_fill_kernel)
   for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = -1;
   __syncthreads();
   int a = anchor[b];
@@ -227,7 +234,7 @@ extern "C" int edg_csr_from_heads(const int32_t* heads, const int32_t* sent_ptr,
   scan_exclusive_kernel<<<1, 1024, 0, s>>>(sent_nnz, sent_nnz, B);
   int threads = max_len <= 64 ? 64 : (max_len <= 128 ? 128 : 256);
   size_t smem = (2 * (size_t)max_len + 1) * sizeof(int32_t);
-  heads_fill_kernel<<<B, threads, smem, s>>>(heads, sent_ptr, sent_nnz, row_ptr, col, row_sent, B, N);
+  heads_fill_kernel<<<B, threads, smem, s>>>(heads, sent_ptr, sent_nnz, row_ptr, col, row_sent, B, N, max_len);
   return check_launch();
 }
 
@@ -270,7 +277,7 @@ extern "C" int edg_tree_dist(const int32_t* row_ptr, const int32_t* col, const i
   if (!row_ptr || !col || !sent_ptr || !anchor || !dist) return EDG_ERR_ARG;
   if (max_len > 8192) return EDG_ERR_UNSUPPORTED;
   int threads = max_len <= 64 ? 64 : (max_len <= 128 ? 128 : 256);
-  tree_dist_kernel<<<B, threads, (size_t)max_len * sizeof(int32_t), (cudaStream_t)stream>>>(row_ptr, col, sent_ptr, anchor, dist);
+  tree_dist_kernel<<<B, threads, (size_t)max_len * sizeof(int32_t), (cudaStream_t)stream>>>(row_ptr, col, sent_ptr, anchor, dist, max_len);
   return check_launch();
 }
 

@@ -43,6 +43,22 @@ def test_csr_from_heads_forest_and_malformed_heads():
     assert np.array_equal(g.col.cpu().numpy()[:len(want["col"])], want["col"])
 
 
+def test_csr_from_heads_mutual_pair_is_one_edge():
+    """h[i] = j and h[j] = i: the reference stores the pair once (`m[s][t] = m[t][s] = 1`, graph.py:73-74: set semantics).
+    The CSR must hold exactly the non-zeros of that matrix -- no uninitialised column slot -- and the distance kernel
+    must terminate on it."""
+    import ed_gated_gcn_b200 as E
+    heads = np.array([1, 0, 0, 2, 5, 4, -1], dtype=np.int32)        # (0,1) and (4,5) are mutual pairs
+    sp = np.array([0, 7], dtype=np.int32)
+    g = E.build_graph(torch.from_numpy(heads), torch.from_numpy(sp), device=DEV)
+    adj = O.dense_adjacency_from_edges([(int(h) + 1, i + 1) for i, h in enumerate(heads) if h >= 0], 7)
+    rp, col = O.csr_from_dense(adj)
+    assert np.array_equal(g.row_ptr.cpu().numpy(), rp)
+    assert np.array_equal(g.col.cpu().numpy()[:len(col)], col)
+    d = E.tree_distance(g, torch.tensor([3], dtype=torch.int32, device=DEV)).cpu().numpy()
+    assert d.tolist() == [3, 4, 2, 1, 100001, 100001, 100001]        # 4, 5, 6 cannot reach the trigger
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.int64])
 def test_csr_from_dense_bit_exact(dtype):
     import ed_gated_gcn_b200 as E
