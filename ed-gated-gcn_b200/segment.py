@@ -5,6 +5,9 @@
   entries over the ``l`` contiguous pieces of a word) as a segment mean over contiguous rows;
   ``transform_bmm`` keeps the reference's dense ``[B,T,L] x [B,L,D]`` call shape.
 * ``lr_pool`` -- N4: BertDM's left/right max-pooling around the trigger (models/bertdm.py:116-140, :174-185).
+* ``span_max`` -- the trigger vector of BertAmir / BertAmir2: max-pool of the LSTM output over the trigger's word
+  pieces (``torch.max(x.masked_fill(aspect_mask, -1e12), 1)``, models/bert_amir.py:118, :259) as a max over one
+  contiguous run of rows per sentence.
 
 CUDA tensors only; no fallback.
 """
@@ -123,3 +126,61 @@ def lr_pool(h: torch.Tensor, graph, anchor_index: torch.Tensor, T_pad: Optional[
     anchor = anchor_index.to(device=h.device, dtype=torch.int32).contiguous()
     pooled, arg = _LRPoolFn.apply(h, graph.sent_ptr, anchor, T_pad if T_pad is not None else graph.max_len, cd)
     return (pooled, arg) if return_arg else pooled
+
+
+class _SpanMaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, span_start, span_len, max_len, cdtype):
+        from .graph import DepGraph
+        xr = ops.as_rows(x, cdtype)
+        P, D = xr.shape
+        B = span_start.numel()
+        dev = x.device
+        # the pooling kernel works on a partition of the rows into "sentences": gap, span, gap, span, ..., gap
+        sp = torch.empty(2 * B + 2, dtype=torch.int32, device=dev)
+        sp[0] = 0
+        sp[1:-1:2] = span_start
+        sp[2:-1:2] = span_start + span_len
+        sp[-1] = P
+        row_sent = torch.bucketize(torch.arange(P, device=dev, dtype=torch.int32), sp[1:].contiguous(), right=True).int()
+        g = DepGraph(sp, sp, sp, row_sent, 2 * B + 1, P, int(max_len))           # (row_ptr / col are not used by pooling)
+        ones = torch.ones((1, 2 * B + 1, D), dtype=torch.float32, device=dev)
+        pooled, arg = ops.pool_fwd(xr, g, ones)
+        pooled, arg = pooled[0, 1::2].contiguous(), arg[0, 1::2].contiguous()
+        empty = (span_len == 0)[:, None]
+        pooled = torch.where(empty, torch.full_like(pooled, -1e12), pooled)      # an all-masked row pools to the fill value
+        ctx.save_for_backward(torch.where(empty, torch.full_like(arg, -1), arg))
+        ctx.meta = (P, D, cdtype, x.dtype)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        P, D, cd, xdt = ctx.meta
+        dx = ops.alloc_rows(P, D, torch.float32, g.device, zero=True)
+        ld = dx.stride(0)
+        flat = dx.as_strided((P * ld,), (1,))
+        ok = arg >= 0
+        idx = (arg.long().clamp_min(0) * ld + torch.arange(D, device=g.device)[None, :])[ok]
+        flat.index_add_(0, idx, g.float()[ok])                                   # one target per (sentence, column): no duplicates
+        return (dx if dx.dtype == xdt else dx.to(xdt)), None, None, None, None
+
+
+def span_max(x_rows: torch.Tensor, span_start: torch.Tensor, span_len: torch.Tensor, max_len: Optional[int] = None,
+             compute_dtype=None) -> torch.Tensor:
+    """``[B,D]`` = max over rows ``span_start[b] .. +span_len[b]`` of the packed rows ``x_rows [P,D]`` (first row wins
+    ties, as ``torch.max``); spans ascending and disjoint (one per sentence).  For ``x [B,L,D]`` with the reference's
+    ``aspect_mask`` (zeros on the trigger's word pieces, data_utils.py:470-472): ``span_start = b*L + first zero``,
+    ``span_len = number of zeros``.  ``max_len`` = longest run between span boundaries (sizes the staging window; read
+    back from the device when omitted)."""
+    if not x_rows.is_cuda:
+        raise L.EdgError("span_max runs on CUDA tensors only (there is no CPU path)")
+    cd = _compute_dtype(compute_dtype) if compute_dtype is not None else (x_rows.dtype if x_rows.dtype in L.DTYPES else torch.float32)
+    dev = x_rows.device
+    s = span_start.to(device=dev, dtype=torch.int32).contiguous()
+    n = span_len.to(device=dev, dtype=torch.int32).contiguous()
+    if max_len is None:
+        bounds = torch.cat([torch.zeros(1, dtype=torch.int32, device=dev), torch.stack([s, s + n], 1).reshape(-1),
+                            torch.full((1,), x_rows.shape[0], dtype=torch.int32, device=dev)])
+        max_len = int((bounds[1:] - bounds[:-1]).max().item())
+    return _SpanMaxFn.apply(x_rows, s, n, max_len, cd)

@@ -360,6 +360,7 @@ def golden_bert_amir(BertAmir) -> None:
 
     model.gate1.register_forward_pre_hook(gate_pre)
     model.gc1.register_forward_pre_hook(gc1_pre)
+    model.text_lstm.register_forward_hook(lambda mod, inp, outp: cap.__setitem__("x_lstm", outp[0]))
     model.dense.register_forward_pre_hook(lambda mod, inp: cap.__setitem__("dense_in", inp[0]))
     logits, xy, kl = model(inputs)                                       # bert_amir.py:83-156
     loss = torch.nn.functional.cross_entropy(logits, targets) + 0.01 * xy + 0.01 * kl
@@ -369,6 +370,7 @@ def golden_bert_amir(BertAmir) -> None:
         "heads": batch.heads, "sent_ptr": batch.sent_ptr, "anchor": batch.anchor, "T": np.int64(T), "targets": targets.numpy(),
         "x": cap["x"].detach().numpy(), "dx": cap["x"].grad.numpy(),
         "aspect": cap["aspect"].detach().numpy(), "daspect": cap["aspect"].grad.numpy(),
+        "x_lstm": cap["x_lstm"].detach().numpy(), "aspect_mask": aspect_mask[:, :L],
         "adj": adj[:, :T, :T], "dist": np.asarray(dist, dtype=np.int64)[:, :T], "view_mask": cls_mask[:, :T],
         "pooled_output": cap["dense_in"].detach().numpy()[:, :768],
         "logits": logits.detach().numpy(), "xy": xy.detach().numpy(), "kl": kl.detach().numpy(), "loss": loss.detach().numpy(),

@@ -56,7 +56,7 @@ bench("pool_fwd V=1 (unfused)", lambda i: ops.pool_fwd(xs[i], graph, gates), N *
 bench("torch copy (ref)", lambda i: xs[(i + 1) % RING].copy_(xs[i]), 2 * N * D * 2)
 
 KEYS = ("V", "EPI_WARPS", "STAGES", "ROWS", "PF", "DEBUG", "SLEEP", "BOXROWS")
-sweeps = [dict(V=2), dict(V=2, STAGES=2), dict(V=1, PF=0)]
+sweeps = [dict(), dict(EPI_WARPS=12), dict(STAGES=3), dict(V=2)]
 only_plain = False
 if len(sys.argv) > 1 and sys.argv[1] == "pipe":       # load-pipeline study: epilogue work switched off
     only_plain = True
