@@ -212,8 +212,10 @@ class _GatedStackFn(torch.autograd.Function):
             # trigger's word pieces, bert_amir.py:118) instead of the trigger row of x (bert_amir5.py:615-618)
             a_raw = aspect.detach().float().contiguous()
             s0 = ops.as_rows(torch.sigmoid(a_raw) if lead else a_raw, cd)
-        else:
-            a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
+        side = _Side(_OVERLAP and cfg["gated"], x.device)
+        if aspect is None:
+            with side.region():                   # the gather feeds the gate MLPs only: it runs on their (side) stream
+                a_raw, s0 = ops.trigger_gather(xr, graph, anchor, lead)
         gate_saved = []
         if gated:
             gates = torch.empty((Lyr, B, D), dtype=torch.float32, device=x.device)
@@ -223,7 +225,6 @@ class _GatedStackFn(torch.autograd.Function):
             gates = torch.ones((Lyr, B, D), dtype=torch.float32, device=x.device)
         use_chain = gated and _chain_ok(cd, D, Lyr, pairs)
         ctx.use_chain = use_chain
-        side = _Side(_OVERLAP and gated, x.device)
         with side.region():                       # overlaps the first aggregate -> projection below
             if use_chain:
                 # every Linear+Sigmoid of every gate in ONE launch (activation tile resident in shared memory)
