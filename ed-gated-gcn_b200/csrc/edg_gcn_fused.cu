@@ -634,13 +634,24 @@ tile_plan_kernel(const int32_t* __restrict__ sent_ptr, const int32_t* __restrict
   }
 }
 
+// out[c] (+)= sum_g part[g][c]: block = 32 columns x 8 partial slices (warp w sums g = w, w + 8, ...), combined through
+// shared memory in warp order -- a fixed summation order (deterministic), ~G/8 dependent-free loads per thread
 __global__ void __launch_bounds__(256)
 colsum_part_reduce_kernel(const float* __restrict__ part, int G, int C, float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float a = 0.f;
-  for (int g = 0; g < G; ++g) a += part[(int64_t)g * C + c];       // fixed order: deterministic
-  out[c] = accumulate ? out[c] + a : a;
+  if (c < C)
+    for (int g = w; g < G; g += 8) a += part[(int64_t)g * C + c];
+  red[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && c < C) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][lane];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // Backward of the gated max-pool views of layer 1 and the diversity term (bert_amir5.py:627-638) from the column
@@ -827,7 +838,7 @@ extern "C" int edg_gcn_layer(const void* x, int64_t ldx, int32_t N, int32_t K, c
   rc = check_launch();
   if (rc) return rc;
   if (colsum) {
-    colsum_part_reduce_kernel<<<(Nout + 255) / 256, 256, 0, s>>>((const float*)ws, groups, Nout, colsum, colsum_accumulate);
+    colsum_part_reduce_kernel<<<(Nout + 31) / 32, 256, 0, s>>>((const float*)ws, groups, Nout, colsum, colsum_accumulate);
     rc = check_launch();
   }
   return rc;

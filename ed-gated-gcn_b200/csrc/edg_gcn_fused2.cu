@@ -716,7 +716,7 @@ static int launch_gcn_layer2(const void* x, int64_t ldx, int32_t N, int32_t K, c
   rc = check_launch();
   if (rc) return rc;
   if (colsum) {
-    colsum_part_reduce_kernel<<<(Nout + 255) / 256, 256, 0, s>>>((const float*)ws, groups, Nout, colsum, colsum_accumulate);
+    colsum_part_reduce_kernel<<<(Nout + 31) / 32, 256, 0, s>>>((const float*)ws, groups, Nout, colsum, colsum_accumulate);
     rc = check_launch();
   }
   return rc;

@@ -208,7 +208,7 @@ extern "C" int edg_head_du(const float* u_unit, const float* g_kl, const float* 
   int rc = check_launch();
   if (rc) return rc;
   if (dbias) {
-    colsum_part_reduce_kernel<<<(D + 255) / 256, 256, 0, s>>>((const float*)ws, grid, D, dbias, 0);
+    colsum_part_reduce_kernel<<<(D + 31) / 32, 256, 0, s>>>((const float*)ws, grid, D, dbias, 0);
     rc = check_launch();
   }
   return rc;
