@@ -44,6 +44,12 @@ SIGNATURES = {
                               _L, _P, c_int, _P, _Z, _P, _P]),
     "edg_row_meta": (c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "edg_adam_multi": (c_int, [_I, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float, _P]),
+    "edg_split_pitch": (_L, [_I]),
+    "edg_split_f16": (c_int, [_P, _L, _I, _I, _P, _L, _P, _P]),
+    "edg_linear_split_ok": (c_int, [_I, _I]),
+    "edg_linear_split": (c_int, [_P, _L, _P, _I, _I, _P, _L, _P, _I, _P, c_int, _P, _L, _P]),
+    "edg_wgrad_split_workspace": (_Z, [_I, _I, _I]),
+    "edg_wgrad_split": (c_int, [_P, _L, _P, _I, _P, _L, _P, _I, _I, _P, _L, _P, c_int, _P, _Z, _P]),
     "edg_linear": (c_int, [_P, c_int, _L, _I, _I, _P, _L, _I, _P, c_int, _P, c_int, _L, _P]),
     "edg_wgrad_workspace": (_Z, [_I, _I, _I, c_int]),
     "edg_wgrad": (c_int, [_P, _L, _I, _P, _L, _I, c_int, _I, _P, _L, _P, c_int, c_int, _P, _Z, _P]),
@@ -125,6 +131,10 @@ def _kernels_of(name: str, args) -> int:
         return 2 + (2 if args[11] else 0)
     if name == "edg_csr_from_heads":
         return 3
+    if name == "edg_wgrad_split":
+        return 4
+    if name == "edg_split_f16":
+        return 2
     if name in ("edg_csr_from_dense_count", "edg_diversity_fwd", "edg_colsum", "edg_fc_head_bwd", "edg_wgrad_batch", "edg_head_du"):
         return 2
     if name == "edg_gcn_layer":

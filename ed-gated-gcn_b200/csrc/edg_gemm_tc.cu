@@ -141,18 +141,21 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
   return d;
 }
 
-// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> fp32.
-static inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 (or fp16 x fp16) -> fp32.
+static inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major, bool f16 = false) {
   uint32_t d = 0;
   d |= 1u << 4;                         // c_format  = F32
-  d |= 1u << 7;                         // a_format  = BF16
-  d |= 1u << 10;                        // b_format  = BF16
+  d |= (f16 ? 0u : 1u) << 7;            // a_format  = BF16 (1) / F16 (0)
+  d |= (f16 ? 0u : 1u) << 10;           // b_format  = BF16 (1) / F16 (0)
   d |= (uint32_t)(a_mn_major & 1) << 15;
   d |= (uint32_t)(b_mn_major & 1) << 16;
   d |= (uint32_t)(N >> 3) << 17;
   d |= (uint32_t)(M >> 4) << 24;
   return d;
 }
+
+// 1.0 in the operand format the instruction descriptor names (bf16 0x3F80, fp16 0x3C00)
+__device__ __forceinline__ uint16_t one_of(uint32_t idesc) { return ((idesc >> 7) & 7u) ? (uint16_t)0x3F80 : (uint16_t)0x3C00; }
 
 // ---------------------------------------------------------------------------------------------
 // common tile constants
@@ -362,10 +365,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // second read of an activation tile is an L2 hit.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWsMaxStages = 8;
+constexpr int kSplitCross = 128;    // TMEM column offset of the cross-term accumulator inside one accumulator stage
 struct WsLayout {
-  uint32_t base; int w_bytes_kb; int num_kb; int stages;
+  uint32_t base; int w_bytes_kb; int num_kb; int stages; int w_boxes; int a_bytes;
   __device__ uint32_t w(int kb) const { return base + kb * w_bytes_kb; }
-  __device__ uint32_t a(int s) const { return base + num_kb * w_bytes_kb + s * kABytes; }
+  __device__ uint32_t a(int s) const { return base + w_boxes * w_bytes_kb + s * a_bytes; }
   __device__ uint32_t bias() const { return a(stages); }
   __device__ uint32_t bars() const { return bias() + kMaxBias * sizeof(float); }
   __device__ uint32_t full(int s) const { return bars() + 8 * s; }
@@ -376,17 +380,57 @@ struct WsLayout {
   __device__ uint32_t tmem_slot() const { return bars() + 8 * (2 * kWsMaxStages + 5); }
 };
 
-template <typename TC>
+// Split operands (the fp32-parity mode, see edg_split.cu): an fp32 matrix x is stored as two fp16 matrices side by
+// side, row = [ hi | lo ] with hi = fp16(x s), lo = fp16(x s - hi), s = split_scale(max |x|) a power of two.
+// hi + lo carries 22 significant bits of x s, and  a w^T = (a_hi w_hi^T + a_hi w_lo^T + a_lo w_hi^T) / (s_a s_w)
+// to ~2^-21 per product with fp32 accumulation in TMEM -- three fp16 MMAs per k step instead of one.
+__device__ __forceinline__ float split_scale(float amax) {          // amax * s in [2^13, 2^14)
+  const int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+  int se = 267 - e;
+  se = se < 1 ? 1 : (se > 254 ? 254 : se);
+  return __uint_as_float((uint32_t)se << 23);
+}
+__device__ __forceinline__ float split_inv_scale(float amax) {
+  const int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+  int se = 267 - e;
+  se = se < 1 ? 1 : (se > 254 ? 254 : se);
+  return se <= 253 ? __uint_as_float((uint32_t)(254 - se) << 23) : __uint_as_float(0x00400000u);
+}
+
+// one 32-column chunk of one accumulator row of the split kernel: scale back, bias, activation, fp32 stores;
+// only columns below `col_end` (what this CTA's N tile owns) are written, columns in [Nout, col_end) as zeros
+__device__ __forceinline__ void epilogue_chunk_scaled(const uint32_t (&r)[32], int col0, int Nout, int col_end, int act,
+                                                      float inv_a, float inv_w, const float* __restrict__ bias_s,
+                                                      float* __restrict__ crow) {
+#pragma unroll
+  for (int g = 0; g < 32; g += 4) {
+    const int col = col0 + g;
+    if (col + 4 <= col_end) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cj = col + j;
+        v[j] = (cj < Nout) ? apply_act(__uint_as_float(r[g + j]) * inv_a * inv_w + bias_s[cj < kMaxBias ? cj : 0], act) : 0.f;
+      }
+      *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+template <typename TC, bool SPLIT>
 __global__ void __launch_bounds__(kLinThreads, 1)
 linear_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  int M, int K, int Nout, int block_n, int n_tiles, int m_tiles, int stages, uint32_t idesc,
-                 const float* __restrict__ bias, int act, TC* __restrict__ C, int64_t ldc) {
+                 const float* __restrict__ bias, int act, TC* __restrict__ C, int64_t ldc,
+                 int k_lo, const float* __restrict__ amax_a, const float* __restrict__ amax_w) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   WsLayout L;
   L.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   L.num_kb = (K + kBlockK - 1) / kBlockK;
   L.w_bytes_kb = block_n * kBlockK * 2;
   L.stages = stages;
+  L.w_boxes = SPLIT ? 2 * L.num_kb : L.num_kb;          // split: hi boxes then lo boxes
+  L.a_bytes = SPLIT ? 2 * kABytes : kABytes;            // split: hi tile then lo tile
   const int num_kb = L.num_kb;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (L.bias() - smem_u32(smem_raw)));
@@ -411,15 +455,18 @@ linear_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      // the stationary weight tile: num_kb boxes [block_n rows x 64 k], one barrier
-      mbar_expect_tx(L.wfull(), (uint32_t)(num_kb * L.w_bytes_kb));
+      // the stationary weight tile: boxes [block_n rows x 64 k], one barrier
+      mbar_expect_tx(L.wfull(), (uint32_t)(L.w_boxes * L.w_bytes_kb));
       for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(L.w(kb), &map_w, L.wfull(), kb * kBlockK, n0);
+      if (SPLIT)
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(L.w(num_kb + kb), &map_w, L.wfull(), k_lo + kb * kBlockK, n0);
       int stage = 0; uint32_t phase = 0;
       for (int mt = m_first; mt < m_tiles; mt += m_step) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(L.empty(stage), phase ^ 1);
-          mbar_expect_tx(L.full(stage), kABytes);
+          mbar_expect_tx(L.full(stage), (uint32_t)L.a_bytes);
           tma_load_2d(L.a(stage), &map_a, L.full(stage), kb * kBlockK, mt * kBlockM);
+          if (SPLIT) tma_load_2d(L.a(stage) + kABytes, &map_a, L.full(stage), k_lo + kb * kBlockK, mt * kBlockM);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -442,7 +489,18 @@ linear_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t ad = make_desc_sw128(L.a(stage) + k * 32, 16, 1024);
             const uint64_t bd = make_desc_sw128(L.w(kb) + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            if (SPLIT) {
+              // The tensor core truncates when it accumulates, so the error grows with the length of the chain:
+              // the two small products get their own accumulator (kSplitCross columns further), which keeps the
+              // hi x hi chain at K/16 steps; the epilogue adds the two.
+              const uint64_t al = make_desc_sw128(L.a(stage) + kABytes + k * 32, 16, 1024);
+              const uint64_t bl = make_desc_sw128(L.w(num_kb + kb) + k * 32, 16, 1024);
+              umma_bf16(d_tmem + kSplitCross, al, bd, idesc, (kb | k) != 0);
+              umma_bf16(d_tmem + kSplitCross, ad, bl, idesc, 1);
+              umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            } else {
+              umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(L.empty(stage));
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -454,6 +512,14 @@ linear_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int n_chunks = (block_n + 31) / 32;
+    float inv_a = 1.f, inv_w = 1.f;
+    int col_end = 0;
+    if (SPLIT) {
+      inv_a = split_inv_scale(__ldg(amax_a));
+      inv_w = split_inv_scale(__ldg(amax_w));
+      col_end = (n_tile == n_tiles - 1) ? (int)ldc : n0 + block_n;
+      if (col_end > (int)ldc) col_end = (int)ldc;
+    }
     int it = 0;
     for (int mt = m_first; mt < m_tiles; mt += m_step, ++it) {
       const int as = it & 1;
@@ -465,19 +531,37 @@ linear_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       TC* crow = C + (int64_t)(row_ok ? row : 0) * ldc;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride;
       uint32_t ra[32], rb[32];
+      auto emit = [&](const uint32_t (&r)[32], int ci) {
+        if (!row_ok) return;
+        if constexpr (SPLIT) {
+          epilogue_chunk_scaled(r, n0 + ci * 32, Nout, col_end, act, inv_a, inv_w, bias_s, reinterpret_cast<float*>(crow));
+        } else {
+          if (n0 + ci * 32 < ldc) epilogue_chunk<TC>(r, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
+        }
+      };
       int ci = half;
+      if constexpr (SPLIT) {
+        for (; ci < n_chunks; ci += 2) {
+          tmem_ld_32x32_nowait(tbase + ci * 32, ra);
+          tmem_ld_32x32_nowait(tbase + kSplitCross + ci * 32, rb);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+          emit(ra, ci);
+        }
+      }
       if (ci < n_chunks) tmem_ld_32x32_nowait(tbase + ci * 32, ra);
       while (ci < n_chunks) {
         tmem_wait_ld();
         const int nxt = ci + 2;
         if (nxt < n_chunks) tmem_ld_32x32_nowait(tbase + nxt * 32, rb);
-        if (row_ok && n0 + ci * 32 < ldc) epilogue_chunk<TC>(ra, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
+        emit(ra, ci);
         ci = nxt;
         if (ci >= n_chunks) break;
         tmem_wait_ld();
         const int nx2 = ci + 2;
         if (nx2 < n_chunks) tmem_ld_32x32_nowait(tbase + nx2 * 32, ra);
-        if (row_ok && n0 + ci * 32 < ldc) epilogue_chunk<TC>(rb, n0 + ci * 32, Nout, ldc, act, bias_s, crow);
+        emit(rb, ci);
         ci = nx2;
       }
       tc_fence_before();
@@ -522,12 +606,12 @@ __device__ __forceinline__ void store_partial_chunk(float* __restrict__ prow, in
 // Bias gradients ride along for free: `ones_a` >= 0 plants a column of ones at A column `ones_a` (= K1), so
 // output row K1 is the column sum of B; `ones_b` >= 0 does the same on the B side (output column K2 = column
 // sums of A).  The ones are written into the landed smem tile (swizzled address) right before the MMAs.
-__device__ __forceinline__ void plant_ones(uint32_t box_base, int col_in_box, int rows_valid, int lane) {
+__device__ __forceinline__ void plant_ones(uint32_t box_base, int col_in_box, int rows_valid, int lane, uint16_t one = 0x3F80) {
   // box = [64 rows x 64 bf16] with 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
   const int chunk = col_in_box >> 3, within = (col_in_box & 7) * 2;
   for (int r = lane; r < 64; r += 32) {
     const uint32_t addr = box_base + r * 128 + (((chunk ^ (r & 7)) << 4) | within);
-    const uint16_t v = (r < rows_valid) ? 0x3F80 : 0;      // bf16 1.0 for real rows only
+    const uint16_t v = (r < rows_valid) ? one : (uint16_t)0;   // 1.0 (bf16 0x3F80 / fp16 0x3C00) for real rows only
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
   }
 }
@@ -583,8 +667,8 @@ __device__ __forceinline__ void wgrad_tc_body(const CUtensorMap& map_a, const CU
       mbar_wait(L.full(stage), phase);
       if (plant_a || plant_b) {                      // whole warp: ones column into the landed tile
         const int rows_valid = r_end - (r_beg + kb * kBlockK);
-        if (plant_a) plant_ones(L.a(stage) + ((ones_a - m0) >> 6) * kBoxBytes, (ones_a - m0) & 63, rows_valid, lane);
-        if (plant_b) plant_ones(L.b(stage) + ((ones_b - n0) >> 6) * kBoxBytes, (ones_b - n0) & 63, rows_valid, lane);
+        if (plant_a) plant_ones(L.a(stage) + ((ones_a - m0) >> 6) * kBoxBytes, (ones_a - m0) & 63, rows_valid, lane, one_of(idesc));
+        if (plant_b) plant_ones(L.b(stage) + ((ones_b - n0) >> 6) * kBoxBytes, (ones_b - n0) & 63, rows_valid, lane, one_of(idesc));
         fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
       }
@@ -660,12 +744,12 @@ constexpr int kTallBBytes = 5 * kTallBBox;                   // 20 KB (block_n <
 constexpr int kTallStageBytes = kTallABytes + kTallBBytes;   // 68 KB
 constexpr size_t kTallSmem = 1024 + (size_t)kTallStages * kTallStageBytes + 256;
 
-__device__ __forceinline__ void plant_ones_sw64(uint32_t box_base, int col_in_box, int rows_valid, int lane) {
+__device__ __forceinline__ void plant_ones_sw64(uint32_t box_base, int col_in_box, int rows_valid, int lane, uint16_t one = 0x3F80) {
   // box = [64 rows x 32 bf16] with 64-byte rows, 16-byte chunks XOR-swizzled by ((row >> 1) & 3)
   const int chunk = col_in_box >> 3, within = (col_in_box & 7) * 2;
   for (int r = lane; r < 64; r += 32) {
     const uint32_t addr = box_base + r * 64 + (((chunk ^ ((r >> 1) & 3)) << 4) | within);
-    const uint16_t v = (r < rows_valid) ? 0x3F80 : 0;
+    const uint16_t v = (r < rows_valid) ? one : (uint16_t)0;
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
   }
 }
@@ -725,8 +809,8 @@ wgrad_tall_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_wait(full(stage), phase);
       if (plant_a || plant_b) {
         const int rows_valid = r_end - (r_beg + kb * kBlockK);
-        if (plant_a) plant_ones(sa(stage) + (ones_a >> 6) * kBoxBytes, ones_a & 63, rows_valid, lane);
-        if (plant_b) plant_ones_sw64(sb(stage) + ((ones_b - n0) >> 5) * kTallBBox, (ones_b - n0) & 31, rows_valid, lane);
+        if (plant_a) plant_ones(sa(stage) + (ones_a >> 6) * kBoxBytes, ones_a & 63, rows_valid, lane, one_of(idesc));
+        if (plant_b) plant_ones_sw64(sb(stage) + ((ones_b - n0) >> 5) * kTallBBox, (ones_b - n0) & 31, rows_valid, lane, one_of(idesc));
         fence_proxy_async();
         __syncwarp();
       }
@@ -831,13 +915,59 @@ template <typename TC>
 static int launch_linear_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, int M, int K, int Nout, int block_n,
                               int n_tiles, int stages, size_t smem, const float* bias, int act, void* C, int64_t ldc,
                               cudaStream_t s) {
-  if (int rc_ = ensure_dyn_smem((const void*)linear_ws_kernel<TC>, 227 * 1024)) return rc_;
+  if (int rc_ = ensure_dyn_smem((const void*)linear_ws_kernel<TC, false>, 227 * 1024)) return rc_;
   const int m_tiles = (M + kBlockM - 1) / kBlockM;
   int groups = kNumSMs / n_tiles;                 // CTAs per N tile
   if (groups > m_tiles) groups = m_tiles;
   const uint32_t idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
-  linear_ws_kernel<TC><<<groups * n_tiles, kLinThreads, smem, s>>>(ma, mw, M, K, Nout, block_n, n_tiles, m_tiles, stages,
-                                                                    idesc, bias, act, (TC*)C, ldc);
+  linear_ws_kernel<TC, false><<<groups * n_tiles, kLinThreads, smem, s>>>(ma, mw, M, K, Nout, block_n, n_tiles, m_tiles,
+                                                                           stages, idesc, bias, act, (TC*)C, ldc, 0, nullptr,
+                                                                           nullptr);
+  return check_launch();
+}
+
+// ---- split operands (fp32-parity mode): rows = [hi | lo] fp16, lo at column k_lo = ld / 2 ----
+// N tile: the widest multiple of 16 whose hi+lo weight boxes leave room for two (hi+lo) activation stages
+struct SplitPlan { bool ok; int block_n, n_tiles, stages; size_t smem; };
+static SplitPlan plan_linear_split(int K, int Nout) {
+  SplitPlan p{};
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const size_t fixed = 1024 + kMaxBias * sizeof(float) + 512;
+  const size_t budget = 227 * 1024;
+  int bn = 256;
+  while (bn >= 16 && fixed + (size_t)2 * num_kb * bn * kBlockK * 2 + 2 * (size_t)(2 * kABytes) > budget) bn -= 16;
+  if (bn > kSplitCross) bn = kSplitCross;             // main and cross-term accumulators share one 256-column stage
+  if (bn < 16 || Nout > kMaxBias) return p;
+  p.n_tiles = (Nout + bn - 1) / bn;
+  p.block_n = (((Nout + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
+  const size_t w_bytes = (size_t)2 * num_kb * p.block_n * kBlockK * 2;
+  p.stages = (int)((budget - fixed - w_bytes) / (2 * kABytes));
+  if (p.stages > kWsMaxStages) p.stages = kWsMaxStages;
+  p.smem = fixed + w_bytes + (size_t)p.stages * 2 * kABytes;
+  p.ok = p.stages >= 2 && p.n_tiles <= kNumSMs;
+  return p;
+}
+bool linear_split_ok(int K, int Nout) { return plan_linear_split(K, Nout).ok; }
+
+int launch_linear_split(const void* A2, int64_t lda, const float* amax_a, int M, int K, const void* W2, int64_t ldw,
+                        const float* amax_w, int Nout, const float* bias, int act, float* C, int64_t ldc, cudaStream_t s) {
+  const SplitPlan p = plan_linear_split(K, Nout);
+  if (!p.ok) return EDG_ERR_UNSUPPORTED;
+  const int k_lo = (int)(lda / 2);
+  if ((lda & 127) || ldw != lda || k_lo < K) return EDG_ERR_ARG;       // hi and lo halves on 64-element boundaries
+  CUtensorMap ma, mw;
+  int rc = make_map_bf16(&ma, A2, M, lda, lda, kBlockK, kBlockM);     // 16-bit elements; the type only names the OOB fill
+  if (rc) return rc;
+  rc = make_map_bf16(&mw, W2, Nout, ldw, ldw, kBlockK, p.block_n);
+  if (rc) return rc;
+  if (int rc_ = ensure_dyn_smem((const void*)linear_ws_kernel<float, true>, 227 * 1024)) return rc_;
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  int groups = kNumSMs / p.n_tiles;
+  if (groups > m_tiles) groups = m_tiles;
+  const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0, /*f16=*/true);
+  linear_ws_kernel<float, true><<<groups * p.n_tiles, kLinThreads, p.smem, s>>>(ma, mw, M, K, Nout, p.block_n, p.n_tiles,
+                                                                                 m_tiles, p.stages, idesc, bias, act, C, ldc,
+                                                                                 k_lo, amax_a, amax_w);
   return check_launch();
 }
 
@@ -937,10 +1067,12 @@ size_t wgrad_tc_workspace(int R, int K1, int K2) {
   return best;
 }
 
-int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, float* dW,
-                    int64_t lddw, float* dbias, int bias_of, int accumulate, float* ws, cudaStream_t s) {
+// the GEMM launch alone: partial sums [slabs][K1e][K2e] into `partial`; `plant` = write the ones row / column
+static int run_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, int bias_of,
+                        bool plant, bool f16, float* partial, int* slabs, cudaStream_t s) {
   if (int rc_ = ensure_dyn_smem((const void*)wgrad_tc_kernel, kSmemBytes)) return rc_;
   const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
+  const int ones_a = (plant && bias_of == 2) ? K1 : -1, ones_b = (plant && bias_of == 1) ? K2 : -1;
   const TallPlan t = plan_wgrad_tall(R, K1e, K2e);
   if (t.ok && tall_enabled()) {
     if (int rc_ = ensure_dyn_smem((const void*)wgrad_tall_kernel, kTallSmem)) return rc_;
@@ -949,11 +1081,10 @@ int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t l
     if (rc) return rc;
     rc = make_map_bf16(&mb, B, R, K2, ldb, 32, kBlockK, /*swizzle64=*/true);
     if (rc) return rc;
-    const uint32_t idesc = make_idesc_bf16(kBlockM, t.block_n, 1, 1);
+    const uint32_t idesc = make_idesc_bf16(kBlockM, t.block_n, 1, 1, f16);
     wgrad_tall_kernel<<<dim3(t.n_tiles, t.splits), kThreads, kTallSmem, s>>>(ma, mb, R, K1e, K2e, t.m_tiles, t.block_n,
-                                                                            t.rows_per, idesc, bias_of == 2 ? K1 : -1,
-                                                                            bias_of == 1 ? K2 : -1, ws);
-    launch_split_reduce_bias(ws, t.splits, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, accumulate, s);
+                                                                            t.rows_per, idesc, ones_a, ones_b, partial);
+    *slabs = t.splits;
     return check_launch();
   }
   WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
@@ -962,11 +1093,48 @@ int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t l
   if (rc) return rc;
   rc = make_map_bf16(&mb, B, R, K2, ldb, 64, kBlockK);
   if (rc) return rc;
-  const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 1, 1);
+  const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 1, 1, f16);
   dim3 grid(p.m_tiles, p.n_tiles, p.splits);
-  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, R, K1e, K2e, p.block_n, p.rows_per, idesc,
-                                                     bias_of == 2 ? K1 : -1, bias_of == 1 ? K2 : -1, ws);
-  launch_split_reduce_bias(ws, p.splits, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, accumulate, s);
+  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma, mb, R, K1e, K2e, p.block_n, p.rows_per, idesc, ones_a, ones_b, partial);
+  *slabs = p.splits;
+  return check_launch();
+}
+
+int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, float* dW,
+                    int64_t lddw, float* dbias, int bias_of, int accumulate, float* ws, cudaStream_t s) {
+  int slabs = 0;
+  if (int rc = run_wgrad_tc(A, lda, K1, B, ldb, K2, R, bias_of, true, false, ws, &slabs, s)) return rc;
+  const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
+  launch_split_reduce_bias(ws, slabs, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, accumulate, s);
+  return check_launch();
+}
+
+// defined in edg_split.cu
+void launch_split_reduce_bias_scaled(const float* partial, int slabs, int K1, int K2, int K1e, int K2e, float* dW,
+                                     int64_t lddw, float* dbias, int bias_of, const float* amax_a, const float* amax_b,
+                                     cudaStream_t s);
+
+// split operands: a^T b = (a_hi^T b_hi + a_hi^T b_lo + a_lo^T b_hi) / (s_a s_b); three GEMM launches into
+// consecutive partial-sum slabs, one scaled reduction.  The ones row / column rides on the hi and lo parts of the
+// operand it sums (launches 0 and 1 for b, 0 and 2 for a), never twice on the same part.
+size_t wgrad_split_workspace(int R, int K1, int K2) { return 3 * wgrad_tc_workspace(R, K1, K2); }
+
+int launch_wgrad_split(const void* A2, int64_t lda, const float* amax_a, int K1, const void* B2, int64_t ldb,
+                       const float* amax_b, int K2, int R, float* dW, int64_t lddw, float* dbias, int bias_of, float* ws,
+                       cudaStream_t s) {
+  const int ka = (int)(lda / 2), kb = (int)(ldb / 2);
+  if ((lda & 127) || (ldb & 127) || ka < K1 || kb < K2) return EDG_ERR_ARG;
+  const uint16_t* A = (const uint16_t*)A2;
+  const uint16_t* B = (const uint16_t*)B2;
+  const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
+  const size_t slab = (size_t)K1e * K2e;
+  int n0 = 0, n1 = 0, n2 = 0;
+  // bias_of 2 = column sums of b (ones row on the a side): wanted for b_hi (launch 0) and b_lo (launch 1)
+  // bias_of 1 = column sums of a (ones column on the b side): wanted for a_hi (launch 0) and a_lo (launch 2)
+  if (int rc = run_wgrad_tc(A, lda, K1, B, ldb, K2, R, bias_of, true, true, ws, &n0, s)) return rc;
+  if (int rc = run_wgrad_tc(A, lda, K1, B + kb, ldb, K2, R, bias_of, bias_of == 2, true, ws + (size_t)n0 * slab, &n1, s)) return rc;
+  if (int rc = run_wgrad_tc(A + ka, lda, K1, B, ldb, K2, R, bias_of, bias_of == 1, true, ws + (size_t)(n0 + n1) * slab, &n2, s)) return rc;
+  launch_split_reduce_bias_scaled(ws, n0 + n1 + n2, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, amax_a, amax_b, s);
   return check_launch();
 }
 

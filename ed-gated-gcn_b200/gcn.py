@@ -59,9 +59,20 @@ class _GCNLayerFn(torch.autograd.Function):
         m = ops.aggregate(xr, graph, mode=0)                               # A_hat x          [N,Din]
         wt = ops.cast_weight(weight, cdtype, transpose=True)               # [Dout,Din], K-major
         b32 = bias.detach().float().contiguous() if bias is not None else None
-        y = ops.linear(m, wt, b32, act=L.ACT_RELU if relu else L.ACT_NONE)  # [N,Dout]
+        act = L.ACT_RELU if relu else L.ACT_NONE
+        # fp32 mode: the projection runs on the tensor cores from split operands (ops.SplitRows); the split form
+        # of A_hat x is what the weight gradient reads, so it is saved instead of the fp32 rows
+        split = cdtype == torch.float32 and ops.f32_tc(m.shape[0], m.shape[1], wt.shape[0]) \
+            and ops.f32_tc(m.shape[0], wt.shape[0], m.shape[1])
+        if split:
+            m2 = ops.split_rows(m)
+            y = ops.linear_split(m2, ops.split_rows(wt), b32, act)
+            ctx.m_amax, ctx.m_shape = m2.amax, m2.shape
+            m = m2.data
+        else:
+            y = ops.linear(m, wt, b32, act=act)                            # [N,Dout]
         ctx.set_materialize_grads(False)
-        ctx.graph, ctx.cdtype, ctx.relu, ctx.has_bias = graph, cdtype, relu, bias is not None
+        ctx.graph, ctx.cdtype, ctx.relu, ctx.has_bias, ctx.split = graph, cdtype, relu, bias is not None, split
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(m, weight, y if relu else None)
         return y
@@ -76,11 +87,17 @@ class _GCNLayerFn(torch.autograd.Function):
             dy = dy * (y > 0)
         dyr = ops.as_rows(dy, cdtype)
         dW = db = dx = None
-        if ctx.needs_input_grad[1] or ctx.has_bias:
-            dW, db = ops.wgrad(m, dyr, bias_of=2 if ctx.has_bias else 0)   # [Din,Dout], [Dout]
+        want_w = ctx.needs_input_grad[1] or ctx.has_bias
+        dy2 = ops.split_rows(dyr) if ctx.split else None                   # shared by dW and dx
+        if want_w:
+            if ctx.split:
+                m2 = ops.SplitRows(m, ctx.m_amax, *ctx.m_shape)
+                dW, db = ops.wgrad_split(m2, dy2, bias_of=2 if ctx.has_bias else 0)
+            else:
+                dW, db = ops.wgrad(m, dyr, bias_of=2 if ctx.has_bias else 0)   # [Din,Dout], [Dout]
         if ctx.needs_input_grad[0]:
             w = ops.cast_weight(weight, cdtype, transpose=False)           # [Din,Dout] = B operand of dy W^T
-            dm = ops.linear(dyr, w, None)                                  # [N,Din]
+            dm = ops.linear_split(dy2, ops.split_rows(w), None) if ctx.split else ops.linear(dyr, w, None)   # [N,Din]
             dx = ops.aggregate(dm, graph, mode=1, out_dtype=ctx.x_dtype if ctx.x_dtype in L.DTYPES else cdtype)
             if dx.dtype != ctx.x_dtype:
                 dx = dx.to(ctx.x_dtype)

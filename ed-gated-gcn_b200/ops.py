@@ -65,12 +65,81 @@ def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype
     return out
 
 
+class SplitRows:
+    """An fp32 row matrix in the split form the fp32-parity tensor-core GEMMs read (``edg_split_f16``):
+    ``data`` fp16 ``[rows, 2 * round_up(cols, 64)]`` = ``[hi | lo]`` of ``x * 2^k``, ``amax`` the device scalar the
+    power-of-two scale is derived from."""
+    __slots__ = ("data", "amax", "rows", "cols")
+
+    def __init__(self, data, amax, rows, cols):
+        self.data, self.amax, self.rows, self.cols = data, amax, rows, cols
+
+    @property
+    def shape(self):
+        return (self.rows, self.cols)
+
+
+F32_TC_MIN_ROWS = 1024      # below this the FFMA kernels win (five launches against one)
+
+
+def f32_tc(rows: int, K: int, Nout: int) -> bool:
+    """Whether an fp32 ``[rows, K] x [Nout, K]^T`` product runs on the tensor cores in split form
+    (``EDG_F32_TC=0`` keeps the FFMA kernels: bring-up switch)."""
+    import os
+    if os.environ.get("EDG_F32_TC", "1") == "0" or rows < F32_TC_MIN_ROWS:
+        return False
+    return bool(L.load().edg_linear_split_ok(int(K), int(Nout)))
+
+
+def split_rows(x: torch.Tensor) -> SplitRows:
+    """``edg_split_f16``: fp32 ``[rows, cols]`` -> :class:`SplitRows` (two launches: max |x|, then hi / lo)."""
+    x = as_rows(x, torch.float32)
+    rows, cols = x.shape
+    pitch = int(L.load().edg_split_pitch(cols))
+    data = torch.empty((max(rows, 1), pitch), dtype=torch.float16, device=x.device)
+    amax = torch.empty((1,), dtype=torch.float32, device=x.device)
+    L.call("edg_split_f16", L.ptr(x), ld(x), rows, cols, L.ptr(data), pitch, L.ptr(amax), L.stream())
+    return SplitRows(data, amax, rows, cols)
+
+
+def linear_split(a: SplitRows, w: SplitRows, bias: Optional[torch.Tensor], act: int = L.ACT_NONE,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(a @ w.T + bias)`` in fp32 from split operands (``edg_linear_split``); ``w`` is ``[Nout, K]``."""
+    M, K = a.shape
+    Nout = w.rows
+    assert w.cols == K
+    if out is None:
+        out = alloc_rows(M, Nout, torch.float32, a.data.device)
+    L.call("edg_linear_split", L.ptr(a.data), a.data.stride(0), L.ptr(a.amax), M, K, L.ptr(w.data), w.data.stride(0),
+           L.ptr(w.amax), Nout, L.ptr(bias), act, L.ptr(out), ld(out), L.stream())
+    return out
+
+
+def wgrad_split(a: SplitRows, b: SplitRows, bias_of: int = 0):
+    """``a.T @ b`` in fp32 (+ column sums of a (1) or b (2)) from split operands (``edg_wgrad_split``)."""
+    R, K1 = a.shape
+    K2 = b.cols
+    assert b.rows == R
+    dev = a.data.device
+    dW = torch.empty((K1, K2), dtype=torch.float32, device=dev)
+    db = torch.empty((K1 if bias_of == 1 else K2,), dtype=torch.float32, device=dev) if bias_of else None
+    nbytes = L.load().edg_wgrad_split_workspace(R, K1, K2)
+    ws = torch.empty((nbytes + 255) // 4, dtype=torch.float32, device=dev)
+    L.call("edg_wgrad_split", L.ptr(a.data), a.data.stride(0), L.ptr(a.amax), K1, L.ptr(b.data), b.data.stride(0),
+           L.ptr(b.amax), K2, R, L.ptr(dW), K2, L.ptr(db), bias_of, L.ptr(ws), ws.numel() * 4, L.stream())
+    return dW, db
+
+
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = L.ACT_NONE,
            out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``act(a @ w.T + bias)`` with ``w`` given as ``[Nout, K]`` (K contiguous)."""
+    """``act(a @ w.T + bias)`` with ``w`` given as ``[Nout, K]`` (K contiguous).  fp32 operands with enough rows go
+    through the split tensor-core path (:func:`f32_tc`)."""
     M, K = a.shape
     Nout = w.shape[0]
     assert w.shape[1] == K and a.dtype == w.dtype
+    if (a.dtype == torch.float32 and (out_dtype or a.dtype) == torch.float32 and (out is None or out.dtype == torch.float32)
+            and f32_tc(M, K, Nout)):
+        return linear_split(split_rows(a), split_rows(w), bias, act, out)
     if out is None:
         out = alloc_rows(M, Nout, out_dtype or a.dtype, a.device)
     L.call("edg_linear", L.ptr(a), L.dt(a), ld(a), M, K, L.ptr(w), ld(w), Nout, L.ptr(bias), act,
@@ -145,6 +214,8 @@ def wgrad(a: torch.Tensor, b: torch.Tensor, bias_of: int = 0):
     R, K1 = a.shape
     K2 = b.shape[1]
     assert b.shape[0] == R and a.dtype == b.dtype
+    if a.dtype == torch.float32 and f32_tc(R, K1, K2) and f32_tc(R, K2, K1):
+        return wgrad_split(split_rows(a), split_rows(b), bias_of)
     dW = torch.empty((K1, K2), dtype=torch.float32, device=a.device)
     db = torch.empty((K1 if bias_of == 1 else K2,), dtype=torch.float32, device=a.device) if bias_of else None
     nbytes = L.load().edg_wgrad_workspace(R, K1, K2, L.dt(a))

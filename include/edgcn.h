@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EDG_ABI_VERSION 2
+#define EDG_ABI_VERSION 3
 
 typedef enum {
   EDG_OK = 0,
@@ -433,6 +433,42 @@ int edg_dropout_rows(const void* x, int dtype, int64_t ldx, void* y, int64_t ldy
 int edg_adam_multi(int32_t n, void* const* param, const void* const* grad, void* const* exp_avg,
                    void* const* exp_avg_sq, void* const* step, const int64_t* numel, float lr, float beta1,
                    float beta2, float eps, float weight_decay, float grad_scale, edg_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* fp32-parity projection on the tensor cores (models/gcn.py:34, fp32 mode)   */
+/* ------------------------------------------------------------------------- */
+
+/* The tensor cores take no fp32 inputs, so the fp32 mode carries an fp32 matrix x as two fp16 matrices stored side by
+ * side in one row, [ hi | lo ] with hi = fp16(x s), lo = fp16(x s - hi), s a power of two chosen from max|x| (device
+ * scalar `amax`) so that max|x s| lies in [2^13, 2^14); each half is zero-padded to a multiple of 64 columns.  hi + lo
+ * carries 22 significant bits of x; a product of two split matrices is three fp16 tensor-core products
+ * (hi hi + hi lo + lo hi) with fp32 accumulation, scaled back by 1/(s_a s_b): error ~2^-21 per product, i.e. the
+ * 1e-5 parity bound of the fp32 mode holds (tests/test_gpu_b_kernels.py).  Nothing here synchronises with the host. */
+
+/* elements (fp16) per row of the split form of a matrix with `cols` columns: 2 * round_up(cols, 64) */
+int64_t edg_split_pitch(int32_t cols);
+
+/* x fp32 [rows, cols] (pitch ldx, multiple of 4) -> out fp16 [rows, ldo] with ldo = edg_split_pitch(cols); amax: device
+ * float[1], written with max|x| (the scale the consumers re-derive). */
+int edg_split_f16(const float* x, int64_t ldx, int32_t rows, int32_t cols, void* out, int64_t ldo, float* amax,
+                  edg_stream stream);
+
+/* 1 when edg_linear_split covers the shape (the hi+lo weight slice must fit in shared memory next to two stages) */
+int edg_linear_split_ok(int32_t K, int32_t Nout);
+
+/* C fp32 [M, Nout] = act(A W^T + bias) from the split forms A2 [M, K], W2 [Nout, K] (same pitch lda == ldw ==
+ * edg_split_pitch(K)) and their amax scalars.  Replaces edg_linear for fp32 operands (same bias / act / padding rules:
+ * columns [Nout, ldc) of C are written as zeros). */
+int edg_linear_split(const void* A2, int64_t lda, const float* amax_a, int32_t M, int32_t K, const void* W2, int64_t ldw,
+                     const float* amax_w, int32_t Nout, const float* bias, int act, float* C, int64_t ldc,
+                     edg_stream stream);
+
+/* dW fp32 [K1, K2] = A^T B (+ dbias as in edg_wgrad: bias_of 1 = column sums of A, 2 = of B) from the split forms
+ * A2 [R, K1], B2 [R, K2].  ws: edg_wgrad_split_workspace(R, K1, K2) bytes. */
+size_t edg_wgrad_split_workspace(int32_t R, int32_t K1, int32_t K2);
+int edg_wgrad_split(const void* A2, int64_t lda, const float* amax_a, int32_t K1, const void* B2, int64_t ldb,
+                    const float* amax_b, int32_t K2, int32_t R, float* dW, int64_t lddw, float* dbias, int bias_of,
+                    void* ws, size_t ws_bytes, edg_stream stream);
 
 #ifdef __cplusplus
 }

@@ -361,3 +361,95 @@ def test_fused_adam_matches_torch_adam():
     assert o_mine.step_count.tolist() == [5.0, 4.0] + [5.0] * (len(shapes) - 2)
     with pytest.raises(E.EdgError):
         E.FusedAdam([torch.nn.Parameter(torch.zeros(3))])      # CPU parameter: no fallback
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32-parity GEMMs on the tensor cores: split operands (csrc/edg_split.cu, include/edgcn.h)
+# ---------------------------------------------------------------------------------------------
+def _wide_rows(M, K, seed, scale=1.0):
+    """fp32 rows whose magnitudes span several orders (per-row factors e^N(0,2)): what a per-tensor scale must survive"""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(M, K, generator=g) * torch.exp(2 * torch.randn(M, 1, generator=g)) * scale
+
+
+@pytest.mark.parametrize("shape", [(1, 8), (1000, 300), (777, 64), (300, 65), (0, 300)])
+@pytest.mark.parametrize("scale", [1.0, 1e-20, 3e18])
+def test_split_rows_reconstruct_the_fp32_matrix(shape, scale):
+    from ed_gated_gcn_b200 import ops
+    M, K = shape
+    x = _wide_rows(M, K, seed=M + K, scale=scale)
+    s = ops.split_rows(x.to(DEV))
+    kp = s.data.shape[1] // 2
+    assert kp % 64 == 0 and kp >= K and s.shape == (M, K)
+    if M == 0:
+        assert float(s.amax) == 0.0
+        return
+    amax = float(s.amax)
+    assert amax == float(x.abs().max())
+    e = int(np.floor(np.log2(amax))) + 1                      # amax in [2^(e-1), 2^e)
+    sc = 2.0 ** (14 - e)
+    d = s.data[:M].double().cpu()
+    hi, lo = d[:, :kp], d[:, kp:]
+    assert (hi[:, K:] == 0).all() and (lo[:, K:] == 0).all()  # the padding the TMA boxes read
+    assert hi.abs().max() < 2 ** 14
+    back = (hi[:, :K] + lo[:, :K]) / sc
+    err = (back - x.double()).abs()
+    # 22 significant bits, absolute floor 2^-25 in scaled units
+    assert bool((err <= torch.maximum(x.double().abs() * 2.0 ** -21, torch.tensor(2.0 ** -24 / sc, dtype=torch.float64))).all())
+
+
+@pytest.mark.parametrize("shape", [(4096, 300, 300), (1025, 64, 48), (1500, 130, 520), (5000, 300, 20), (2047, 768, 768),
+                                   (112_640, 300, 300)])
+@pytest.mark.parametrize("act", [0, 2])
+def test_linear_split_matches_fp64(shape, act):
+    from ed_gated_gcn_b200 import ops
+    M, K, Nout = shape
+    a = _wide_rows(M, K, seed=M)
+    g = torch.Generator().manual_seed(K)
+    w = torch.randn(Nout, K, generator=g) / K ** 0.5
+    bias = torch.randn(Nout, generator=g)
+    assert ops.f32_tc(M, K, Nout)
+    ad = a.to(DEV)
+    got = ops.linear_split(ops.split_rows(ad), ops.split_rows(w.to(DEV)), bias.to(DEV), act=act)
+    want = ad.double() @ w.to(DEV).double().t() + bias.to(DEV).double()
+    if act == 2:
+        want = want.clamp_min(0)
+    assert rel(got, want) < 3e-6, shape          # fp32 accumulation in TMEM truncates: ~1e-6 at K = 300
+    # row by row: a row 1e4 times smaller than the largest one still has to be right on its own scale
+    row_err = (got.double() - want).abs().amax(1) / want.abs().amax(1).clamp_min(1e-30)
+    assert float(row_err.max()) < 1e-4
+    base = got.as_strided((M, got.stride(0)), (got.stride(0), 1))
+    assert (base[:, Nout:] == 0).all()
+    # ops.linear takes the same route for fp32 operands of this size
+    assert torch.equal(ops.linear(ad, w.to(DEV), bias.to(DEV), act=act), got)
+
+
+@pytest.mark.parametrize("shape", [(4096, 256, 256), (3000, 768, 768), (20000, 300, 300), (1100, 300, 40), (9600, 100, 24),
+                                   (204_800, 300, 300)])
+def test_wgrad_split_matches_fp64(shape):
+    from ed_gated_gcn_b200 import ops
+    R, K1, K2 = shape
+    a = _wide_rows(R, K1, seed=R).to(DEV)
+    b = _wide_rows(R, K2, seed=R + 1, scale=1e-6).to(DEV)
+    a2, b2 = ops.split_rows(a), ops.split_rows(b)
+    ad, bd = a.double(), b.double()
+    want = ad.t() @ bd
+    for bias_of in (0, 1, 2):
+        dW, db = ops.wgrad_split(a2, b2, bias_of=bias_of)
+        assert rel(dW, want) < 5e-6, (shape, bias_of)
+        if bias_of == 1:
+            assert rel(db, ad.sum(0)) < 2e-6
+        if bias_of == 2:
+            assert rel(db, bd.sum(0)) < 2e-6
+
+
+def test_fp32_ffma_kernels_still_cover_the_large_shapes(monkeypatch):
+    """EDG_F32_TC=0 (and every shape the split kernels do not take) keeps the FFMA kernels"""
+    from ed_gated_gcn_b200 import ops
+    monkeypatch.setenv("EDG_F32_TC", "0")
+    assert not ops.f32_tc(4096, 300, 300)
+    g = torch.Generator().manual_seed(5)
+    a, w = torch.randn(4096, 300, generator=g).to(DEV), (torch.randn(300, 300, generator=g) / 17).to(DEV)
+    assert rel(ops.linear(a, w, None), a.double() @ w.double().t()) < 2e-6
+    dW, db = ops.wgrad(a, a, bias_of=2)
+    assert rel(dW, a.double().t() @ a.double()) < 2e-6 and rel(db, a.double().sum(0)) < 2e-6
