@@ -1009,7 +1009,9 @@ int launch_linear_tc(const void* A, int64_t lda, int M, int K, const void* W, in
 }
 
 struct WgradPlan { int block_n, n_tiles, m_tiles, splits, rows_per; };
-static WgradPlan plan_wgrad_tc(int R, int K1, int K2) {
+// `max_rows` > 0 caps the rows one CTA accumulates (the fp32-parity mode keeps the accumulation chains short: the
+// tensor core truncates on every accumulate, so the error grows with the chain), in whole waves of the usual split
+static WgradPlan plan_wgrad_tc(int R, int K1, int K2, int max_rows = 0) {
   WgradPlan p;
   p.block_n = pick_block_n(K2, 64, &p.n_tiles);
   p.m_tiles = (K1 + kBlockM - 1) / kBlockM;
@@ -1019,6 +1021,10 @@ static WgradPlan plan_wgrad_tc(int R, int K1, int K2) {
   p.splits = want < maxs ? want : maxs;
   if (p.splits < 1) p.splits = 1;
   p.rows_per = (((R + p.splits - 1) / p.splits) + kBlockK - 1) / kBlockK * kBlockK;
+  if (max_rows > 0 && p.rows_per > max_rows) {
+    const int waves = (p.rows_per + max_rows - 1) / max_rows;
+    p.rows_per = (((R + p.splits * waves - 1) / (p.splits * waves)) + kBlockK - 1) / kBlockK * kBlockK;
+  }
   p.splits = (R + p.rows_per - 1) / p.rows_per;
   if (p.splits < 1) p.splits = 1;
   return p;
@@ -1028,7 +1034,7 @@ void launch_split_reduce_bias(const float* partial, int splits, int K1, int K2, 
                               float* dbias, int bias_of, int accumulate, cudaStream_t s);
 
 struct TallPlan { bool ok; int m_tiles, block_n, n_tiles, splits, rows_per; };
-static TallPlan plan_wgrad_tall(int R, int K1e, int K2e) {
+static TallPlan plan_wgrad_tall(int R, int K1e, int K2e, int max_rows = 0) {
   TallPlan p;
   p.m_tiles = (K1e + kBlockM - 1) / kBlockM;
   p.ok = p.m_tiles <= kTallMaxM && R >= 64 * kNumSMs;          // big activations only; small ones keep wgrad_tc
@@ -1039,6 +1045,10 @@ static TallPlan plan_wgrad_tall(int R, int K1e, int K2e) {
   int want = kNumSMs / p.n_tiles;
   if (want < 1) want = 1;
   p.rows_per = (((R + want - 1) / want) + kBlockK - 1) / kBlockK * kBlockK;
+  if (max_rows > 0 && p.rows_per > max_rows) {
+    const int waves = (p.rows_per + max_rows - 1) / max_rows;
+    p.rows_per = (((R + want * waves - 1) / (want * waves)) + kBlockK - 1) / kBlockK * kBlockK;
+  }
   p.splits = (R + p.rows_per - 1) / p.rows_per;
   return p;
 }
@@ -1048,11 +1058,11 @@ static bool tall_enabled() {
   return v == 1;
 }
 
-size_t wgrad_tc_workspace(int R, int K1, int K2) {
+size_t wgrad_tc_workspace(int R, int K1, int K2, int max_rows) {
   size_t best = 0;
   for (int v = 0; v < 3; ++v) {
     const int K1e = K1 + (v == 2), K2e = K2 + (v == 1);
-    TallPlan t = plan_wgrad_tall(R, K1e, K2e);
+    TallPlan t = plan_wgrad_tall(R, K1e, K2e, max_rows);
     if (t.ok) {
       const size_t b = (size_t)t.splits * K1e * K2e * sizeof(float);
       if (b > best) best = b;
@@ -1060,20 +1070,21 @@ size_t wgrad_tc_workspace(int R, int K1, int K2) {
   }                                      // the plan depends on where the ones row / column sits
   for (int v = 0; v < 3; ++v) {
     const int K1e = K1 + (v == 2), K2e = K2 + (v == 1);
-    WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
+    WgradPlan p = plan_wgrad_tc(R, K1e, K2e, max_rows);
     const size_t b = (size_t)p.splits * K1e * K2e * sizeof(float);
     if (b > best) best = b;
   }
   return best;
 }
+size_t wgrad_tc_workspace(int R, int K1, int K2) { return wgrad_tc_workspace(R, K1, K2, 0); }
 
 // the GEMM launch alone: partial sums [slabs][K1e][K2e] into `partial`; `plant` = write the ones row / column
 static int run_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, int bias_of,
-                        bool plant, bool f16, float* partial, int* slabs, cudaStream_t s) {
+                        bool plant, bool f16, int max_rows, float* partial, int* slabs, cudaStream_t s) {
   if (int rc_ = ensure_dyn_smem((const void*)wgrad_tc_kernel, kSmemBytes)) return rc_;
   const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
   const int ones_a = (plant && bias_of == 2) ? K1 : -1, ones_b = (plant && bias_of == 1) ? K2 : -1;
-  const TallPlan t = plan_wgrad_tall(R, K1e, K2e);
+  const TallPlan t = plan_wgrad_tall(R, K1e, K2e, max_rows);
   if (t.ok && tall_enabled()) {
     if (int rc_ = ensure_dyn_smem((const void*)wgrad_tall_kernel, kTallSmem)) return rc_;
     CUtensorMap ma, mb;
@@ -1087,7 +1098,7 @@ static int run_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64
     *slabs = t.splits;
     return check_launch();
   }
-  WgradPlan p = plan_wgrad_tc(R, K1e, K2e);
+  WgradPlan p = plan_wgrad_tc(R, K1e, K2e, max_rows);
   CUtensorMap ma, mb;
   int rc = make_map_bf16(&ma, A, R, K1, lda, 64, kBlockK);      // true widths: columns >= K are zero-filled
   if (rc) return rc;
@@ -1103,7 +1114,7 @@ static int run_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64
 int launch_wgrad_tc(const void* A, int64_t lda, int K1, const void* B, int64_t ldb, int K2, int R, float* dW,
                     int64_t lddw, float* dbias, int bias_of, int accumulate, float* ws, cudaStream_t s) {
   int slabs = 0;
-  if (int rc = run_wgrad_tc(A, lda, K1, B, ldb, K2, R, bias_of, true, false, ws, &slabs, s)) return rc;
+  if (int rc = run_wgrad_tc(A, lda, K1, B, ldb, K2, R, bias_of, true, false, 0, ws, &slabs, s)) return rc;
   const int K1e = K1 + (bias_of == 2 ? 1 : 0), K2e = K2 + (bias_of == 1 ? 1 : 0);
   launch_split_reduce_bias(ws, slabs, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, accumulate, s);
   return check_launch();
@@ -1117,7 +1128,10 @@ void launch_split_reduce_bias_scaled(const float* partial, int slabs, int K1, in
 // split operands: a^T b = (a_hi^T b_hi + a_hi^T b_lo + a_lo^T b_hi) / (s_a s_b); three GEMM launches into
 // consecutive partial-sum slabs, one scaled reduction.  The ones row / column rides on the hi and lo parts of the
 // operand it sums (launches 0 and 1 for b, 0 and 2 for a), never twice on the same part.
-size_t wgrad_split_workspace(int R, int K1, int K2) { return 3 * wgrad_tc_workspace(R, K1, K2); }
+constexpr int kSplitMainRows = 768;    // hi x hi: at most 48 accumulation steps per CTA (the cross terms are 2^-11 smaller)
+size_t wgrad_split_workspace(int R, int K1, int K2) {
+  return wgrad_tc_workspace(R, K1, K2, kSplitMainRows) + 2 * wgrad_tc_workspace(R, K1, K2, 0);
+}
 
 int launch_wgrad_split(const void* A2, int64_t lda, const float* amax_a, int K1, const void* B2, int64_t ldb,
                        const float* amax_b, int K2, int R, float* dW, int64_t lddw, float* dbias, int bias_of, float* ws,
@@ -1131,9 +1145,9 @@ int launch_wgrad_split(const void* A2, int64_t lda, const float* amax_a, int K1,
   int n0 = 0, n1 = 0, n2 = 0;
   // bias_of 2 = column sums of b (ones row on the a side): wanted for b_hi (launch 0) and b_lo (launch 1)
   // bias_of 1 = column sums of a (ones column on the b side): wanted for a_hi (launch 0) and a_lo (launch 2)
-  if (int rc = run_wgrad_tc(A, lda, K1, B, ldb, K2, R, bias_of, true, true, ws, &n0, s)) return rc;
-  if (int rc = run_wgrad_tc(A, lda, K1, B + kb, ldb, K2, R, bias_of, bias_of == 2, true, ws + (size_t)n0 * slab, &n1, s)) return rc;
-  if (int rc = run_wgrad_tc(A + ka, lda, K1, B, ldb, K2, R, bias_of, bias_of == 1, true, ws + (size_t)(n0 + n1) * slab, &n2, s)) return rc;
+  if (int rc = run_wgrad_tc(A, lda, K1, B, ldb, K2, R, bias_of, true, true, kSplitMainRows, ws, &n0, s)) return rc;
+  if (int rc = run_wgrad_tc(A, lda, K1, B + kb, ldb, K2, R, bias_of, bias_of == 2, true, 0, ws + (size_t)n0 * slab, &n1, s)) return rc;
+  if (int rc = run_wgrad_tc(A + ka, lda, K1, B, ldb, K2, R, bias_of, bias_of == 1, true, 0, ws + (size_t)(n0 + n1) * slab, &n2, s)) return rc;
   launch_split_reduce_bias_scaled(ws, n0 + n1 + n2, K1, K2, K1e, K2e, dW, lddw, dbias, bias_of, amax_a, amax_b, s);
   return check_launch();
 }

@@ -23,17 +23,33 @@ namespace edg {
 // order like unsigned integers); *amax must be zero on entry
 __global__ void __launch_bounds__(256)
 amax_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, float* __restrict__ amax) {
-  const int c4 = (cols + 3) >> 2;
-  const int64_t total = (int64_t)rows * c4;
+  const uint32_t c4 = (uint32_t)(cols + 3) >> 2;
+  const uint32_t total = (uint32_t)rows * c4;                    // the launcher keeps rows * ceil(cols / 4) below 2^32
+  const uint32_t stride = gridDim.x * blockDim.x;
   float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / c4), g = (int)(i - (int64_t)r * c4);
-    const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)r * ld + 4 * g);   // ld % 4 == 0: in-row read
-    const int c = 4 * g;
+  auto take = [&](const float4& v, uint32_t g) {
+    const int c = 4 * (int)g;
     m = fmaxf(m, fabsf(v.x));
     if (c + 1 < cols) m = fmaxf(m, fabsf(v.y));
     if (c + 2 < cols) m = fmaxf(m, fabsf(v.z));
     if (c + 3 < cols) m = fmaxf(m, fabsf(v.w));
+  };
+  auto at = [&](uint32_t i, uint32_t& g) {                        // ld % 4 == 0: the 16-byte read stays inside the row
+    const uint32_t r = i / c4;
+    g = i - r * c4;
+    return reinterpret_cast<const float4*>(x + (int64_t)r * ld + 4 * g);
+  };
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < total && total - i > 3 * stride; i += 4 * stride) {  // four independent 16-byte loads in flight
+    uint32_t g0, g1, g2, g3;
+    const float4 v0 = __ldg(at(i, g0)), v1 = __ldg(at(i + stride, g1)), v2 = __ldg(at(i + 2 * stride, g2)),
+                 v3 = __ldg(at(i + 3 * stride, g3));
+    take(v0, g0); take(v1, g1); take(v2, g2); take(v3, g3);
+  }
+  for (; i < total; i += stride) {
+    uint32_t g;
+    const float4 v = __ldg(at(i, g));
+    take(v, g);
   }
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   __shared__ float wm[8];
@@ -49,11 +65,12 @@ amax_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, float* 
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, const float* __restrict__ amax,
                  __half* __restrict__ out, int64_t ldo, int kp) {
-  const int g8 = kp >> 3;
-  const int64_t total = (int64_t)rows * g8;
+  const uint32_t g8 = (uint32_t)kp >> 3;
+  const uint32_t total = (uint32_t)rows * g8;                    // < 2^32 (launcher)
   const float s = split_scale(__ldg(amax));
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / g8), c0 = 8 * (int)(i - (int64_t)r * g8);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t rr = i / g8;
+    const int r = (int)rr, c0 = 8 * (int)(i - rr * g8);
     float v[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -79,15 +96,25 @@ split_f16_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, co
 
 // sum of the partial-sum slabs of the three split products, scaled back: dW by 1/(s_a s_b), the bias row / column by
 // the inverse scale of the operand it sums
-__global__ void split_reduce_bias_scaled_kernel(const float* __restrict__ partial, int slabs, int K1, int K2, int K1e, int K2e,
-                                                float* __restrict__ dW, int64_t lddw, float* __restrict__ dbias, int bias_of,
-                                                const float* __restrict__ amax_a, const float* __restrict__ amax_b) {
+__global__ void __launch_bounds__(256)
+split_reduce_bias_scaled_kernel(const float* __restrict__ partial, int slabs, int K1, int K2, int K1e, int K2e,
+                                float* __restrict__ dW, int64_t lddw, float* __restrict__ dbias, int bias_of,
+                                const float* __restrict__ amax_a, const float* __restrict__ amax_b) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t tot = (int64_t)K1e * K2e;
   if (idx >= tot) return;
   const int m = (int)(idx / K2e), n = (int)(idx - (int64_t)m * K2e);
-  float s = 0.f;
-  for (int z = 0; z < slabs; ++z) s += partial[(int64_t)z * tot + idx];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                   // four chains: enough loads in flight to stream
+  const float* p = partial + idx;
+  int z = 0;
+  for (; z + 8 <= slabs; z += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (int64_t)(z + u) * tot);
+    s0 += v[0] + v[4]; s1 += v[1] + v[5]; s2 += v[2] + v[6]; s3 += v[3] + v[7];
+  }
+  for (; z < slabs; ++z) s0 += __ldg(p + (int64_t)z * tot);
+  const float s = (s0 + s1) + (s2 + s3);
   const float ia = split_inv_scale(__ldg(amax_a)), ib = split_inv_scale(__ldg(amax_b));
   if (m < K1 && n < K2) dW[(int64_t)m * lddw + n] = s * ia * ib;
   else if (bias_of == 2 && m == K1 && n < K2) dbias[n] = s * ib;
@@ -111,6 +138,7 @@ extern "C" int64_t edg_split_pitch(int32_t cols) { return cols > 0 ? 2 * (((int6
 extern "C" int edg_split_f16(const float* x, int64_t ldx, int32_t rows, int32_t cols, void* out, int64_t ldo,
                              float* amax, edg_stream stream) {
   if (rows < 0 || cols <= 0 || !amax) return EDG_ERR_ARG;
+  if ((int64_t)rows * ((cols + 63) / 64 * 16) >= ((int64_t)1 << 31)) return EDG_ERR_UNSUPPORTED;  // 32-bit element counters
   if (ldo != edg_split_pitch(cols) || ldx < cols) return EDG_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(amax, 0, sizeof(float), s);
