@@ -233,8 +233,13 @@ def run_b200(args):
     else:
         opt = E.FusedAdam(params, lr=1e-3)
     reducer = parallel.GradientAllReducer(params)
-    if world > 1 and args.overlap_allreduce:
+    if args.allreduce == "none" and not args.overlap_allreduce:
+        reducer = lambda: None
+    ar_mode = "layer" if args.overlap_allreduce else args.allreduce
+    if world > 1 and ar_mode == "layer":
         stack.grad_ready_hook = reducer.hook          # per-layer all-reduce from inside the backward pass
+    if world > 1 and ar_mode == "bucket":
+        stack.grad_bucket_hook = reducer.bucket       # one flat all-reduce next to the input-gradient projection
     logits_fn = lambda a, p: dense(torch.cat([a, p], 1))
     head_params = list(dense.parameters())
 
@@ -448,6 +453,7 @@ def run_b200(args):
                                    f"({batch.n_rows} rows), fwd+bwd + gate-diversity + importance-score loss + Adam",
                        "graphs_per_gpu": batch.n_graphs, "rows_per_gpu": batch.n_rows, "hidden": c["D"],
                        "layers": c["L"], "classes": c["C"], "parallelism": f"dp{world}",
+                       "allreduce": (ar_mode if world > 1 else None),
                        "l2": f"no explicit flush: each step streams ~{work_mb:.0f} MB of distinct row matrices "
                              f"(> {L2_BYTES / 1e6:.0f} MB L2) so inputs are evicted between steps",
                        "loss": float(loss_val)},
@@ -565,6 +571,11 @@ def main():
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="all-reduce every gradient group from inside the backward pass (GradientAllReducer.hook) instead of "
                          "one coalesced in-place all-reduce after it")
+    ap.add_argument("--allreduce", default=os.environ.get("EDG_BENCH_ALLREDUCE", "bucket"), choices=["flat", "layer", "bucket", "none"],
+                    help="flat: one flat-bucket all-reduce after the backward pass; bucket: the same bucket packed inside the "
+                         "backward pass as soon as the last parameter gradient exists, reduced next to the input-gradient "
+                         "projection (GradientAllReducer.bucket); layer = --overlap-allreduce; none = NO all-reduce (diagnostic "
+                         "only: what N processes cost without the collective; not a training step)")
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused, capturable) instead of edg_adam_multi")
     ap.add_argument("--no-graph", action="store_true", help="enqueue kernels from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

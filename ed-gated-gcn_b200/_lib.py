@@ -44,6 +44,7 @@ SIGNATURES = {
                               _L, _P, c_int, _P, _Z, _P, _P]),
     "edg_row_meta": (c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "edg_adam_multi": (c_int, [_I, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float, _P]),
+    "edg_set_sm_budget": (c_int, [_I]),
     "edg_split_pitch": (_L, [_I]),
     "edg_split_f16": (c_int, [_P, _L, _I, _I, _P, _L, _P, _P]),
     "edg_linear_split_ok": (c_int, [_I, _I]),

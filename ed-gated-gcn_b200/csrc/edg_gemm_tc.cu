@@ -911,13 +911,24 @@ static int launch_linear_tc_t(const CUtensorMap& ma, const CUtensorMap& mw, int 
   return check_launch();
 }
 
+// SMs the persistent projection kernel may occupy (edg_set_sm_budget): a caller that wants a collective to run NEXT to
+// it leaves a few SMs free -- a one-CTA-per-SM kernel with a static tile assignment is otherwise delayed by whatever
+// holds one of its SMs
+static int g_sm_budget = kNumSMs;
+int set_sm_budget(int n) {
+  const int prev = g_sm_budget;
+  g_sm_budget = n < 1 ? 1 : (n > kNumSMs ? kNumSMs : n);
+  return prev;
+}
+
 template <typename TC>
 static int launch_linear_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, int M, int K, int Nout, int block_n,
                               int n_tiles, int stages, size_t smem, const float* bias, int act, void* C, int64_t ldc,
                               cudaStream_t s) {
   if (int rc_ = ensure_dyn_smem((const void*)linear_ws_kernel<TC, false>, 227 * 1024)) return rc_;
   const int m_tiles = (M + kBlockM - 1) / kBlockM;
-  int groups = kNumSMs / n_tiles;                 // CTAs per N tile
+  int groups = g_sm_budget / n_tiles;             // CTAs per N tile
+  if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
   const uint32_t idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
   linear_ws_kernel<TC, false><<<groups * n_tiles, kLinThreads, smem, s>>>(ma, mw, M, K, Nout, block_n, n_tiles, m_tiles,

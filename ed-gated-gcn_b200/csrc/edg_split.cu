@@ -133,6 +133,8 @@ void launch_split_reduce_bias_scaled(const float* partial, int slabs, int K1, in
 
 using namespace edg;
 
+extern "C" int edg_set_sm_budget(int32_t n) { return set_sm_budget(n); }
+
 extern "C" int64_t edg_split_pitch(int32_t cols) { return cols > 0 ? 2 * (((int64_t)cols + 63) / 64 * 64) : 0; }
 
 extern "C" int edg_split_f16(const float* x, int64_t ldx, int32_t rows, int32_t cols, void* out, int64_t ldo,

@@ -66,6 +66,9 @@ _OVERLAP = os.environ.get("EDG_OVERLAP", "1") != "0"
 # the idle side stream: 0.983 vs 0.965 ms -- same cause)
 _OVERLAP_WGRAD = _OVERLAP and os.environ.get("EDG_OVERLAP_WGRAD", "0") == "1"
 _SIDE_STREAMS = {}
+# SMs the input-gradient projection uses while the bucket all-reduce (grad_bucket_hook) runs next to it: the rest is
+# what the collective's CTAs get
+_BUCKET_LINEAR_SMS = 148 - int(os.environ.get("EDG_ALLREDUCE_SMS", "32"))
 
 # The fused layer kernel (edg_gcn_layer: projection + tree aggregation + max-pool in one launch, both directions).
 # EDG_FUSED=0 keeps the unfused aggregate -> linear -> pool kernels (bring-up / A-B timing).
@@ -396,6 +399,7 @@ class _GatedStackFn(torch.autograd.Function):
             g_xout = ops.as_rows(g_xout, cd)
         need_scores = g_kl is not None or g_scores is not None
         grad_hook = cfg.get("grad_hook") or (lambda ts: None)
+        bucket_hook = cfg.get("bucket_hook")
         gated = cfg["gated"]
         views_active = g_xy is not None and Lyr > 1 and gated
         dgates = torch.empty((Lyr, B, D), dtype=torch.float32, device=dev)
@@ -594,6 +598,20 @@ class _GatedStackFn(torch.autograd.Function):
                 grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db_next.to(b.dtype)
                 grad_hook(grads_out[2 * l:2 * l + 2])
                 wk = ctx.w_n[l]                                                 # [in,out] = B operand of du W^T
+                if l == 0 and bucket_hook is not None:
+                    # every parameter gradient of the block exists now (the gate MLPs' come from the side stream): hand
+                    # them to the all-reduce and let it run NEXT to the input-gradient projection, which leaves it SMs
+                    side.join()
+                    side_w.join()
+                    grads_out[-2], grads_out[-1] = d_fcw, d_fcb
+                    n_out = len(grads_out)
+                    reduced = bucket_hook(list(grads_out) + list(head_grads))
+                    grads_out[:] = reduced[:n_out]
+                    head_grads = list(reduced[n_out:])
+                    d_fcw, d_fcb = grads_out[-2], grads_out[-1]
+                    with ops.sm_budget(_BUCKET_LINEAR_SMS):
+                        dh = ops.linear(du, wk, None)
+                    continue
                 if l > 0:
                     if l == 1 and patch_ready is not None:
                         torch.cuda.current_stream(dev).wait_event(patch_ready)
@@ -676,6 +694,11 @@ class GatedGCNStack(nn.Module):
         # data parallelism: called inside the backward pass with every group of parameter gradients the moment it exists
         # (parallel.GradientAllReducer.hook all-reduces it in place while the layers below still run); None = single GPU
         self.grad_ready_hook = None
+        # optional callable(list of gradient tensors or None) -> same list with the tensors it took replaced: called ONCE
+        # per backward pass of the fused path, when every parameter gradient of the block exists and only the input
+        # gradient is left to compute (parallel.GradientAllReducer.bucket packs them into one flat buffer and starts
+        # its all-reduce, which then overlaps that last projection)
+        self.grad_bucket_hook = None
         self.fc_sigmoid = fc_sigmoid
         if fc_sigmoid:                                                   # BertAmir54, bert_amir5.py:464-465 (keys fc.1.*)
             self.fc = nn.Sequential(nn.Sigmoid(), nn.Linear(2 * hidden, n_classes))
@@ -730,7 +753,7 @@ class GatedGCNStack(nn.Module):
             raise L.EdgError(f"expected {self.hidden} feature columns (or the padded pitch), got {x.shape[-1]}")
         cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
-                   head_params=list(head_params), n_head=len(list(head_params)), grad_enabled=torch.is_grad_enabled(), grad_hook=self.grad_ready_hook,
+                   head_params=list(head_params), n_head=len(list(head_params)), grad_enabled=torch.is_grad_enabled(), grad_hook=self.grad_ready_hook, bucket_hook=self.grad_bucket_hook,
                    relu=self.relu, return_x_out=return_x_out, gated=self.gated,
                    drop_p=drop_p, seed=seed, fc_sigmoid=self.fc_sigmoid, view_len=view_len)
         logits, xy, kl, scores, pooled, x_out, p_arg, v_arg = _GatedStackFn.apply(cfg, x, aspect, *self._flat_params(),

@@ -65,6 +65,22 @@ def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype
     return out
 
 
+class sm_budget:
+    """``with ops.sm_budget(n):`` the persistent projection kernel launched inside uses at most ``n`` SMs
+    (``edg_set_sm_budget``), leaving the rest to a collective running next to it."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+
+    def __enter__(self):
+        self.prev = int(L.load().edg_set_sm_budget(self.n))
+        return self
+
+    def __exit__(self, *exc):
+        L.load().edg_set_sm_budget(self.prev)
+        return False
+
+
 class SplitRows:
     """An fp32 row matrix in the split form the fp32-parity tensor-core GEMMs read (``edg_split_f16``):
     ``data`` fp16 ``[rows, 2 * round_up(cols, 64)]`` = ``[hi | lo]`` of ``x * 2^k``, ``amax`` the device scalar the

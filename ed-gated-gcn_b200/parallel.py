@@ -90,10 +90,32 @@ class GradientAllReducer:
             self._done.add(t.data_ptr())
         self._reduce(ts)
 
+    def bucket(self, tensors):
+        """Called ONCE from inside a backward pass with every gradient it produces (``None`` entries allowed): the fp32
+        tensors are packed into one flat buffer whose all-reduce starts right away, and the list comes back with each of
+        them replaced by its view of that buffer -- the caller returns those views to autograd, so ``.grad`` ends up
+        inside the reduced buffer with no copy back (``GatedGCNStack.grad_bucket_hook = reducer.bucket``: the
+        collective then runs next to the input-gradient projection, which is launched on fewer SMs to leave it room)."""
+        if not self._active():
+            return tensors
+        idx = [i for i, t in enumerate(tensors) if t is not None and t.numel() > 0 and t.dtype == torch.float32]
+        if not idx:
+            return tensors
+        flat = torch.cat([tensors[i].reshape(-1) for i in idx])
+        self._reduce([flat])
+        out, off = list(tensors), 0
+        for i in idx:
+            n = tensors[i].numel()
+            out[i] = flat[off:off + n].view_as(tensors[i])
+            self._done.add(out[i].data_ptr())
+            off += n
+        return out
+
     def start(self) -> None:
         if not self._active():
             return
         rest = [p for p in self.params if p.grad is not None and p.grad.data_ptr() not in self._done]
+        self.n_late = len(rest)          # gradients no hook announced (diagnostic)
         if not rest:
             return
         if len(rest) == 1:

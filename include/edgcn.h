@@ -445,6 +445,11 @@ int edg_adam_multi(int32_t n, void* const* param, const void* const* grad, void*
  * (hi hi + hi lo + lo hi) with fp32 accumulation, scaled back by 1/(s_a s_b): error ~2^-21 per product, i.e. the
  * 1e-5 parity bound of the fp32 mode holds (tests/test_gpu_b_kernels.py).  Nothing here synchronises with the host. */
 
+/* SMs (1..148, default 148) the persistent projection kernel behind edg_linear (bf16) may occupy; returns the previous
+ * value.  Process-wide and not thread-safe: set it around the one launch that should leave room for a concurrent
+ * collective (parallel.GradientAllReducer.bucket) and restore it. */
+int edg_set_sm_budget(int32_t n);
+
 /* elements (fp16) per row of the split form of a matrix with `cols` columns: 2 * round_up(cols, 64) */
 int64_t edg_split_pitch(int32_t cols);
 

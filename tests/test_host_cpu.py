@@ -154,6 +154,17 @@ Wl.grad = None; Bl.grad = None
 loss_of(sub, rows, Wl, Bl).backward()
 red()
 ok = ok and torch.allclose(Wl.grad, W.grad, atol=1e-6) and torch.allclose(Bl.grad, Bv.grad, atol=1e-6)
+# third variant: a backward pass hands ALL its gradients over at once (GradientAllReducer.bucket) and returns the views
+# of the reduced flat buffer to autograd -- emulated here by installing the views as .grad
+Wl.grad = None; Bl.grad = None
+loss_of(sub, rows, Wl, Bl).backward()
+gW, gB = Wl.grad, Bl.grad
+out = red.bucket([gW, None, gB])
+ok = ok and out[1] is None and out[0].shape == gW.shape and out[0].data_ptr() != gW.data_ptr()
+Wl.grad, Bl.grad = out[0], out[2]
+red()                        # nothing left to announce: only waits (and applies the gloo scale)
+ok = ok and red.n_late == 0
+ok = ok and torch.allclose(Wl.grad, W.grad, atol=1e-6) and torch.allclose(Bl.grad, Bv.grad, atol=1e-6)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 3)
