@@ -342,6 +342,21 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int chunk
   out[c] = accumulate ? out[c] + s : s;
 }
 
+// one element summed over `slabs` partial-sum slabs `tot` floats apart: eight loads in flight, four chains (the plain
+// loop has one load in flight per thread and is latency-bound: 54 -> 40 us at 444 slabs of 361 KB)
+__device__ __forceinline__ float sum_slabs(const float* __restrict__ p, int slabs, int64_t tot) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int z = 0;
+  for (; z + 8 <= slabs; z += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (int64_t)(z + u) * tot);
+    s0 += v[0] + v[4]; s1 += v[1] + v[5]; s2 += v[2] + v[6]; s3 += v[3] + v[7];
+  }
+  for (; z < slabs; ++z) s0 += __ldg(p + (int64_t)z * tot);
+  return (s0 + s1) + (s2 + s3);
+}
+
 // as split_reduce, for partials of extended shape [K1e, K2e] whose extra row (bias_of 2) or column (bias_of 1)
 // holds the bias gradient
 __global__ void split_reduce_bias_kernel(const float* __restrict__ partial, int splits, int K1, int K2, int K1e, int K2e,
@@ -351,8 +366,7 @@ __global__ void split_reduce_bias_kernel(const float* __restrict__ partial, int 
   const int64_t tot = (int64_t)K1e * K2e;
   if (idx >= tot) return;
   const int m = (int)(idx / K2e), n = (int)(idx - (int64_t)m * K2e);
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * tot + idx];
+  const float s = sum_slabs(partial + idx, splits, tot);
   float* o = nullptr;
   if (m < K1 && n < K2) o = dW + (int64_t)m * lddw + n;
   else if (bias_of == 2 && m == K1 && n < K2) o = dbias + n;
@@ -377,8 +391,7 @@ __global__ void split_reduce_bias_batch_kernel(const float* __restrict__ partial
   const int p = blockIdx.y;
   const float* base = partial + (int64_t)p * splits * tot;
   const int m = (int)(idx / K2e), n = (int)(idx - (int64_t)m * K2e);
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += base[(int64_t)z * tot + idx];
+  const float s = sum_slabs(base + idx, splits, tot);
   if (m < K1 && n < K2) ptrs.dW[p][(int64_t)m * lddw + n] = s;
   else if (bias_of == 2 && m == K1 && n < K2) ptrs.dbias[p][n] = s;
   else if (bias_of == 1 && n == K2 && m < K1) ptrs.dbias[p][m] = s;

@@ -104,17 +104,7 @@ split_reduce_bias_scaled_kernel(const float* __restrict__ partial, int slabs, in
   const int64_t tot = (int64_t)K1e * K2e;
   if (idx >= tot) return;
   const int m = (int)(idx / K2e), n = (int)(idx - (int64_t)m * K2e);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                   // four chains: enough loads in flight to stream
-  const float* p = partial + idx;
-  int z = 0;
-  for (; z + 8 <= slabs; z += 8) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (int64_t)(z + u) * tot);
-    s0 += v[0] + v[4]; s1 += v[1] + v[5]; s2 += v[2] + v[6]; s3 += v[3] + v[7];
-  }
-  for (; z < slabs; ++z) s0 += __ldg(p + (int64_t)z * tot);
-  const float s = (s0 + s1) + (s2 + s3);
+  const float s = sum_slabs(partial + idx, slabs, tot);
   const float ia = split_inv_scale(__ldg(amax_a)), ib = split_inv_scale(__ldg(amax_b));
   if (m < K1 && n < K2) dW[(int64_t)m * lddw + n] = s * ia * ib;
   else if (bias_of == 2 && m == K1 && n < K2) dbias[n] = s * ib;

@@ -207,3 +207,53 @@ def test_head_du_matches_head_bwd_then_aggregate(D, with_scores_grad):
         ar = arg[b].cpu().long() - lo
         dh64[ar, torch.arange(D)] += (gate[b] * gp[b]).double().cpu()
         assert rel(du[lo:hi].float(), ah.t() @ dh64) < 8e-3, b
+
+
+def test_bucket_hook_backward_equals_plain_backward():
+    """`GatedGCNStack.grad_bucket_hook` (what parallel.GradientAllReducer.bucket plugs into): the backward pass hands all
+    parameter gradients over before the input-gradient projection, gets views of one flat buffer back and runs that
+    projection on fewer SMs.  With a hook that only packs, every gradient must equal the plain pass bit for bit, and
+    every parameter's .grad must live inside the flat buffer."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import synth
+    torch.manual_seed(7)
+    D, C, B = 300, 34, 600
+    batch = synth.make_batch(B, 5, 50, seed=11)
+    stack = E.GatedGCNStack(D, n_layers=2, n_classes=C, gate_arch="sig-2", compute_dtype=torch.bfloat16).to(DEV)
+    dense = torch.nn.Linear(2 * D, C).to(DEV)
+    graph = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=DEV)
+    anchor = torch.from_numpy(batch.anchor).to(DEV)
+    dist = E.tree_distance(graph, anchor)
+    x = torch.randn(batch.n_rows, D, device=DEV).requires_grad_(True)
+    tgt = (torch.arange(B) % C).to(DEV)
+    params = list(stack.parameters()) + list(dense.parameters())
+
+    def run():
+        for p in params:
+            p.grad = None
+        x.grad = None
+        out = stack(x, graph, anchor, dist, lambda a, p: dense(torch.cat([a, p], 1)), head_params=list(dense.parameters()))
+        (torch.nn.functional.cross_entropy(out.logits, tgt) + 0.01 * out.xy + 0.01 * out.kl).backward()
+        return [p.grad for p in params], x.grad
+
+    g_plain, dx_plain = run()
+    seen = {}
+
+    def pack_only(tensors):
+        idx = [i for i, t in enumerate(tensors) if t is not None and t.dtype == torch.float32]
+        flat = torch.cat([tensors[i].reshape(-1) for i in idx])
+        seen["flat"], seen["n"] = flat, len(idx)
+        out, off = list(tensors), 0
+        for i in idx:
+            out[i] = flat[off:off + tensors[i].numel()].view_as(tensors[i])
+            off += tensors[i].numel()
+        return out
+
+    stack.grad_bucket_hook = pack_only
+    g_hook, dx_hook = run()
+    assert seen["n"] == len(params)
+    assert torch.equal(dx_hook, dx_plain)
+    lo, hi = seen["flat"].data_ptr(), seen["flat"].data_ptr() + seen["flat"].numel() * 4
+    for a, b in zip(g_hook, g_plain):
+        assert torch.equal(a, b)
+        assert lo <= a.data_ptr() < hi          # autograd installed the view itself: nothing was copied back
