@@ -184,12 +184,14 @@ class KernelTimer:
 
 
 # ---------------------------------------------------------------------------------------------
-def build_model(c, device):
+def build_model(c, device, torch_head=False):
     import ed_gated_gcn_b200 as E
     torch.manual_seed(14181)
     stack = E.GatedGCNStack(c["D"], n_layers=c["L"], n_classes=c["C"], gate_arch="sig-2",
                             compute_dtype=c["dtype"]).to(device)
-    dense = torch.nn.Linear(2 * c["D"], c["C"]).to(device)       # stands for self.dense (bert_amir5.py:643)
+    # self.dense (bert_amir5.py:643): E.DenseHead is that nn.Linear run by the block's own kernels; --torch-head keeps
+    # torch's nn.Linear + F.cross_entropy (cat, three cuBLAS GEMMs, four loss kernels) for comparison
+    dense = (torch.nn.Linear if torch_head else E.DenseHead)(2 * c["D"], c["C"]).to(device)
     for p in list(stack.parameters()) + list(dense.parameters()):        # train.py:75-84
         if p.dim() > 1:
             torch.nn.init.xavier_uniform_(p)
@@ -221,7 +223,7 @@ def run_b200(args):
         # the caller's own classifier head (self.dense, bert_amir5.py:643) is host torch: let cuBLAS use TF32
         # tensor cores for it in the bf16 configuration (the fp32 parity mode keeps full fp32)
         torch.backends.cuda.matmul.allow_tf32 = True
-    stack, dense = build_model(c, dev)
+    stack, dense = build_model(c, dev, torch_head=args.torch_head)
     params = list(stack.parameters()) + list(dense.parameters())
     if world > 1:
         for p in params:
@@ -240,7 +242,12 @@ def run_b200(args):
         stack.grad_ready_hook = reducer.hook          # per-layer all-reduce from inside the backward pass
     if world > 1 and ar_mode == "bucket":
         stack.grad_bucket_hook = reducer.bucket       # one flat all-reduce next to the input-gradient projection
-    logits_fn = lambda a, p: dense(torch.cat([a, p], 1))
+    if args.torch_head:
+        logits_fn = lambda a, p: dense(torch.cat([a, p], 1))
+        ce_loss = torch.nn.functional.cross_entropy
+    else:
+        logits_fn = dense
+        ce_loss = E.cross_entropy                     # nn.CrossEntropyLoss (train.py:96) in two launches
     head_params = list(dense.parameters())
 
     # ---- device-resident inputs (the `value` number)
@@ -258,7 +265,7 @@ def run_b200(args):
         opt.zero_grad(set_to_none=True)
         x_dev.grad = None
         out = stack(x_dev, graph, anchor, dist_dev, logits_fn, head_params=head_params)
-        loss = torch.nn.functional.cross_entropy(out.logits, tgt) + GATE_W * out.xy + KL_W * out.kl
+        loss = ce_loss(out.logits, tgt) + GATE_W * out.xy + KL_W * out.kl
         loss.backward()
         reducer()
         opt.step()
@@ -284,7 +291,7 @@ def run_b200(args):
         tg = tgt_pin.to(dev, non_blocking=True)
         dd = E.tree_distance(g, an)
         out = stack(xb, g, an, dd, logits_fn, head_params=head_params)
-        loss = torch.nn.functional.cross_entropy(out.logits, tg) + GATE_W * out.xy + KL_W * out.kl
+        loss = ce_loss(out.logits, tg) + GATE_W * out.xy + KL_W * out.kl
         loss.backward()
         reducer()
         opt.step()
@@ -356,7 +363,7 @@ def run_b200(args):
             g = E.build_graph(st["heads"], st["sp"], max_len=max_len, device=dev)
             dd = E.tree_distance(g, st["anchor"])
             out = stack(st["x"], g, st["anchor"], dd, logits_fn, head_params=head_params)
-            loss = torch.nn.functional.cross_entropy(out.logits, st["tgt"]) + GATE_W * out.xy + KL_W * out.kl
+            loss = ce_loss(out.logits, st["tgt"]) + GATE_W * out.xy + KL_W * out.kl
             loss.backward()
             reducer()
             opt.step()
@@ -576,6 +583,8 @@ def main():
                          "backward pass as soon as the last parameter gradient exists, reduced next to the input-gradient "
                          "projection (GradientAllReducer.bucket); layer = --overlap-allreduce; none = NO all-reduce (diagnostic "
                          "only: what N processes cost without the collective; not a training step)")
+    ap.add_argument("--torch-head", action="store_true",
+                    help="torch nn.Linear + F.cross_entropy for the classifier head and the loss instead of E.DenseHead / E.cross_entropy")
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused, capturable) instead of edg_adam_multi")
     ap.add_argument("--no-graph", action="store_true", help="enqueue kernels from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -44,6 +44,12 @@ SIGNATURES = {
                               _L, _P, c_int, _P, _Z, _P, _P]),
     "edg_row_meta": (c_int, [_P, _P, _P, _P, _I, _P, _P]),
     "edg_adam_multi": (c_int, [_I, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float, _P]),
+    "edg_dense_head_fwd": (c_int, [_P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P]),
+    "edg_dense_head_bwd_workspace": (_Z, [_I, _I, _I]),
+    "edg_dense_head_bwd": (c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, c_int, _P, _P, _P, _L, _P, _P, _Z, _P]),
+    "edg_cross_entropy_workspace": (_Z, [_I]),
+    "edg_cross_entropy_fwd": (c_int, [_P, _L, _P, _I, _I, _L, _P, _P, _P, _Z, _P]),
+    "edg_cross_entropy_bwd": (c_int, [_P, _L, _P, _I, _I, _L, _P, _P, _P, _L, _P]),
     "edg_set_sm_budget": (c_int, [_I]),
     "edg_split_pitch": (_L, [_I]),
     "edg_split_f16": (c_int, [_P, _L, _I, _I, _P, _L, _P, _P]),
@@ -134,6 +140,8 @@ def _kernels_of(name: str, args) -> int:
         return 3
     if name == "edg_wgrad_split":
         return 4
+    if name == "edg_dense_head_bwd":
+        return 2 if (args[11] & 2) else 1
     if name == "edg_split_f16":
         return 2
     if name in ("edg_csr_from_dense_count", "edg_diversity_fwd", "edg_colsum", "edg_fc_head_bwd", "edg_wgrad_batch", "edg_head_du"):

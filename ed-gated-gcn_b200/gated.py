@@ -321,12 +321,20 @@ class _GatedStackFn(torch.autograd.Function):
         # ---- classifier head: logits_fn is the model's own dense head (host torch, :643); the per-sentence
         # operands of the collapsed scores, [v_b | va_b] = logits_b @ fc.weight and
         # c_b = a_b . va_b + logits_b . fc.bias  (= logits_b . (Wfc[:, D:] a_b + bfc)), are one kernel
-        with torch.enable_grad():
-            a_leaf = a_raw.detach().requires_grad_(True)
-            p_leaf = pooled.detach().requires_grad_(True)
-            logits = logits_fn(a_leaf, p_leaf)
-        if logits.requires_grad and cfg["grad_enabled"]:
-            _check_head_leaves(logits, (a_leaf, p_leaf), cfg["head_params"])
+        # A head.DenseHead (= the reference's nn.Linear on cat[a, pooled]) is run by the block's own kernels: no inner
+        # autograd graph, its weight and bias are head_params[0:2].
+        dense_head = cfg.get("dense_head")
+        a_leaf = p_leaf = None
+        if dense_head is not None:
+            hp = cfg["head_params"]
+            logits = ops.dense_head_fwd(a_raw, pooled, hp[0], hp[1] if len(hp) > 1 else None)
+        else:
+            with torch.enable_grad():
+                a_leaf = a_raw.detach().requires_grad_(True)
+                p_leaf = pooled.detach().requires_grad_(True)
+                logits = logits_fn(a_leaf, p_leaf)
+            if logits.requires_grad and cfg["grad_enabled"]:
+                _check_head_leaves(logits, (a_leaf, p_leaf), cfg["head_params"])
         lg = logits.detach().float().contiguous()
         fcw32, fcb32 = fc_w.detach().float().contiguous(), fc_b.detach().float().contiguous()
         fc_sig = cfg["fc_sigmoid"]
@@ -355,6 +363,9 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not zero tensors
         ctx.cfg = cfg
         ctx.head = (a_leaf, p_leaf, logits, lg, a_raw, v)
+        # (detached alias: `pooled` itself is an output of this node, and an output stored on its own node is a reference
+        # cycle that keeps the whole graph -- and its AccumulateGrad nodes with their stream -- alive until the cyclic GC)
+        ctx.pooled_head = pooled.detach() if dense_head is not None else None
         ctx.gate_saved = gate_saved
         ctx.n_params = len(params)
         ctx.n_head = n_head
@@ -448,7 +459,17 @@ class _GatedStackFn(torch.autograd.Function):
         # ---- host head backward through logits_fn: d a, d pooled, and .grad of the parameters it closes over
         ga_head = gp_head = None
         head_grads: List[Optional[torch.Tensor]] = [None] * ctx.n_head
-        if g_lg is not None and logits.requires_grad:
+        if g_lg is not None and cfg.get("dense_head") is not None:
+            hp = cfg["head_params"]
+            ga_head, gp_head, _, _ = ops.dense_head_bwd(g_lg, a_raw, ctx.pooled_head, hp[0], parts=1)
+            with side.region():       # nothing downstream waits for the head's parameter gradients: side stream
+                _, _, d_hw, d_hb = ops.dense_head_bwd(g_lg, a_raw, ctx.pooled_head, hp[0], parts=2)
+                if hp[0].requires_grad:
+                    head_grads[0] = d_hw.to(hp[0].dtype)
+                if len(hp) > 1 and hp[1].requires_grad:
+                    head_grads[1] = d_hb.to(hp[1].dtype)
+                grad_hook([g for g in head_grads if g is not None and g.dtype == torch.float32])
+        elif g_lg is not None and logits.requires_grad:
             cap = [(i, p) for i, p in enumerate(cfg["head_params"]) if p.requires_grad]
             res = torch.autograd.grad([logits], [a_leaf, p_leaf] + [p for _, p in cap], [g_lg.to(logits.dtype)],
                                       allow_unused=True, retain_graph=True)
@@ -751,7 +772,11 @@ class GatedGCNStack(nn.Module):
         lead, pairs = GATE_ARCHS[self.gate_arch]
         if x.shape[-1] != self.hidden and x.shape[-1] != ops.row_pitch(self.hidden, x.dtype):
             raise L.EdgError(f"expected {self.hidden} feature columns (or the padded pitch), got {x.shape[-1]}")
-        cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, L=self.n_layers, pairs=pairs, lead=lead,
+        from .head import DenseHead
+        dense_head = logits_fn if isinstance(logits_fn, DenseHead) and logits_fn.fusable(self.hidden) else None
+        if dense_head is not None:          # its parameters are the head parameters: nothing to declare
+            head_params = [p for p in (dense_head.weight, dense_head.bias) if p is not None]
+        cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, dense_head=dense_head, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
                    head_params=list(head_params), n_head=len(list(head_params)), grad_enabled=torch.is_grad_enabled(), grad_hook=self.grad_ready_hook, bucket_hook=self.grad_bucket_hook,
                    relu=self.relu, return_x_out=return_x_out, gated=self.gated,

@@ -457,6 +457,67 @@ def fc_head_bwd(logits, fc_w, fc_b, a, dv, dc, scale: Optional[torch.Tensor] = N
     return d_lg, d_a, d_w, d_b
 
 
+DENSE_HEAD_MAX_CLASSES = 64
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def dense_head_fwd(a: torch.Tensor, p: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """``edg_dense_head_fwd``: ``cat([a, p], 1) @ w.T + bias`` with ``a, p`` fp32 ``[B, D]``, ``w`` fp32 ``[C, 2D]``."""
+    a, p, w = _f32c(a), _f32c(p), _f32c(w)
+    B, D = a.shape
+    C = w.shape[0]
+    assert p.shape == (B, D) and w.shape[1] == 2 * D
+    bias = _f32c(bias) if bias is not None else None
+    logits = torch.empty((B, C), dtype=torch.float32, device=a.device)
+    L.call("edg_dense_head_fwd", L.ptr(a), ld(a), L.ptr(p), ld(p), L.ptr(w), ld(w), L.ptr(bias), B, D, C,
+           L.ptr(logits), C, L.stream())
+    return logits
+
+
+def dense_head_bwd(g: torch.Tensor, a: torch.Tensor, p: torch.Tensor, w: torch.Tensor, parts: int = 3):
+    """``edg_dense_head_bwd`` -> ``(da [B,D], dp [B,D])`` (``parts & 1``), ``(dW [C,2D], dbias [C])`` (``parts & 2``)
+    from ``g = d logits [B,C]``."""
+    g, a, p, w = _f32c(g), _f32c(a), _f32c(p), _f32c(w)
+    B, D = a.shape
+    C = w.shape[0]
+    dev = a.device
+    da = torch.empty((B, D), dtype=torch.float32, device=dev) if parts & 1 else None
+    dp = torch.empty((B, D), dtype=torch.float32, device=dev) if parts & 1 else None
+    dW = torch.empty((C, 2 * D), dtype=torch.float32, device=dev) if parts & 2 else None
+    db = torch.empty((C,), dtype=torch.float32, device=dev) if parts & 2 else None
+    nbytes = L.load().edg_dense_head_bwd_workspace(B, D, C)
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+    L.call("edg_dense_head_bwd", L.ptr(g), ld(g), L.ptr(a), ld(a), L.ptr(p), ld(p), L.ptr(w), ld(w), B, D, C, int(parts),
+           L.ptr(da), L.ptr(dp), L.ptr(dW), 2 * D, L.ptr(db), L.ptr(ws), ws.numel() * 4, L.stream())
+    return da, dp, dW, db
+
+
+def cross_entropy_fwd(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = -100):
+    """``edg_cross_entropy_fwd`` -> ``(out fp32 [2] = {mean loss, counted rows}, bad int32 [1])``."""
+    B, C = logits.shape
+    out = torch.empty((2,), dtype=torch.float32, device=logits.device)
+    nbytes = L.load().edg_cross_entropy_workspace(B)
+    # one zeroed allocation: [bad flag | per-block partial sums | ticket counter]
+    buf = torch.zeros((1 + (nbytes + 3) // 4,), dtype=torch.int32, device=logits.device)
+    bad, ws = buf[:1], buf[1:]
+    L.call("edg_cross_entropy_fwd", L.ptr(logits), ld(logits), L.ptr(target), B, C, int(ignore_index), L.ptr(out),
+           L.ptr(bad), L.ptr(ws), ws.numel() * 4, L.stream())
+    return out, bad
+
+
+def cross_entropy_bwd(logits: torch.Tensor, target: torch.Tensor, gscale: Optional[torch.Tensor], fwd_out: torch.Tensor,
+                      ignore_index: int = -100) -> torch.Tensor:
+    B, C = logits.shape
+    dlg = torch.empty((B, C), dtype=torch.float32, device=logits.device)
+    L.call("edg_cross_entropy_bwd", L.ptr(logits), ld(logits), L.ptr(target), B, C, int(ignore_index), L.ptr(gscale),
+           L.ptr(fwd_out), L.ptr(dlg), C, L.stream())
+    return dlg
+
+
 def head_bwd(h, graph, gate, v, dist, scores, kl_b, g_kl, g_scores, g_pooled, arg, g_xout, want_dh: bool,
              want_dv: bool, dgate_out: Optional[torch.Tensor] = None):
     B, D = gate.shape

@@ -475,6 +475,36 @@ int edg_wgrad_split(const void* A2, int64_t lda, const float* amax_a, int32_t K1
                     const float* amax_b, int32_t K2, int32_t R, float* dW, int64_t lddw, float* dbias, int bias_of,
                     void* ws, size_t ws_bytes, edg_stream stream);
 
+/* ------------------------------------------------------------------------- */
+/* Classifier head and loss (bert_amir5.py:643 self.dense, train.py:121)      */
+/* ------------------------------------------------------------------------- */
+
+/* logits fp32 [B, C] = [a | p] W^T + bias with a, p fp32 [B, D], W fp32 [C, 2D] (nn.Linear(2D, C).weight), bias [C] or
+ * NULL: `self.dense(torch.cat([aspect, pooled], 1))` without the cat.  C <= 64. */
+int edg_dense_head_fwd(const float* a, int64_t lda, const float* p, int64_t ldp, const float* W, int64_t ldw,
+                       const float* bias, int32_t B, int32_t D, int32_t C, float* logits, int64_t ldl, edg_stream stream);
+
+/* Its backward from g = d logits [B, C]:  da = g W[:, :D], dp = g W[:, D:] (fp32 [B, D] contiguous; either may be NULL),
+ * dW [C, 2D] = g^T [a | p], dbias [C] = colsum(g); fixed summation order.  parts: bit 0 = da / dp, bit 1 = dW / dbias (two
+ * calls on two streams keep the parameter gradients off the critical path).  ws: edg_dense_head_bwd_workspace bytes. */
+size_t edg_dense_head_bwd_workspace(int32_t B, int32_t D, int32_t C);
+int edg_dense_head_bwd(const float* g, int64_t ldg, const float* a, int64_t lda, const float* p, int64_t ldp,
+                       const float* W, int64_t ldw, int32_t B, int32_t D, int32_t C, int parts, float* da, float* dp,
+                       float* dW, int64_t lddw, float* dbias, void* ws, size_t ws_bytes, edg_stream stream);
+
+/* nn.CrossEntropyLoss (mean reduction, ignore_index): out = device float[2] {mean loss over the rows whose target is not
+ * ignore_index, number of such rows}; bad = device int[1], OR-ed with 1 when a target lies outside [0, C) (checked by the
+ * caller when it chooses to: nothing here synchronises).  The backward writes
+ * dlogits[b, c] = (softmax(logits_b)[c] - [c == target_b]) * (*gscale) / count (gscale NULL = 1), zero rows for ignored
+ * targets; fwd_out is the forward's `out`.  ws: edg_cross_entropy_workspace(B) bytes of per-block partial sums whose last
+ * 4 bytes are a ticket counter: zero before the first call, left zero by every call. */
+size_t edg_cross_entropy_workspace(int32_t B);
+int edg_cross_entropy_fwd(const float* logits, int64_t ldl, const int64_t* target, int32_t B, int32_t C,
+                          int64_t ignore_index, float* out, int32_t* bad, void* ws, size_t ws_bytes, edg_stream stream);
+int edg_cross_entropy_bwd(const float* logits, int64_t ldl, const int64_t* target, int32_t B, int32_t C,
+                          int64_t ignore_index, const float* gscale, const float* fwd_out, float* dlogits, int64_t lddl,
+                          edg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

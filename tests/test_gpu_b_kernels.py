@@ -453,3 +453,56 @@ def test_fp32_ffma_kernels_still_cover_the_large_shapes(monkeypatch):
     assert rel(ops.linear(a, w, None), a.double() @ w.double().t()) < 2e-6
     dW, db = ops.wgrad(a, a, bias_of=2)
     assert rel(dW, a.double().t() @ a.double()) < 2e-6 and rel(db, a.double().sum(0)) < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# classifier head + loss (csrc/edg_dense_head.cu): bert_amir5.py:643 self.dense, train.py:121 criterion
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4096, 300, 34), (33, 300, 34), (1, 64, 2), (257, 768, 34), (100, 20, 7), (64, 300, 50)])
+def test_dense_head_forward_backward_vs_torch(shape):
+    import ed_gated_gcn_b200 as E
+    B, D, C = shape
+    g = torch.Generator().manual_seed(B + D)
+    a = torch.randn(B, D, generator=g).to(DEV).requires_grad_(True)
+    p = torch.randn(B, D, generator=g).to(DEV).requires_grad_(True)
+    head = E.DenseHead(2 * D, C).to(DEV)
+    probe = torch.randn(B, C, generator=g).to(DEV)
+    got = head(a, p)
+    (got * probe).sum().backward()
+    mine = [a.grad.clone(), p.grad.clone(), head.weight.grad.clone(), head.bias.grad.clone()]
+    a.grad = p.grad = None
+    head.zero_grad()
+    ad, pd_ = a.detach().double().requires_grad_(True), p.detach().double().requires_grad_(True)
+    wd, bd = head.weight.detach().double().requires_grad_(True), head.bias.detach().double().requires_grad_(True)
+    want = torch.cat([ad, pd_], 1) @ wd.t() + bd                        # the reference's self.dense(cat[...])
+    (want * probe.double()).sum().backward()
+    assert rel(got, want) < 2e-6
+    for m, w in zip(mine, [ad.grad, pd_.grad, wd.grad, bd.grad]):
+        assert rel(m, w) < 2e-6
+    # plain nn.Linear call (one concatenated argument) still works, same numbers
+    assert rel(head(torch.cat([a, p], 1)), want) < 2e-6
+
+
+@pytest.mark.parametrize("B,C", [(4096, 34), (7, 3), (1, 2), (5000, 64), (300, 1000)])
+def test_cross_entropy_matches_torch(B, C):
+    import ed_gated_gcn_b200 as E
+    g = torch.Generator().manual_seed(B + C)
+    logits = (4 * torch.randn(B, C, generator=g)).to(DEV).requires_grad_(True)
+    tgt = torch.randint(0, C, (B,), generator=g).to(DEV)
+    if B > 4:
+        tgt[1::5] = -100                                               # nn.CrossEntropyLoss's ignore_index
+    w = torch.tensor(0.37, device=DEV)
+    loss = E.cross_entropy(logits, tgt)
+    (loss * w).backward()
+    got_g = logits.grad.clone()
+    logits.grad = None
+    ref = torch.nn.functional.cross_entropy(logits.double(), tgt)
+    (ref * w.double()).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+    assert rel(got_g, logits.grad) < 5e-6
+    assert float(E.CrossEntropyLoss()(logits.detach(), tgt)) == float(loss)
+    # every target ignored: zero loss, zero gradient (torch returns nan here; the reference never feeds such a batch)
+    logits.grad = None
+    l0 = E.cross_entropy(logits, torch.full_like(tgt, -100))
+    l0.backward()
+    assert float(l0) == 0.0 and float(logits.grad.abs().max()) == 0.0

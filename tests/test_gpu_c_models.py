@@ -631,3 +631,50 @@ def test_tensors_on_a_second_gpu_with_device_0_current():
     assert torch.cuda.current_device() == 0
     for a, b in zip(outs[0], outs[1]):              # same arithmetic on both devices: bitwise equal
         assert (torch.equal(a, b) if torch.is_tensor(a) else a == b)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f32", "bf16"])
+def test_dense_head_and_fused_loss_equal_the_torch_head(dtype):
+    """`E.DenseHead` passed as logits_fn (run inside the block by edg_dense_head_fwd/bwd) + `E.cross_entropy` against the
+    same stack with torch's nn.Linear-on-cat head and F.cross_entropy: same loss, same gradients everywhere."""
+    import ed_gated_gcn_b200 as E
+    from ed_gated_gcn_b200 import synth
+    torch.manual_seed(5)
+    D, C, B = 300, 34, 200
+    batch = synth.make_batch(B, 5, 50, seed=3)
+    stack = E.GatedGCNStack(D, n_layers=2, n_classes=C, gate_arch="sig-2", compute_dtype=dtype).to(DEV)
+    head = E.DenseHead(2 * D, C).to(DEV)
+    graph = E.build_graph(torch.from_numpy(batch.heads), torch.from_numpy(batch.sent_ptr), device=DEV)
+    anchor = torch.from_numpy(batch.anchor).to(DEV)
+    dist = E.tree_distance(graph, anchor)
+    x = torch.randn(batch.n_rows, D, device=DEV).requires_grad_(True)
+    tgt = (torch.arange(B) % C).to(DEV)
+    params = list(stack.parameters()) + list(head.parameters())
+
+    def run(fused):
+        for p in params:
+            p.grad = None
+        x.grad = None
+        if fused:
+            out = stack(x, graph, anchor, dist, head)
+            loss = E.cross_entropy(out.logits, tgt) + 0.01 * out.xy + 0.01 * out.kl
+        else:
+            out = stack(x, graph, anchor, dist, lambda a, p: torch.nn.functional.linear(torch.cat([a, p], 1), head.weight, head.bias),
+                        head_params=list(head.parameters()))
+            loss = torch.nn.functional.cross_entropy(out.logits, tgt) + 0.01 * out.xy + 0.01 * out.kl
+        loss.backward()
+        return out.logits.clone(), float(loss), [p.grad.clone() for p in params], x.grad.clone()
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    lg_t, loss_t, g_t, dx_t = run(False)
+    lg_f, loss_f, g_f, dx_f = run(True)
+    tol = 1e-5 if dtype == torch.float32 else 2e-3       # same bf16 kernels on both sides: only the head's fp32 rounding differs
+    assert rel(lg_f, lg_t) < 1e-5
+    assert abs(loss_f - loss_t) < 1e-5 * max(1.0, abs(loss_t))
+    assert rel(dx_f, dx_t) < tol
+    scale = max(float(b.abs().max()) for b in g_t)
+    for a, b in zip(g_f, g_t):
+        # against the larger of the tensor's own magnitude and 1e-3 of the largest gradient: fc.bias' gradient is
+        # analytically zero here (1e-12 of rounding noise on both sides, next to gradients of 6e-2)
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= tol * max(float(b.abs().max()), 1e-3 * scale)
