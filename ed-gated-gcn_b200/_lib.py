@@ -46,7 +46,8 @@ SIGNATURES = {
     "edg_adam_multi": (c_int, [_I, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float, _P]),
     "edg_dense_head_fwd": (c_int, [_P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P]),
     "edg_dense_head_bwd_workspace": (_Z, [_I, _I, _I]),
-    "edg_dense_head_bwd": (c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, c_int, _P, _P, _P, _L, _P, _P, _Z, _P]),
+    "edg_dense_head_bwd": (c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, c_int, _P, _L, _P, _P, _P, _P, _P, _L, _P, _P, _Z,
+                                   _P]),
     "edg_cross_entropy_workspace": (_Z, [_I]),
     "edg_cross_entropy_fwd": (c_int, [_P, _L, _P, _I, _I, _L, _P, _P, _P, _Z, _P]),
     "edg_cross_entropy_bwd": (c_int, [_P, _L, _P, _I, _I, _L, _P, _P, _P, _L, _P]),

@@ -106,8 +106,11 @@ template <int CP>
 __global__ void __launch_bounds__(kHeadThreads, 2)
 dense_head_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ a, int64_t lda,
                       const float* __restrict__ p, int64_t ldp, const float* __restrict__ W, int64_t ldw, int B, int D,
-                      int C, int vec4, int parts, float* __restrict__ da, float* __restrict__ dp,
-                      float* __restrict__ partial) {
+                      int C, int vec4, int parts, const float* __restrict__ g2, int64_t ldg2,
+                      const float* __restrict__ da_add, const float* __restrict__ dp_add, float* __restrict__ da,
+                      float* __restrict__ dp, float* __restrict__ partial) {
+  // g2 (optional): a second d logits term added to g on load (the loss' share + the scores term's share); da_add /
+  // dp_add (optional, [B, D] contiguous): added to the input gradients on store (what else flows into a and pooled)
   // parts: bit 0 = input gradients (needs W), bit 1 = parameter-gradient partials (needs the rows): two launches on two
   // streams keep the parameter gradients, which nothing downstream waits for, off the critical path
   extern __shared__ __align__(16) float head_smem[];
@@ -121,7 +124,8 @@ dense_head_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __r
   const int W2 = 2 * D;
   for (int i = threadIdx.x; i < CP * kHeadGraphs; i += kHeadThreads) {
     const int gi = i / CP, cc = i - gi * CP;
-    const float x = (gi < nb && cc < C) ? g[(int64_t)(b0 + gi) * ldg + cc] : 0.f;
+    float x = (gi < nb && cc < C) ? g[(int64_t)(b0 + gi) * ldg + cc] : 0.f;
+    if (g2 && gi < nb && cc < C) x += g2[(int64_t)(b0 + gi) * ldg2 + cc];
     g_t[cc][gi] = x;
     g_s[gi][cc] = x;
   }
@@ -130,6 +134,7 @@ dense_head_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __r
   const float* x = half == 0 ? a : p;
   const int64_t ldx = half == 0 ? lda : ldp;
   float* dx = half == 0 ? da : dp;
+  const float* dx_add = half == 0 ? da_add : dp_add;
   float* P = partial + (int64_t)blockIdx.x * C * (W2 + 1);
   for (int d0 = 0; d0 < D; d0 += kHeadPitch) {
     __syncthreads();
@@ -143,7 +148,10 @@ dense_head_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __r
         dot4<CP>(Ws + jj, g_t, g0, s);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (g0 + q < nb) dx[(int64_t)(b0 + g0 + q) * D + d0 + jj] = s[q];
+          if (g0 + q < nb) {
+            const int64_t o = (int64_t)(b0 + g0 + q) * D + d0 + jj;
+            dx[o] = dx_add ? s[q] + __ldg(dx_add + o) : s[q];
+          }
       }
     }
     for (int jj = threadIdx.x; (parts & 2) && jj < lim; jj += kHeadThreads) {   // thread = column of the pass
@@ -286,7 +294,8 @@ extern "C" size_t edg_dense_head_bwd_workspace(int32_t B, int32_t D, int32_t C) 
 }
 
 extern "C" int edg_dense_head_bwd(const float* g, int64_t ldg, const float* a, int64_t lda, const float* p, int64_t ldp,
-                                  const float* W, int64_t ldw, int32_t B, int32_t D, int32_t C, int parts, float* da,
+                                  const float* W, int64_t ldw, int32_t B, int32_t D, int32_t C, int parts,
+                                  const float* g2, int64_t ldg2, const float* da_add, const float* dp_add, float* da,
                                   float* dp, float* dW, int64_t lddw, float* dbias, void* ws, size_t ws_bytes,
                                   edg_stream stream) {
   if (B < 0 || D <= 0 || C <= 0 || parts < 1 || parts > 3) return EDG_ERR_ARG;
@@ -301,7 +310,7 @@ extern "C" int edg_dense_head_bwd(const float* g, int64_t ldg, const float* a, i
     return check_launch();
   }
   if (!g || !a || !p || !W || !ws) return EDG_ERR_ARG;
-  if (ldg < C || lda < D || ldp < D || ldw < 2 * D) return EDG_ERR_ARG;
+  if (ldg < C || lda < D || ldp < D || ldw < 2 * D || (g2 && ldg2 < C)) return EDG_ERR_ARG;
   if (ws_bytes < edg_dense_head_bwd_workspace(B, D, C)) return EDG_ERR_WORKSPACE;
   const int vec4 = ((D & 3) == 0 && (ldw & 3) == 0 && (lda & 3) == 0 && (ldp & 3) == 0 && aligned16(W) && aligned16(a) &&
                     aligned16(p)) ? 1 : 0;
@@ -310,7 +319,8 @@ extern "C" int edg_dense_head_bwd(const float* g, int64_t ldg, const float* a, i
   auto launch = [&](auto kern, int CP) -> int {
     const size_t smem = (size_t)(CP + kHeadGraphs) * kHeadPitch * sizeof(float);
     if (int rc_ = ensure_dyn_smem((const void*)kern, smem)) return rc_;
-    kern<<<dim3(blocks, 2), kHeadThreads, smem, s>>>(g, ldg, a, lda, p, ldp, W, ldw, B, D, C, vec4, parts, da, dp, partial);
+    kern<<<dim3(blocks, 2), kHeadThreads, smem, s>>>(g, ldg, a, lda, p, ldp, W, ldw, B, D, C, vec4, parts, g2, ldg2, da_add, dp_add,
+                                                     da, dp, partial);
     return check_launch();
   };
   int rc;

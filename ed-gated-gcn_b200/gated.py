@@ -435,7 +435,7 @@ class _GatedStackFn(torch.autograd.Function):
         # ---- d v, d c: the per-unit gradients of the forward sweep times d kl, or (when scores itself carries
         # gradient) pass A over h_L
         fc_w, fc_b = params[-2], params[-1]
-        d_fcw = d_fcb = da_fc = None
+        d_fcw = d_fcb = da_fc = g_lg2 = None
         g_lg = g_logits.float() if g_logits is not None else None
         if need_scores:
             if g_scores is None:
@@ -455,15 +455,21 @@ class _GatedStackFn(torch.autograd.Function):
                 grad_hook([d_fcw, d_fcb])
             if ctx.fc_sig:
                 da_fc = da_fc * a_fc * (1.0 - a_fc)                   # through sigmoid(a)
-            g_lg = d_lg if g_lg is None else g_lg + d_lg
+            if cfg.get("dense_head") is not None and g_lg is not None:
+                g_lg2 = d_lg                      # the fused head adds the two d logits terms while it loads them
+            else:
+                g_lg = d_lg if g_lg is None else g_lg + d_lg
         # ---- host head backward through logits_fn: d a, d pooled, and .grad of the parameters it closes over
         ga_head = gp_head = None
         head_grads: List[Optional[torch.Tensor]] = [None] * ctx.n_head
         if g_lg is not None and cfg.get("dense_head") is not None:
             hp = cfg["head_params"]
-            ga_head, gp_head, _, _ = ops.dense_head_bwd(g_lg, a_raw, ctx.pooled_head, hp[0], parts=1)
+            # d a and d pooled leave with everything else that flows into a / pooled already added (da_fc, g_pooled)
+            ga_head, gp_head, _, _ = ops.dense_head_bwd(g_lg, a_raw, ctx.pooled_head, hp[0], parts=1, g2=g_lg2,
+                                                        da_add=da_fc, dp_add=g_pooled)
+            da_fc = g_pooled = None
             with side.region():       # nothing downstream waits for the head's parameter gradients: side stream
-                _, _, d_hw, d_hb = ops.dense_head_bwd(g_lg, a_raw, ctx.pooled_head, hp[0], parts=2)
+                _, _, d_hw, d_hb = ops.dense_head_bwd(g_lg, a_raw, ctx.pooled_head, hp[0], parts=2, g2=g_lg2)
                 if hp[0].requires_grad:
                     head_grads[0] = d_hw.to(hp[0].dtype)
                 if len(hp) > 1 and hp[1].requires_grad:

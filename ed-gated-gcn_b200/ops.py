@@ -478,10 +478,15 @@ def dense_head_fwd(a: torch.Tensor, p: torch.Tensor, w: torch.Tensor, bias: Opti
     return logits
 
 
-def dense_head_bwd(g: torch.Tensor, a: torch.Tensor, p: torch.Tensor, w: torch.Tensor, parts: int = 3):
+def dense_head_bwd(g: torch.Tensor, a: torch.Tensor, p: torch.Tensor, w: torch.Tensor, parts: int = 3,
+                   g2: Optional[torch.Tensor] = None, da_add: Optional[torch.Tensor] = None,
+                   dp_add: Optional[torch.Tensor] = None):
     """``edg_dense_head_bwd`` -> ``(da [B,D], dp [B,D])`` (``parts & 1``), ``(dW [C,2D], dbias [C])`` (``parts & 2``)
-    from ``g = d logits [B,C]``."""
+    from ``d logits = g (+ g2) [B,C]``; ``da_add`` / ``dp_add`` (fp32 ``[B,D]``) are added to ``da`` / ``dp``."""
     g, a, p, w = _f32c(g), _f32c(a), _f32c(p), _f32c(w)
+    g2 = _f32c(g2) if g2 is not None else None
+    da_add = _f32c(da_add) if da_add is not None else None
+    dp_add = _f32c(dp_add) if dp_add is not None else None
     B, D = a.shape
     C = w.shape[0]
     dev = a.device
@@ -492,6 +497,7 @@ def dense_head_bwd(g: torch.Tensor, a: torch.Tensor, p: torch.Tensor, w: torch.T
     nbytes = L.load().edg_dense_head_bwd_workspace(B, D, C)
     ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
     L.call("edg_dense_head_bwd", L.ptr(g), ld(g), L.ptr(a), ld(a), L.ptr(p), ld(p), L.ptr(w), ld(w), B, D, C, int(parts),
+           L.ptr(g2), ld(g2) if g2 is not None else 0, L.ptr(da_add), L.ptr(dp_add),
            L.ptr(da), L.ptr(dp), L.ptr(dW), 2 * D, L.ptr(db), L.ptr(ws), ws.numel() * 4, L.stream())
     return da, dp, dW, db
 

@@ -486,11 +486,14 @@ int edg_dense_head_fwd(const float* a, int64_t lda, const float* p, int64_t ldp,
 
 /* Its backward from g = d logits [B, C]:  da = g W[:, :D], dp = g W[:, D:] (fp32 [B, D] contiguous; either may be NULL),
  * dW [C, 2D] = g^T [a | p], dbias [C] = colsum(g); fixed summation order.  parts: bit 0 = da / dp, bit 1 = dW / dbias (two
- * calls on two streams keep the parameter gradients off the critical path).  ws: edg_dense_head_bwd_workspace bytes. */
+ * calls on two streams keep the parameter gradients off the critical path).  Optional: g2 [B, C] is added to g on load,
+ * da_add / dp_add [B, D] (contiguous) are added to da / dp on store -- the sums torch would run as separate elementwise
+ * launches.  ws: edg_dense_head_bwd_workspace bytes. */
 size_t edg_dense_head_bwd_workspace(int32_t B, int32_t D, int32_t C);
 int edg_dense_head_bwd(const float* g, int64_t ldg, const float* a, int64_t lda, const float* p, int64_t ldp,
-                       const float* W, int64_t ldw, int32_t B, int32_t D, int32_t C, int parts, float* da, float* dp,
-                       float* dW, int64_t lddw, float* dbias, void* ws, size_t ws_bytes, edg_stream stream);
+                       const float* W, int64_t ldw, int32_t B, int32_t D, int32_t C, int parts, const float* g2,
+                       int64_t ldg2, const float* da_add, const float* dp_add, float* da, float* dp, float* dW,
+                       int64_t lddw, float* dbias, void* ws, size_t ws_bytes, edg_stream stream);
 
 /* nn.CrossEntropyLoss (mean reduction, ignore_index): out = device float[2] {mean loss over the rows whose target is not
  * ignore_index, number of such rows}; bad = device int[1], OR-ed with 1 when a target lies outside [0, C) (checked by the
