@@ -98,6 +98,10 @@ class GradientAllReducer:
         collective then runs next to the input-gradient projection, which is launched on fewer SMs to leave it room)."""
         if not self._active():
             return tensors
+        if any(p.grad is not None for p in self.params):
+            # autograd would ACCUMULATE the views into the existing .grad tensors on the compute stream while the
+            # collective is still writing them: leave everything to the flat bucket after the backward pass
+            return tensors
         idx = [i for i, t in enumerate(tensors) if t is not None and t.numel() > 0 and t.dtype == torch.float32]
         if not idx:
             return tensors

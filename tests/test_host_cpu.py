@@ -159,6 +159,9 @@ ok = ok and torch.allclose(Wl.grad, W.grad, atol=1e-6) and torch.allclose(Bl.gra
 Wl.grad = None; Bl.grad = None
 loss_of(sub, rows, Wl, Bl).backward()
 gW, gB = Wl.grad, Bl.grad
+keep = red.bucket([gW, None, gB])          # .grad already populated: the bucket must refuse (autograd would accumulate)
+ok = ok and keep[0] is gW and keep[2] is gB
+Wl.grad = None; Bl.grad = None             # inside a real backward pass nothing is installed yet
 out = red.bucket([gW, None, gB])
 ok = ok and out[1] is None and out[0].shape == gW.shape and out[0].data_ptr() != gW.data_ptr()
 Wl.grad, Bl.grad = out[0], out[2]
