@@ -104,6 +104,8 @@ def f32_tc(rows: int, K: int, Nout: int) -> bool:
     import os
     if os.environ.get("EDG_F32_TC", "1") == "0" or rows < F32_TC_MIN_ROWS:
         return False
+    if rows * ((max(K, Nout) + 63) // 64) * 16 >= 2 ** 31:      # edg_split_f16 counts elements in 32 bits
+        return False
     return bool(L.load().edg_linear_split_ok(int(K), int(Nout)))
 
 

@@ -301,3 +301,22 @@ def test_built_library_contains_tcgen05_and_tma_instructions():
         assert "LDTM" in ops_of(kern), kern                          # accumulators read back from TMEM
     for kern in ("aggregate_staged_kernel", "pool_staged_kernel", "scores_staged_kernel", "head_bwd_staged_kernel"):
         assert "UBLKCP" in ops_of(kern), kern                        # windows staged by bulk async copies
+
+
+def test_head_and_loss_modules_keep_the_reference_parameter_layout_and_refuse_cpu_tensors():
+    """E.DenseHead is an nn.Linear(2*hidden, polarities) (bert_amir5.py:573): same state-dict keys and shapes, so a
+    reference checkpoint loads; called with ONE argument it is a plain Linear (works on CPU); the two-argument form and the
+    loss are CUDA kernels only and say so."""
+    import torch
+    import ed_gated_gcn_b200 as E
+    head = E.DenseHead(600, 34)
+    ref = torch.nn.Linear(600, 34)
+    assert {k: tuple(v.shape) for k, v in head.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    head.load_state_dict(ref.state_dict())
+    x = torch.randn(3, 600)
+    assert torch.equal(head(x), ref(x))
+    assert not head.fusable(300)                     # CPU parameters: the block would keep the torch path
+    with pytest.raises(E.EdgError):
+        head(torch.randn(3, 300), torch.randn(3, 300))
+    with pytest.raises(E.EdgError):
+        E.cross_entropy(torch.randn(3, 34), torch.zeros(3, dtype=torch.long))
