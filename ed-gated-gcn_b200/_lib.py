@@ -67,7 +67,7 @@ SIGNATURES = {
     "edg_cast_2d": (c_int, [_P, _L, _I, _I, _P, c_int, _L, c_int, _P]),
     "edg_cast_batch": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "edg_trigger_gather": (c_int, [_P, c_int, _L, _P, _P, _I, _I, _P, _P, _L, c_int, _P]),
-    "edg_trigger_scatter_add": (c_int, [_P, _I, _I, _P, _P, _P, c_int, _L, _P]),
+    "edg_trigger_scatter_add": (c_int, [_P, _P, _I, _I, _I, _P, _P, _P, c_int, _L, _P]),
     "edg_pool_fwd": (c_int, [_P, c_int, _L, _P, _I, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P]),
     "edg_diversity_fwd": (c_int, [_P, _I, _I, _I, _P, _P, _P]),
     "edg_views_bwd": (c_int, [_P, _P, _P, _P, c_int, _L, _I, _I, _I, _P, _P, _P, _L, _P, c_int, _P]),

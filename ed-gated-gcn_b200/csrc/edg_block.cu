@@ -27,9 +27,11 @@ __global__ void trigger_gather_kernel(const T* __restrict__ x, int64_t ldx, cons
   if (act) act[(int64_t)b * ldact + d] = from_f32<T>(lead_sigmoid ? sigmoidf_(v) : v);
 }
 
+// da (optional) plus `n_extra` more [B, D] terms stored one after the other in `extra` (the gate MLPs' input gradients
+// come as one [L, B, D] array): summed here instead of by separate elementwise launches
 template <typename T>
-__global__ void trigger_scatter_add_kernel(const float* __restrict__ da, int B, int D,
-                                           const int32_t* __restrict__ sent_ptr, const int32_t* __restrict__ anchor,
+__global__ void trigger_scatter_add_kernel(const float* __restrict__ da, const float* __restrict__ extra, int n_extra, int B,
+                                           int D, const int32_t* __restrict__ sent_ptr, const int32_t* __restrict__ anchor,
                                            T* __restrict__ dx, int64_t lddx) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = (int)(idx / D);
@@ -37,7 +39,10 @@ __global__ void trigger_scatter_add_kernel(const float* __restrict__ da, int B, 
   const int d = (int)(idx - (int64_t)b * D);
   const int64_t row = (int64_t)sent_ptr[b] + anchor[b];
   T* p = dx + row * lddx + d;
-  *p = from_f32<T>(to_f32(*p) + da[(int64_t)b * D + d]);
+  const int64_t e = (int64_t)b * D + d, BD = (int64_t)B * D;
+  float v = da ? da[e] : 0.f;
+  for (int k = 0; k < n_extra; ++k) v += extra[k * BD + e];
+  *p = from_f32<T>(to_f32(*p) + v);
 }
 
 // ---- gated max-pool views ---------------------------------------------------
@@ -541,15 +546,15 @@ extern "C" int edg_trigger_gather(const void* x, int dtype, int64_t ldx, const i
   return check_launch();
 }
 
-extern "C" int edg_trigger_scatter_add(const float* da, int32_t B, int32_t D, const int32_t* sent_ptr,
-                                       const int32_t* anchor, void* dx, int dtype, int64_t lddx,
+extern "C" int edg_trigger_scatter_add(const float* da, const float* extra, int32_t n_extra, int32_t B, int32_t D,
+                                       const int32_t* sent_ptr, const int32_t* anchor, void* dx, int dtype, int64_t lddx,
                                        edg_stream stream) {
-  if (B < 0 || D <= 0) return EDG_ERR_ARG;
+  if (B < 0 || D <= 0 || n_extra < 0) return EDG_ERR_ARG;
   if (B == 0) return EDG_OK;
-  if (!da || !sent_ptr || !anchor || !dx) return EDG_ERR_ARG;
+  if ((!da && n_extra == 0) || (n_extra > 0 && !extra) || !sent_ptr || !anchor || !dx) return EDG_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   EDG_DISPATCH_T(dtype, trigger_scatter_add_kernel<T><<<blocks_for((int64_t)B * D, 256), 256, 0, s>>>(
-      da, B, D, sent_ptr, anchor, (T*)dx, lddx);)
+      da, extra, n_extra, B, D, sent_ptr, anchor, (T*)dx, lddx);)
   return check_launch();
 }
 

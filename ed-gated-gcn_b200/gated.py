@@ -562,7 +562,7 @@ class _GatedStackFn(torch.autograd.Function):
                         grads_out[o + 2 * (g * pairs + i)] = dW.to(w.dtype)
                         grads_out[o + 2 * (g * pairs + i) + 1] = db.to(b.dtype)
                 grad_hook(grads_out[o:o + 2 * Lyr * pairs])
-                return da_parts.sum(0) if Lyr > 1 else da_parts[0]
+                return ("parts", da_parts)         # [L,B,D], summed where it is consumed (edg_trigger_scatter_add)
             for g in range(Lyr):
                 acts = ctx.gate_saved[g]
                 dz = dz_all[g * B:(g + 1) * B]
@@ -678,14 +678,19 @@ class _GatedStackFn(torch.autograd.Function):
         side.join()
         side_w.join()
         da = ga_head.float() if ga_head is not None else None
+        da_extra = None
+        if isinstance(da_gate, tuple):            # the gate MLPs' input gradients, one [B,D] slab per gate
+            da_extra, da_gate = da_gate[1], None
+            if ctx.ext_aspect:                    # the caller gets d aspect as a tensor: sum them here
+                da_gate, da_extra = (da_extra.sum(0) if da_extra.shape[0] > 1 else da_extra[0]), None
         if da_gate is not None:
             da = da_gate if da is None else da + da_gate
         d_aspect = None
-        if da is not None:
+        if da is not None or da_extra is not None:
             if ctx.ext_aspect:
                 d_aspect = da
             else:
-                ops.trigger_scatter_add(da.contiguous(), graph, anchor, dx)
+                ops.trigger_scatter_add(da, graph, anchor, dx, extra=da_extra)
         grads_out[-2], grads_out[-1] = d_fcw, d_fcb
         if ctx.x_padded:        # hand back the whole [N, pitch] allocation (padding columns are finite)
             dx = dx.as_strided((N, dx.stride(0)), (dx.stride(0), 1))

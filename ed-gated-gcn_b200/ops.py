@@ -47,6 +47,11 @@ def ld(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
 # ---------------------------------------------------------------------------
 def aggregate(x: torch.Tensor, graph, mode: int, out_dtype: Optional[torch.dtype] = None, patch=None) -> torch.Tensor:
     """``patch`` = (patch_arg int32 [B,D], patch_val fp32 [B,D]) from :func:`views_patch`: added to the rows it
@@ -352,10 +357,16 @@ def trigger_gather(x: torch.Tensor, graph, anchor: torch.Tensor, lead_sigmoid: b
     return raw, act
 
 
-def trigger_scatter_add(da: torch.Tensor, graph, anchor: torch.Tensor, dx: torch.Tensor) -> None:
-    B, D = da.shape
-    L.call("edg_trigger_scatter_add", L.ptr(da), B, D, L.ptr(graph.sent_ptr), L.ptr(anchor), L.ptr(dx), L.dt(dx),
-           ld(dx), L.stream())
+def trigger_scatter_add(da: Optional[torch.Tensor], graph, anchor: torch.Tensor, dx: torch.Tensor,
+                        extra: Optional[torch.Tensor] = None) -> None:
+    """``dx[trigger row of b] += da[b] + extra.sum(0)[b]``; ``da`` fp32 ``[B,D]`` or None, ``extra`` fp32 ``[K,B,D]`` or None."""
+    if extra is not None:
+        extra = _f32c(extra)
+    if da is not None:
+        da = _f32c(da)
+    B, D = (da.shape if da is not None else extra.shape[1:])
+    L.call("edg_trigger_scatter_add", L.ptr(da), L.ptr(extra), extra.shape[0] if extra is not None else 0, B, D,
+           L.ptr(graph.sent_ptr), L.ptr(anchor), L.ptr(dx), L.dt(dx), ld(dx), L.stream())
 
 
 def pool_fwd(h: torch.Tensor, graph, gates: torch.Tensor, want_hmax: bool = False):
@@ -460,11 +471,6 @@ def fc_head_bwd(logits, fc_w, fc_b, a, dv, dc, scale: Optional[torch.Tensor] = N
 
 
 DENSE_HEAD_MAX_CLASSES = 64
-
-
-def _f32c(t: torch.Tensor) -> torch.Tensor:
-    t = t.detach()
-    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
 def dense_head_fwd(a: torch.Tensor, p: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

@@ -238,9 +238,10 @@ int edg_cast_batch(int32_t n, const void* const* src, void* const* dst, const in
 int edg_trigger_gather(const void* x, int dtype, int64_t ldx, const int32_t* sent_ptr,
                        const int32_t* anchor, int32_t B, int32_t D, float* raw, void* act,
                        int64_t ldact, int lead_sigmoid, edg_stream stream);
-/* backward of the gather: dx[sent_ptr[b]+anchor[b]] += da[b]  (rows are distinct). */
-int edg_trigger_scatter_add(const float* da, int32_t B, int32_t D, const int32_t* sent_ptr,
-                            const int32_t* anchor, void* dx, int dtype, int64_t lddx,
+/* backward of the gather: dx[sent_ptr[b]+anchor[b]] += da[b] + sum_k extra[k][b]  (rows are distinct).  da fp32 [B,D] or
+ * NULL; extra = n_extra further fp32 [B,D] terms stored one after the other (the gate MLPs' input gradients), or NULL. */
+int edg_trigger_scatter_add(const float* da, const float* extra, int32_t n_extra, int32_t B, int32_t D,
+                            const int32_t* sent_ptr, const int32_t* anchor, void* dx, int dtype, int64_t lddx,
                             edg_stream stream);
 
 /* bert_amir5.py:627-636,640: pooled[v,b,:] = max_t h[t,:]*gates[v,b,:] over the
