@@ -248,6 +248,11 @@ def run_b200(args):
     else:
         logits_fn = dense
         ce_loss = E.cross_entropy                     # nn.CrossEntropyLoss (train.py:96) in two launches
+    # train.py:115-118: loss = CE + gate_weight * xy + kl_weight * kl
+    if args.torch_head or os.environ.get("EDG_BENCH_TORCH_SUM") == "1":      # (env: same-box A/B of E.total_loss)
+        combine = lambda ce, xy, kl: ce + GATE_W * xy + KL_W * kl
+    else:
+        combine = lambda ce, xy, kl: E.total_loss(ce, xy, kl, GATE_W, KL_W)
     head_params = list(dense.parameters())
 
     # ---- device-resident inputs (the `value` number)
@@ -265,7 +270,7 @@ def run_b200(args):
         opt.zero_grad(set_to_none=True)
         x_dev.grad = None
         out = stack(x_dev, graph, anchor, dist_dev, logits_fn, head_params=head_params)
-        loss = ce_loss(out.logits, tgt) + GATE_W * out.xy + KL_W * out.kl
+        loss = combine(ce_loss(out.logits, tgt), out.xy, out.kl)
         loss.backward()
         reducer()
         opt.step()
@@ -291,7 +296,7 @@ def run_b200(args):
         tg = tgt_pin.to(dev, non_blocking=True)
         dd = E.tree_distance(g, an)
         out = stack(xb, g, an, dd, logits_fn, head_params=head_params)
-        loss = ce_loss(out.logits, tg) + GATE_W * out.xy + KL_W * out.kl
+        loss = combine(ce_loss(out.logits, tg), out.xy, out.kl)
         loss.backward()
         reducer()
         opt.step()
@@ -363,7 +368,7 @@ def run_b200(args):
             g = E.build_graph(st["heads"], st["sp"], max_len=max_len, device=dev)
             dd = E.tree_distance(g, st["anchor"])
             out = stack(st["x"], g, st["anchor"], dd, logits_fn, head_params=head_params)
-            loss = ce_loss(out.logits, st["tgt"]) + GATE_W * out.xy + KL_W * out.kl
+            loss = combine(ce_loss(out.logits, st["tgt"]), out.xy, out.kl)
             loss.backward()
             reducer()
             opt.step()

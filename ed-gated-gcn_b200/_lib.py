@@ -51,6 +51,8 @@ SIGNATURES = {
     "edg_cross_entropy_workspace": (_Z, [_I]),
     "edg_cross_entropy_fwd": (c_int, [_P, _L, _P, _I, _I, _L, _P, _P, _P, _Z, _P]),
     "edg_cross_entropy_bwd": (c_int, [_P, _L, _P, _I, _I, _L, _P, _P, _P, _L, _P]),
+    "edg_loss_combine": (c_int, [_P, _P, _P, c_float, c_float, c_float, _P, _P]),
+    "edg_loss_combine_bwd": (c_int, [_P, c_float, c_float, c_float, _P, _P]),
     "edg_set_sm_budget": (c_int, [_I]),
     "edg_split_pitch": (_L, [_I]),
     "edg_split_f16": (c_int, [_P, _L, _I, _I, _P, _L, _P, _P]),

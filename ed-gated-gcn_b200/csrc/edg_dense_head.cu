@@ -259,9 +259,34 @@ ce_bwd_kernel(const float* __restrict__ lg, int64_t ldl, const int64_t* __restri
   for (int c = lane; c < C; c += 32) o[c] = (expf(__ldg(row + c) - m) * inv - (c == t ? 1.f : 0.f)) * k;
 }
 
+// ---- loss = w0 t0 + w1 t1 + w2 t2 on device scalars (train.py:115-118: CE + gate_w xy + kl_w kl) and its backward ----
+__global__ void loss_combine_kernel(const float* __restrict__ t0, const float* __restrict__ t1, const float* __restrict__ t2,
+                                    float w0, float w1, float w2, float* __restrict__ out) {
+  if (threadIdx.x == 0) out[0] = (t0 ? w0 * t0[0] : 0.f) + (t1 ? w1 * t1[0] : 0.f) + (t2 ? w2 * t2[0] : 0.f);
+}
+__global__ void loss_combine_bwd_kernel(const float* __restrict__ g, float w0, float w1, float w2, float* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    const float gg = g ? g[0] : 1.f;
+    out[0] = gg * w0; out[1] = gg * w1; out[2] = gg * w2;
+  }
+}
+
 }  // namespace edg
 
 using namespace edg;
+
+extern "C" int edg_loss_combine(const float* t0, const float* t1, const float* t2, float w0, float w1, float w2, float* out,
+                                edg_stream stream) {
+  if (!out) return EDG_ERR_ARG;
+  loss_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t0, t1, t2, w0, w1, w2, out);
+  return check_launch();
+}
+
+extern "C" int edg_loss_combine_bwd(const float* g, float w0, float w1, float w2, float* out3, edg_stream stream) {
+  if (!out3) return EDG_ERR_ARG;
+  loss_combine_bwd_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g, w0, w1, w2, out3);
+  return check_launch();
+}
 
 extern "C" int edg_dense_head_fwd(const float* a, int64_t lda, const float* p, int64_t ldp, const float* W, int64_t ldw,
                                   const float* bias, int32_t B, int32_t D, int32_t C, float* logits, int64_t ldl,

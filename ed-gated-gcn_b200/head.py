@@ -85,3 +85,36 @@ class CrossEntropyLoss(nn.Module):
 
     def forward(self, logits, target):
         return cross_entropy(logits, target, self.ignore_index)
+
+
+class _TotalLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ce, xy, kl, gate_w, kl_w):
+        def dev_scalar(t):
+            if not torch.is_tensor(t):
+                return None                       # the ungated ablation returns xy = 0.0 (bert_amir5.py:742)
+            t = t.detach()
+            return t if t.dtype == torch.float32 else t.float()
+        terms = [dev_scalar(ce), dev_scalar(xy), dev_scalar(kl)]
+        out = torch.empty((1,), dtype=torch.float32, device=terms[0].device)
+        L.call("edg_loss_combine", L.ptr(terms[0]), L.ptr(terms[1]), L.ptr(terms[2]), 1.0, float(gate_w), float(kl_w),
+               L.ptr(out), L.stream())
+        ctx.w = (1.0, float(gate_w), float(kl_w))
+        ctx.is_t = [t is not None for t in terms]
+        ctx.shapes = [tuple(t.shape) if t is not None else None for t in terms]
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g if (g.dtype == torch.float32 and g.is_cuda) else g.float().cuda()
+        o3 = torch.empty((3,), dtype=torch.float32, device=g.device)
+        L.call("edg_loss_combine_bwd", L.ptr(g.reshape(1)), ctx.w[0], ctx.w[1], ctx.w[2], L.ptr(o3), L.stream())
+        return tuple(o3[i].reshape(ctx.shapes[i]) if ctx.is_t[i] else None for i in range(3)) + (None, None)
+
+
+def total_loss(ce: torch.Tensor, xy, kl, gate_weight: float, kl_weight: float) -> torch.Tensor:
+    """``loss = ce + gate_weight * xy + kl_weight * kl`` (train.py:115-118) in one launch forward and one backward
+    (torch: two multiplies + two adds, and as many again in the backward pass, each a launch on the critical path)."""
+    if not ce.is_cuda:
+        raise L.EdgError("libedgcn takes CUDA tensors only (there is no CPU path)")
+    return _TotalLossFn.apply(ce, xy, kl, gate_weight, kl_weight)

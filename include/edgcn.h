@@ -509,6 +509,12 @@ int edg_cross_entropy_bwd(const float* logits, int64_t ldl, const int64_t* targe
                           int64_t ignore_index, const float* gscale, const float* fwd_out, float* dlogits, int64_t lddl,
                           edg_stream stream);
 
+/* train.py:115-118: loss = t0 w0 + t1 w1 + t2 w2 on device scalars (CE + gate_weight xy + kl_weight kl; a NULL term
+ * counts as zero), and its backward: out3[i] = (*g) w_i (g NULL = 1).  One launch each instead of four / six. */
+int edg_loss_combine(const float* t0, const float* t1, const float* t2, float w0, float w1, float w2, float* out,
+                     edg_stream stream);
+int edg_loss_combine_bwd(const float* g, float w0, float w1, float w2, float* out3, edg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

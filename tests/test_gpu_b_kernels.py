@@ -506,3 +506,21 @@ def test_cross_entropy_matches_torch(B, C):
     l0 = E.cross_entropy(logits, torch.full_like(tgt, -100))
     l0.backward()
     assert float(l0) == 0.0 and float(logits.grad.abs().max()) == 0.0
+
+
+def test_total_loss_matches_the_torch_expression():
+    """train.py:115-118: loss = CE + gate_weight * xy + kl_weight * kl, forward and backward, incl. the ungated xy = 0.0"""
+    import ed_gated_gcn_b200 as E
+    ce = torch.tensor(1.7, device=DEV, requires_grad=True)
+    xy = torch.tensor(0.31, device=DEV, requires_grad=True)
+    kl = torch.tensor(2.9, device=DEV, requires_grad=True)
+    up = torch.tensor(0.5, device=DEV)
+    loss = E.total_loss(ce, xy, kl, 0.01, 0.02)
+    (loss * up).backward()
+    want = 1.7 + 0.01 * 0.31 + 0.02 * 2.9
+    assert abs(float(loss) - want) < 1e-6
+    assert abs(float(ce.grad) - 0.5) < 1e-7 and abs(float(xy.grad) - 0.005) < 1e-8 and abs(float(kl.grad) - 0.01) < 1e-8
+    ce.grad = None
+    loss = E.total_loss(ce, 0.0, kl, 0.01, 0.02)            # BertAmir55NoGate returns xy = 0.0 (a Python float)
+    loss.backward()
+    assert abs(float(loss) - (1.7 + 0.02 * 2.9)) < 1e-6 and float(ce.grad) == 1.0
