@@ -785,8 +785,8 @@ class GatedGCNStack(nn.Module):
             raise L.EdgError(f"expected {self.hidden} feature columns (or the padded pitch), got {x.shape[-1]}")
         from .head import DenseHead
         dense_head = logits_fn if isinstance(logits_fn, DenseHead) and logits_fn.fusable(self.hidden) else None
-        if dense_head is not None:          # its parameters are the head parameters: nothing to declare
-            head_params = [p for p in (dense_head.weight, dense_head.bias) if p is not None]
+        if isinstance(logits_fn, DenseHead):        # its parameters are the head parameters: nothing to declare
+            head_params = [p for p in (logits_fn.weight, logits_fn.bias) if p is not None]
         cfg = dict(graph=graph, cdtype=self.compute_dtype, D=self.hidden, dense_head=dense_head, L=self.n_layers, pairs=pairs, lead=lead,
                    anchor=anchor_index.to(torch.int32).contiguous(), dist=dist, logits_fn=logits_fn,
                    head_params=list(head_params), n_head=len(list(head_params)), grad_enabled=torch.is_grad_enabled(), grad_hook=self.grad_ready_hook, bucket_hook=self.grad_bucket_hook,
