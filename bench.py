@@ -218,6 +218,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     c, batch, x_host, tgt_host = make_workload(args.config, rank)
+    if args.dtype:                       # not the headline: the fp32-parity mode of the same step
+        c["dtype"] = args.dtype
     cd = torch.bfloat16 if c["dtype"] == "bf16" else torch.float32
     if cd == torch.bfloat16:
         # the caller's own classifier head (self.dense, bert_amir5.py:643) is host torch: let cuBLAS use TF32
@@ -580,6 +582,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default=None, choices=["bf16", "f32"],
+                    help="override the configuration's compute mode (f32 = the 1e-5 parity mode; the headline is the config's own)")
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="all-reduce every gradient group from inside the backward pass (GradientAllReducer.hook) instead of "
                          "one coalesced in-place all-reduce after it")
