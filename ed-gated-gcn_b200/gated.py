@@ -257,7 +257,7 @@ class _GatedStackFn(torch.autograd.Function):
         # ---- ungated GCN chain (bert_amir5.py:626, :639; gcn.py:33-45); after layer 1 the gated views of h_1 and
         # the diversity term (:627-638) go to the side stream (behind the gate MLPs) while layers 2.. run here
         h = xr
-        ms, hs = [], []
+        ms, hs, ms_split = [], [], []
         v_pooled = v_arg = v_hmax = None
         hmaxL = None
         xy = torch.zeros((), dtype=torch.float32, device=x.device)
@@ -286,8 +286,19 @@ class _GatedStackFn(torch.autograd.Function):
             for l, (w, b) in enumerate(gcn_p):
                 m = ops.aggregate(h, graph, mode=0)
                 wt = w_t[id(w)]                                                     # [out,in]: K-major B operand
-                h = ops.linear(m, wt, b.detach().float().contiguous() if b is not None else None,
-                               act=L.ACT_RELU if cfg["relu"] else L.ACT_NONE)
+                b32 = b.detach().float().contiguous() if b is not None else None
+                act = L.ACT_RELU if cfg["relu"] else L.ACT_NONE
+                if (cd == torch.float32 and ops.f32_tc(m.shape[0], m.shape[1], wt.shape[0])
+                        and ops.f32_tc(m.shape[0], wt.shape[0], m.shape[1])):
+                    # fp32 mode: the projection reads split operands (ops.SplitRows); the split form of A^ h is also what
+                    # the weight gradient reads, so it is kept INSTEAD of the fp32 rows (same bytes, one split per layer)
+                    m2 = ops.split_rows(m)
+                    h = ops.linear_split(m2, ops.split_rows(wt), b32, act)
+                    ms_split.append((m2.amax, m2.rows, m2.cols))
+                    m = m2.data
+                else:
+                    h = ops.linear(m, wt, b32, act=act)
+                    ms_split.append(None)
                 ms.append(m)
                 hs.append(h)
                 if l == 0 and gated:
@@ -375,7 +386,9 @@ class _GatedStackFn(torch.autograd.Function):
         ctx.hmaxL = hmaxL
         if fused is not None:
             ms = [None] * Lyr                     # never materialised
+            ms_split = [None] * Lyr
             v_arg = v_arg.contiguous() if v_arg is not None else None
+        ctx.ms_split = ms_split
         ctx.save_for_backward(xr, gates, v_pooled, v_arg, p_arg, scores, kl_b, *ms, *hs, *params)
         # arg-max rows (global row ids), like the indices torch.max returns at :635-636/:640
         if v_arg is None:
@@ -665,12 +678,17 @@ class _GatedStackFn(torch.autograd.Function):
                 w, b = params[2 * l], params[2 * l + 1]
                 if cfg["relu"]:
                     dh = ops.as_rows(dh * (hs[l] > 0), cd)
+                msp = ctx.ms_split[l]
+                dh2 = ops.split_rows(dh) if msp is not None else None              # shared by dW and the input gradient
                 with side_w.region():
-                    dW, db = ops.wgrad(ms[l], dh, bias_of=2)
+                    if msp is not None:
+                        dW, db = ops.wgrad_split(ops.SplitRows(ms[l], *msp), dh2, bias_of=2)
+                    else:
+                        dW, db = ops.wgrad(ms[l], dh, bias_of=2)
                     grads_out[2 * l], grads_out[2 * l + 1] = dW.to(w.dtype), db.to(b.dtype)
                     grad_hook(grads_out[2 * l:2 * l + 2])
                 wk = ctx.w_n[l]                                                     # [in,out] = B operand of dh W^T
-                dm = ops.linear(dh, wk, None)
+                dm = ops.linear_split(dh2, ops.split_rows(wk), None) if msp is not None else ops.linear(dh, wk, None)
                 if l == 1 and patch is not None and patch_ev is not None:
                     torch.cuda.current_stream(dev).wait_event(patch_ev)       # the patch arrays come from the side stream
                 dh = ops.aggregate(dm, graph, mode=1, patch=patch if l == 1 else None)
