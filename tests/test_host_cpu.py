@@ -320,3 +320,22 @@ def test_head_and_loss_modules_keep_the_reference_parameter_layout_and_refuse_cp
         head(torch.randn(3, 300), torch.randn(3, 300))
     with pytest.raises(E.EdgError):
         E.cross_entropy(torch.randn(3, 34), torch.zeros(3, dtype=torch.long))
+
+
+def test_host_side_planning_entry_points_of_the_round_2_additions():
+    """No GPU needed: pitches, shape coverage, workspace sizes and the SM budget are host arithmetic."""
+    from ed_gated_gcn_b200 import _lib
+    lib = _lib.load()
+    assert lib.edg_split_pitch(300) == 640 and lib.edg_split_pitch(64) == 128 and lib.edg_split_pitch(65) == 256
+    assert lib.edg_split_pitch(0) == 0
+    # the hi+lo weight slice of the fp32-parity projection has to fit next to two activation stages
+    assert lib.edg_linear_split_ok(300, 300) == 1 and lib.edg_linear_split_ok(768, 768) == 1
+    assert lib.edg_linear_split_ok(300, 2000) == 0          # bias table (kMaxBias) exceeded
+    assert lib.edg_linear_split_ok(8192, 300) == 0          # no N tile of 16 columns fits any more
+    # three products: the hi x hi launch in short chains (more slabs) + two cross-term launches
+    assert lib.edg_wgrad_split_workspace(204800, 300, 300) > 3 * 301 * 300 * 4
+    assert lib.edg_wgrad_split_workspace(0, 300, 300) == 16
+    assert lib.edg_dense_head_bwd_workspace(4096, 300, 34) == 128 * 34 * 601 * 4
+    assert lib.edg_cross_entropy_workspace(4096) == (2 * 512 + 1) * 4
+    prev = lib.edg_set_sm_budget(116)
+    assert prev == 148 and lib.edg_set_sm_budget(1000) == 116 and lib.edg_set_sm_budget(148) == 148
